@@ -1,0 +1,129 @@
+"""Pin the oracle (oracle/) against outputs of the unmodified reference.
+
+tests/golden/*.npz were produced by tools/make_golden.py running /root/reference
+on CPU.  The oracle is a restatement evaluated with the same torch build, so it
+is expected to agree to a few ulp; tolerances are written per check.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import pose, rays, encode, composite, resample, render, image_formation, events
+from tests.cases import CASES, make_inputs, load_golden
+
+TIGHT = dict(rtol=0, atol=2e-6)
+
+
+@pytest.fixture(scope="module")
+def fn():
+    return load_golden("functions")
+
+
+def test_spline_and_linear_match_reference(fn):
+    ts = fn["spline_ts"]
+    for s in range(3):
+        k = fn[f"spline_knots_{s}"]
+        ks = [k[i].reshape(1, 1, 6) for i in range(4)]
+        torch.testing.assert_close(pose.cubic_poses(*ks, ts.clone()), fn[f"spline_cubic_{s}"], **TIGHT)
+        torch.testing.assert_close(pose.linear_poses(ks[0], ks[3], ts.clone()), fn[f"spline_linear_{s}"], **TIGHT)
+
+
+def test_spline_outputs_are_rotations(fn):
+    R = fn["spline_cubic_2"][:, :, :3]
+    eye = torch.eye(3).expand_as(R)
+    torch.testing.assert_close(R @ R.transpose(1, 2), eye, rtol=0, atol=5e-6)
+    torch.testing.assert_close(torch.linalg.det(R), torch.ones(R.shape[0]), rtol=0, atol=5e-6)
+
+
+def test_positional_encoding_matches_reference(fn):
+    assert torch.equal(encode.positional_encoding(fn["pe_x"], 10), fn["pe_pts"])
+    assert torch.equal(encode.positional_encoding(fn["pe_x"], 4), fn["pe_dirs"])
+    assert fn["pe_pts"].shape[1] == 63 and fn["pe_dirs"].shape[1] == 27
+
+
+def test_sample_pdf_matches_reference_including_degenerate_rows(fn):
+    got = resample.inverse_cdf_samples(fn["pdf_bins"], fn["pdf_weights"], fn["pdf_u"])
+    assert torch.equal(got, fn["pdf_samples"])
+
+
+@pytest.mark.parametrize("C", [3, 1])
+def test_raw2output_matches_reference(fn, C):
+    got = composite.composite(fn[f"r2o{C}_raw"], fn[f"r2o{C}_z"], fn[f"r2o{C}_d"], fn[f"r2o{C}_noise"], C)
+    for key in ("rgb_map", "disp_map", "acc_map", "weights", "depth_map", "sigma"):
+        torch.testing.assert_close(got[key], fn[f"r2o{C}_{key}"], rtol=0, atol=0, equal_nan=True)
+
+
+def test_rays_and_ndc_match_reference(fn):
+    H, W, f = 12, 20, 15.0
+    K = torch.tensor([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=torch.float32)
+    idx = torch.arange(H * W)
+    o, d, view = rays.ray_batch(fn["rays_pose"][None], idx, H, W, K, ndc=False)
+    assert torch.equal(d, fn["rays_d"].reshape(-1, 3)) and torch.equal(o, fn["rays_o"].reshape(-1, 3))
+    on, dn, _ = rays.ray_batch(fn["rays_pose"][None], idx, H, W, K, ndc=True)
+    assert torch.equal(on, fn["rays_o_ndc"].reshape(-1, 3)) and torch.equal(dn, fn["rays_d_ndc"].reshape(-1, 3))
+    torch.testing.assert_close(view.norm(dim=-1), torch.ones(H * W), rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_full_iteration_matches_reference(name):
+    """get_pose_* -> two renders -> image formation -> loss (+ gradients) per BASELINE config."""
+    case, gold = CASES[name], load_golden(name)
+    inp = make_inputs(case)
+    knots = inp["knots"].clone().requires_grad_(True)
+    transform = inp["transform"].clone().requires_grad_(True)
+    for p in list(inp["coarse"].values()) + (list(inp["fine"].values()) if inp["fine"] else []):
+        p.requires_grad_(True)
+    poses_evt = pose.poses_from_knots(knots, None, *case.window, 2, case.traj)
+    poses_rgb = pose.poses_from_knots(knots, transform, *case.exposure, case.n_poses, case.traj)
+    torch.testing.assert_close(poses_evt, gold["poses_evt"], **TIGHT)
+    torch.testing.assert_close(poses_rgb, gold["poses_rgb"], **TIGHT)
+    rets = {}
+    for tag, poses, idx, draws in (("evt", poses_evt, inp["idx_evt"], inp["rng_evt"]),
+                                   ("rgb", poses_rgb, inp["idx_rgb"], inp["rng_rgb"])):
+        ret = render.render(inp["coarse"], inp["fine"], poses, idx, case.H, case.W, case.K, draws,
+                            n_samples=case.n_samples, n_importance=case.n_importance,
+                            channels=case.channels, return_intermediates=True)
+        ex = ret.pop("_extra")
+        rets[tag] = ret
+        torch.testing.assert_close(ex["z_coarse"], gold[f"{tag}_z_c"], rtol=0, atol=0)
+        torch.testing.assert_close(ex["raw_coarse"], gold[f"{tag}_raw_c"], rtol=0, atol=5e-6)
+        torch.testing.assert_close(ex["weights_coarse"], gold[f"{tag}_weights_c"], rtol=0, atol=5e-6)
+        if case.n_importance > 0:
+            torch.testing.assert_close(ex["z_fine"], gold[f"{tag}_z_f"], rtol=0, atol=2e-6)
+            torch.testing.assert_close(ex["raw_fine"], gold[f"{tag}_raw_f"], rtol=0, atol=2e-5)
+        expected_keys = {"rgb_map", "disp_map", "acc_map"} | (
+            {"rgb0", "disp0", "acc0", "sigma"} if case.n_importance > 0 else set())
+        assert set(ret) == expected_keys
+        for k, v in ret.items():
+            tol = dict(rtol=1e-4, atol=1e-5) if k.startswith("disp") else dict(rtol=0, atol=1e-5)
+            torch.testing.assert_close(v, gold[f"{tag}_{k}"], equal_nan=True, **tol)
+    ev = inp["events"]
+    win = events.select_window(ev, *case.window)
+    accu = events.accumulate(case.H, case.W, win["x"], win["y"], win["pol"])
+    assert accu.dtype == torch.float64 and torch.equal(accu, gold["events_accu"])
+    if case.n_importance == 0:
+        return
+    loss, parts = image_formation.training_loss(
+        rets["evt"], rets["rgb"], accu, inp["idx_evt"], inp["blur_target"], n_poses=case.n_poses,
+        dataset=case.dataset, channels=case.channels, threshold=case.event_threshold)
+    torch.testing.assert_close(image_formation.blur_mean(rets["rgb"]["rgb_map"], case.n_poses),
+                               gold["blur_rgb_map"], rtol=0, atol=1e-5)
+    torch.testing.assert_close(image_formation.event_log_diff(rets["evt"]["rgb_map"], case.dataset, case.channels),
+                               gold["event_diff_rgb_map"], rtol=0, atol=1e-4)
+    got_parts = torch.stack([parts["event_rgb_map"], parts["event_rgb0"],
+                             parts["blur_rgb_map"] / 1.0, parts["blur_rgb0"] / 1.0]).to(gold["loss_parts"].dtype)
+    torch.testing.assert_close(got_parts, gold["loss_parts"], rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(loss.reshape(1).to(gold["loss"].dtype), gold["loss"], rtol=1e-4, atol=1e-7)
+    loss.backward()
+    torch.testing.assert_close(knots.grad, gold["grad_knots"], rtol=2e-3, atol=1e-6)
+    torch.testing.assert_close(transform.grad, gold["grad_transform"], rtol=2e-3, atol=1e-6)
+    for lvl, params in (("c", inp["coarse"]), ("f", inp["fine"])):
+        norms = torch.stack([p.grad.norm() for p in params.values()])
+        torch.testing.assert_close(norms, gold[f"grad_norms_{lvl}"], rtol=1e-3, atol=1e-8)
+        samples = torch.cat([p.grad.reshape(-1)[::97] for p in params.values()])
+        torch.testing.assert_close(samples, gold[f"grad_samples_{lvl}"], rtol=1e-3, atol=1e-6)
+
+
+def test_work_per_sample_matches_survey():
+    assert oracle.mlp.macs_per_sample(3) == 593_408 and oracle.mlp.macs_per_sample(1) == 593_152
