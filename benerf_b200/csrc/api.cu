@@ -1,0 +1,285 @@
+// C-ABI entry points (include/benerf_b200.h): context, weight cache, render orchestration.
+#include <stdarg.h>
+#include <math.h>
+#include "common.cuh"
+
+namespace bnrf {
+
+char g_create_error[512] = "";
+
+int fail(bnrf_ctx* ctx, int code, const char* fmt, ...) {
+    char* dst = ctx ? ctx->err : g_create_error;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// dst[(k_dst + k) * N + n] = W[n * in_f + k_src + k]   (PyTorch (out,in) -> k-major)
+__global__ void pack_transpose_kernel(const float* __restrict__ W, int out_f, int in_f, int k_src, int k_dst, int k_count,
+                                      int N, float* __restrict__ dst) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= k_count * out_f) return;
+    const int k = idx / out_f, n = idx % out_f;
+    dst[(size_t)(k_dst + k) * N + n] = W[(size_t)n * in_f + k_src + k];
+}
+__global__ void copy_kernel(const float* __restrict__ src, int n, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+int pack_tc_stream(bnrf_ctx*, int net, cudaStream_t);   // mlp_tc.cu
+
+int alloc_net(bnrf_ctx* ctx, int n) {
+    NetParams& np = ctx->net[n];
+    memset(&np, 0, sizeof(np));
+    for (int s = 0; s < 10; ++s) {
+        BNRF_CUDA(ctx, cudaMalloc(&np.wt[s], (size_t)gemm_k(s) * gemm_n(s) * sizeof(float)));
+        BNRF_CUDA(ctx, cudaMalloc(&np.bias[s], gemm_n(s) * sizeof(float)));
+    }
+    BNRF_CUDA(ctx, cudaMalloc(&np.w_alpha, kWidth * sizeof(float)));
+    BNRF_CUDA(ctx, cudaMalloc(&np.b_alpha, sizeof(float)));
+    BNRF_CUDA(ctx, cudaMalloc(&np.w_rgb, 3 * kHalf * sizeof(float)));
+    BNRF_CUDA(ctx, cudaMalloc(&np.b_rgb, 3 * sizeof(float)));
+    BNRF_CUDA(ctx, cudaMalloc(&np.w_dir, kDirCh * kHalf * sizeof(float)));
+    BNRF_CUDA(ctx, cudaMalloc(&np.tc_stream, tc_stream_halfs() * sizeof(__half)));
+    BNRF_CUDA(ctx, cudaMalloc(&np.tc_scale, 16 * sizeof(float)));
+    return BNRF_OK;
+}
+
+void free_net(bnrf_ctx* ctx, int n) {
+    NetParams& np = ctx->net[n];
+    for (int s = 0; s < 10; ++s) { cudaFree(np.wt[s]); cudaFree(np.bias[s]); }
+    cudaFree(np.w_alpha); cudaFree(np.b_alpha); cudaFree(np.w_rgb); cudaFree(np.b_rgb); cudaFree(np.w_dir);
+    cudaFree(np.tc_stream); cudaFree(np.tc_scale);
+    memset(&np, 0, sizeof(np));
+}
+
+int pack_weights(bnrf_ctx* ctx, int n, const float* const* w, const float* const* b, cudaStream_t st) {
+    NetParams& np = ctx->net[n];
+    const int C = ctx->cfg.channels;
+    auto tr = [&](const float* W, int out_f, int in_f, int k_src, int k_dst, int k_count, int N, float* dst) {
+        const int total = k_count * out_f;
+        pack_transpose_kernel<<<(total + 255) / 256, 256, 0, st>>>(W, out_f, in_f, k_src, k_dst, k_count, N, dst);
+    };
+    auto cp = [&](const float* src, int cnt, float* dst) { copy_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(src, cnt, dst); };
+    // GEMM step s <- reference linear: 0-7 pts_linears, 8 feature_linear, 9 views_linears.0 (feature block)
+    for (int s = 0; s < 10; ++s)
+        BNRF_CUDA(ctx, cudaMemsetAsync(np.wt[s], 0, (size_t)gemm_k(s) * gemm_n(s) * sizeof(float), st));
+    tr(w[BNRF_L_PTS0], kWidth, kPtsCh, 0, 0, kPtsCh, kWidth, np.wt[0]);
+    for (int l = 1; l < 8; ++l) {
+        if (l == 5) {   // cat([input_pts, h]) -> [pe64 | h256]  (model/nerf.py:98)
+            tr(w[l], kWidth, kPtsCh + kWidth, 0, 0, kPtsCh, kWidth, np.wt[5]);
+            tr(w[l], kWidth, kPtsCh + kWidth, kPtsCh, kPtsChPad, kWidth, kWidth, np.wt[5]);
+        } else {
+            tr(w[l], kWidth, kWidth, 0, 0, kWidth, kWidth, np.wt[l]);
+        }
+    }
+    tr(w[BNRF_L_FEATURE], kWidth, kWidth, 0, 0, kWidth, kWidth, np.wt[8]);
+    tr(w[BNRF_L_VIEWS], kHalf, kWidth + kDirCh, 0, 0, kWidth, kHalf, np.wt[9]);       // cat([feature, dirs]) (model/nerf.py:103)
+    tr(w[BNRF_L_VIEWS], kHalf, kWidth + kDirCh, kWidth, 0, kDirCh, kHalf, np.w_dir);
+    for (int l = 0; l < 8; ++l) cp(b[l], kWidth, np.bias[l]);
+    cp(b[BNRF_L_FEATURE], kWidth, np.bias[8]);
+    cp(b[BNRF_L_VIEWS], kHalf, np.bias[9]);
+    cp(w[BNRF_L_ALPHA], kWidth, np.w_alpha);
+    cp(b[BNRF_L_ALPHA], 1, np.b_alpha);
+    BNRF_CUDA(ctx, cudaMemsetAsync(np.w_rgb, 0, 3 * kHalf * sizeof(float), st));
+    BNRF_CUDA(ctx, cudaMemsetAsync(np.b_rgb, 0, 3 * sizeof(float), st));
+    cp(w[BNRF_L_RGB], C * kHalf, np.w_rgb);
+    cp(b[BNRF_L_RGB], C, np.b_rgb);
+    BNRF_LAUNCH_CHECK(ctx);
+    int rc = pack_tc_stream(ctx, n, st);
+    if (rc != BNRF_OK) return rc;
+    np.ready = true;
+    return BNRF_OK;
+}
+
+// Workspace carve-up for bnrf_render_forward (all regions 256-byte aligned).
+struct Workspace {
+    float *o, *d, *view, *vb, *z_c, *z_f, *raw, *w_c;
+    size_t bytes;
+};
+static Workspace carve(const bnrf_cfg& c, int64_t n, void* base) {
+    Workspace w;
+    size_t off = 0;
+    auto take = [&](size_t floats) {
+        float* p = base ? reinterpret_cast<float*>(static_cast<char*>(base) + off) : nullptr;
+        off += (floats * sizeof(float) + 255) / 256 * 256;
+        return p;
+    };
+    const int Sc = c.n_samples, Sf = c.n_samples + c.n_importance, Smax = Sf;
+    w.o = take(n * 3); w.d = take(n * 3); w.view = take(n * 3);
+    w.vb = take(n * kHalf);
+    w.z_c = take(n * Sc);
+    w.z_f = take(c.n_importance > 0 ? n * Sf : 0);
+    w.raw = take(n * Smax * (c.channels + 1));
+    w.w_c = take(n * Sc);
+    w.bytes = off;
+    return w;
+}
+
+static int run_mlp(bnrf_ctx* ctx, int net, const float* o, const float* d, const float* vb, const float* z, int64_t n,
+                   int S, float* raw, cudaStream_t st) {
+    if (!ctx->net[net].ready) return fail(ctx, BNRF_ERR_STATE, "weights of network %d not set (bnrf_set_weights)", net);
+    if (ctx->cfg.mlp_mode == BNRF_MLP_SIMT_FP32) return launch_mlp_simt(ctx, net, o, d, vb, z, n, S, raw, st);
+    return launch_mlp_tc(ctx, net, o, d, vb, z, n, S, raw, st);
+}
+
+}  // namespace bnrf
+
+using namespace bnrf;
+
+extern "C" {
+
+int bnrf_abi_version(void) { return BNRF_ABI_VERSION; }
+
+const char* bnrf_last_error(const bnrf_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
+
+int bnrf_create(bnrf_ctx** out, int device, const bnrf_cfg* cfg) {
+    if (!out || !cfg) return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: null argument");
+    *out = nullptr;
+    if (cfg->n_samples < 3 || cfg->n_importance < 0 || cfg->n_samples + cfg->n_importance > kMaxSamples)
+        return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: need 3 <= n_samples and n_samples + n_importance <= %d", kMaxSamples);
+    if (cfg->channels != 1 && cfg->channels != 3) return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: channels must be 1 or 3");
+    if (cfg->mlp_mode != BNRF_MLP_TC_FP16X2 && cfg->mlp_mode != BNRF_MLP_SIMT_FP32)
+        return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: unknown mlp_mode %d", cfg->mlp_mode);
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+        return fail(nullptr, BNRF_ERR_DEVICE, "bnrf_create: CUDA device %d not available (%d visible); there is no CPU path", device, count);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+        return fail(nullptr, BNRF_ERR_DEVICE, "bnrf_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    bnrf_ctx* ctx = new bnrf_ctx();
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    ctx->cfg = *cfg;
+    ctx->sm_count = prop.multiProcessorCount;
+    auto bail = [&](int rc) { strncpy(g_create_error, ctx->err, 511); bnrf_destroy(ctx); return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(fail(ctx, BNRF_ERR_CUDA, "cudaSetDevice failed"));
+    int rc;
+    for (int n = 0; n < 2; ++n)
+        if ((rc = alloc_net(ctx, n)) != BNRF_OK) return bail(rc);
+    if (cudaMalloc(&ctx->t_vals, kMaxSamples * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&ctx->tile_counter, 64 * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&ctx->err_flag, sizeof(unsigned int)) != cudaSuccess)
+        return bail(fail(ctx, BNRF_ERR_CUDA, "cudaMalloc failed"));
+    cudaMemset(ctx->tile_counter, 0, 64 * sizeof(int));
+    cudaMemset(ctx->err_flag, 0, sizeof(unsigned int));
+    // default sampling grid = torch.linspace(0, 1, S) as the CUDA kernel of the reference's device computes it:
+    // start + step*i below the midpoint, end - step*(S-1-i) above, single rounding (fma).
+    const int S = cfg->n_samples;
+    float host[kMaxSamples];
+    const float step = 1.0f / (float)(S - 1);
+    for (int i = 0; i < S; ++i) host[i] = (i < S / 2) ? fmaf(step, (float)i, 0.0f) : fmaf(-step, (float)(S - i - 1), 1.0f);
+    if (cudaMemcpy(ctx->t_vals, host, S * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+        return bail(fail(ctx, BNRF_ERR_CUDA, "cudaMemcpy failed"));
+    *out = ctx;
+    return BNRF_OK;
+}
+
+void bnrf_destroy(bnrf_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (int n = 0; n < 2; ++n) free_net(ctx, n);
+    cudaFree(ctx->t_vals); cudaFree(ctx->tile_counter); cudaFree(ctx->err_flag);
+    delete ctx;
+}
+
+int bnrf_set_sample_grid(bnrf_ctx* ctx, const float* t_vals_host, int S, void* stream) {
+    if (!ctx || !t_vals_host || S != ctx->cfg.n_samples) return fail(ctx, BNRF_ERR_ARG, "set_sample_grid: S must equal cfg.n_samples");
+    BNRF_CUDA(ctx, cudaMemcpyAsync(ctx->t_vals, t_vals_host, S * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    BNRF_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));   // the host buffer is borrowed only for the call
+    return BNRF_OK;
+}
+
+int bnrf_set_weights(bnrf_ctx* ctx, int net, const float* const* weights, const float* const* biases, void* stream) {
+    if (!ctx || !weights || !biases || net < 0 || net > 1) return fail(ctx, BNRF_ERR_ARG, "set_weights: bad argument");
+    for (int i = 0; i < BNRF_NUM_LINEARS; ++i)
+        if (!weights[i] || !biases[i]) return fail(ctx, BNRF_ERR_ARG, "set_weights: linear %d is null", i);
+    return pack_weights(ctx, net, weights, biases, (cudaStream_t)stream);
+}
+
+int bnrf_spline_poses(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts, int P, int traj,
+                      float* poses_out, void* stream) {
+    if (!ctx) return BNRF_ERR_ARG;
+    return launch_spline(ctx, knots, transform, ts, P, traj, poses_out, (cudaStream_t)stream);
+}
+
+size_t bnrf_workspace_bytes(const bnrf_ctx* ctx, int64_t n_rays) {
+    if (!ctx || n_rays <= 0) return 0;
+    return carve(ctx->cfg, n_rays, nullptr).bytes;
+}
+
+int bnrf_render_forward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W,
+                        const float* K, const float* remap, const bnrf_rng* rng, const bnrf_outputs* out,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    if (!ctx) return BNRF_ERR_ARG;
+    if (!poses || !ray_idx || !K || !out || !workspace || P <= 0 || R <= 0) return fail(ctx, BNRF_ERR_ARG, "render_forward: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bnrf_cfg& c = ctx->cfg;
+    const int64_t n = (int64_t)P * R;
+    Workspace w = carve(c, n, workspace);
+    if (workspace_bytes < w.bytes) return fail(ctx, BNRF_ERR_STATE, "render_forward: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
+    bnrf_rng r = rng ? *rng : bnrf_rng{};
+    const bool fine = c.n_importance > 0;
+    const int Sc = c.n_samples, Sf = c.n_samples + c.n_importance;
+    int rc;
+    if ((rc = launch_rays(ctx, poses, ray_idx, P, R, H, W, K, remap, w.o, w.d, w.view, st))) return rc;
+    if ((rc = launch_stratified(ctx, r.t_rand, &r, n, Sc, w.z_c, st))) return rc;
+    if ((rc = launch_viewbias(ctx, 0, w.view, n, w.vb, st))) return rc;
+    if ((rc = run_mlp(ctx, 0, w.o, w.d, w.vb, w.z_c, n, Sc, w.raw, st))) return rc;
+    // coarse composite: outputs go to rgb0/disp0/acc0 when a fine pass follows (model/nerf.py:319-343)
+    if ((rc = launch_composite(ctx, w.raw, w.z_c, w.d, r.noise_c, &r, kStreamNoiseC, n, Sc,
+                               fine ? out->rgb0 : out->rgb_map, fine ? out->disp0 : out->disp_map,
+                               fine ? out->acc0 : out->acc_map, w.w_c, fine ? nullptr : out->depth_map,
+                               fine ? nullptr : out->sigma, st))) return rc;
+    if (!fine) return BNRF_OK;
+    if ((rc = launch_resample(ctx, w.z_c, w.w_c, r.u, &r, n, Sc, c.n_importance, w.z_f, st))) return rc;
+    if ((rc = launch_viewbias(ctx, 1, w.view, n, w.vb, st))) return rc;
+    if ((rc = run_mlp(ctx, 1, w.o, w.d, w.vb, w.z_f, n, Sf, w.raw, st))) return rc;
+    return launch_composite(ctx, w.raw, w.z_f, w.d, r.noise_f, &r, kStreamNoiseF, n, Sf, out->rgb_map, out->disp_map,
+                            out->acc_map, nullptr, out->depth_map, out->sigma, st);
+}
+
+int bnrf_op_rays(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W, const float* K,
+                 const float* remap, float* rays_o, float* rays_d, float* viewdirs, void* stream) {
+    if (!ctx) return BNRF_ERR_ARG;
+    return launch_rays(ctx, poses, ray_idx, P, R, H, W, K, remap, rays_o, rays_d, viewdirs, (cudaStream_t)stream);
+}
+
+int bnrf_op_stratified(bnrf_ctx* ctx, const float* t_rand, int64_t n_rays, int S, float* z, void* stream) {
+    if (!ctx || !t_rand) return fail(ctx, BNRF_ERR_ARG, "op_stratified: bad argument");
+    return launch_stratified(ctx, t_rand, nullptr, n_rays, S, z, (cudaStream_t)stream);
+}
+
+int bnrf_op_mlp(bnrf_ctx* ctx, int net, const float* rays_o, const float* rays_d, const float* viewdirs, const float* z,
+                int64_t n_rays, int S, float* raw, void* stream) {
+    if (!ctx) return BNRF_ERR_ARG;
+    if (!rays_o || !rays_d || !viewdirs || !z || !raw || n_rays <= 0 || S <= 0 || net < 0 || net > 1)
+        return fail(ctx, BNRF_ERR_ARG, "op_mlp: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* vb = nullptr;                      // operator-level call: scratch for the per-ray view bias
+    BNRF_CUDA(ctx, cudaMallocAsync(&vb, (size_t)n_rays * kHalf * sizeof(float), st));
+    int rc = ctx->net[net].ready ? launch_viewbias(ctx, net, viewdirs, n_rays, vb, st)
+                                 : fail(ctx, BNRF_ERR_STATE, "weights of network %d not set", net);
+    if (rc == BNRF_OK) rc = run_mlp(ctx, net, rays_o, rays_d, vb, z, n_rays, S, raw, st);
+    cudaFreeAsync(vb, st);
+    return rc;
+}
+
+int bnrf_op_composite(bnrf_ctx* ctx, const float* raw, const float* z, const float* rays_d, const float* noise,
+                      int64_t n_rays, int S, float* rgb_map, float* disp_map, float* acc_map, float* weights,
+                      float* depth_map, float* sigma, void* stream) {
+    if (!ctx || !noise) return fail(ctx, BNRF_ERR_ARG, "op_composite: bad argument");
+    return launch_composite(ctx, raw, z, rays_d, noise, nullptr, 0, n_rays, S, rgb_map, disp_map, acc_map, weights,
+                            depth_map, sigma, (cudaStream_t)stream);
+}
+
+int bnrf_op_resample(bnrf_ctx* ctx, const float* z_coarse, const float* weights, const float* u, int64_t n_rays, int S,
+                     int K, float* z_fine, void* stream) {
+    if (!ctx || !u) return fail(ctx, BNRF_ERR_ARG, "op_resample: bad argument");
+    return launch_resample(ctx, z_coarse, weights, u, nullptr, n_rays, S, K, z_fine, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// Shared declarations of the benerf_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/benerf_b200.h"
+
+namespace bnrf {
+
+constexpr int kWidth = 256;        // hidden width W          (model/optimize.py:9)
+constexpr int kHalf = 128;         // view-branch width W/2   (model/nerf.py:58)
+constexpr int kPtsFreqs = 10;      // multires                (config.py:89)
+constexpr int kDirFreqs = 4;       // multires_views          (config.py:91)
+constexpr int kPtsCh = 63;         // 3 + 3*2*10
+constexpr int kPtsChPad = 64;
+constexpr int kDirCh = 27;         // 3 + 3*2*4
+constexpr int kMaxSamples = 512;   // S_c + N_i limit of the per-ray warp kernels
+constexpr int kNumGemmSteps = 10;  // L0..L7, feature, views
+
+// ---- packed parameters of one network (private cache inside the context) -------------
+struct NetParams {
+    // fp32 "k-major" copies used by the SIMT path and by every epilogue:
+    float* wt[10];        // W^T [K_pad][N] for the 10 GEMM steps (L5 reordered to [pe64 | h256])
+    float* bias[10];      // [N]
+    float* w_alpha;       // [256]
+    float* b_alpha;       // [1]
+    float* w_rgb;         // [3][128] (rows >= C are zero)
+    float* b_rgb;         // [3]
+    float* w_dir;         // [27][128]  view-direction block of views_linears.0, transposed
+    // tensor-core stream: fp16 hi/lo tiles in the SW128 K-major shared-memory image,
+    // in the exact order the TMA producer consumes them (mlp_tc.cu).
+    __half* tc_stream;
+    float* tc_scale;      // [10] 2^-s per GEMM step undoing the fp16 weight pre-scale
+    bool ready;
+};
+
+inline int gemm_k(int step) { return step == 0 ? 64 : (step == 5 ? 320 : 256); }
+inline int gemm_n(int step) { return step == 9 ? 128 : 256; }
+
+}  // namespace bnrf
+
+struct bnrf_ctx {
+    int device;
+    int sm_count;
+    bnrf_cfg cfg;
+    bnrf::NetParams net[2];
+    float* t_vals;            // device [n_samples] sampling grid (linspace(0,1,S) by default)
+    int* tile_counter;        // device scratch for the persistent tile scheduler
+    unsigned int* err_flag;   // device: set by kernels on watchdog timeout
+    char err[512];
+};
+
+namespace bnrf {
+
+extern char g_create_error[512];
+
+int fail(bnrf_ctx* ctx, int code, const char* fmt, ...);
+
+#define BNRF_CUDA(ctx, expr)                                                              \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess)                                                           \
+            return bnrf::fail((ctx), BNRF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,       \
+                              cudaGetErrorString(e__), __FILE__, __LINE__);               \
+    } while (0)
+
+#define BNRF_LAUNCH_CHECK(ctx) BNRF_CUDA(ctx, cudaGetLastError())
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- Philox4x32-10 counter RNG (production mode; parity mode reads tensors) ------------
+struct Philox {
+    __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    }
+    // counter = (ray lo, ray hi, sample, stream id); key = seed
+    __device__ static inline void draw(uint64_t seed, uint64_t offset, uint64_t ray, uint32_t sample,
+                                       uint32_t stream, uint32_t (&out)[4]) {
+        uint32_t c[4] = {(uint32_t)ray, (uint32_t)(ray >> 32), sample, stream ^ (uint32_t)(offset * 0x9E3779B9u)};
+        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            round(c, k0, k1);
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+        out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+    }
+    __device__ static inline float uniform(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }  // [0,1)
+    __device__ static inline float normal(uint32_t a, uint32_t b) {
+        const float u1 = ((float)(a >> 8) + 1.0f) * (1.0f / 16777216.0f);                                   // (0,1]
+        const float u2 = uniform(b);
+        return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+    }
+};
+enum : uint32_t { kStreamTRand = 1, kStreamNoiseC = 2, kStreamU = 3, kStreamNoiseF = 4 };
+
+// ---- launchers implemented in the individual .cu files ---------------------------------
+int launch_spline(bnrf_ctx*, const float* knots, const float* transform, const float* ts, int P, int traj,
+                  float* poses, cudaStream_t);
+int launch_rays(bnrf_ctx*, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W, const float* K,
+                const float* remap, float* o, float* d, float* view, cudaStream_t);
+int launch_stratified(bnrf_ctx*, const float* t_rand, const bnrf_rng* rng, int64_t n, int S, float* z, cudaStream_t);
+int launch_viewbias(bnrf_ctx*, int net, const float* view, int64_t n, float* vb, cudaStream_t);
+int launch_mlp_simt(bnrf_ctx*, int net, const float* o, const float* d, const float* vb, const float* z,
+                    int64_t n, int S, float* raw, cudaStream_t);
+int launch_mlp_tc(bnrf_ctx*, int net, const float* o, const float* d, const float* vb, const float* z,
+                  int64_t n, int S, float* raw, cudaStream_t);
+int launch_composite(bnrf_ctx*, const float* raw, const float* z, const float* d, const float* noise,
+                     const bnrf_rng* rng, uint32_t stream_id, int64_t n, int S, float* rgb, float* disp, float* acc,
+                     float* weights, float* depth, float* sigma, cudaStream_t);
+int launch_resample(bnrf_ctx*, const float* zc, const float* w, const float* u, const bnrf_rng* rng, int64_t n,
+                    int S, int K, float* zf, cudaStream_t);
+int pack_weights(bnrf_ctx*, int net, const float* const* w, const float* const* b, cudaStream_t);
+int alloc_net(bnrf_ctx*, int net);
+void free_net(bnrf_ctx*, int net);
+size_t tc_stream_halfs();
+
+}  // namespace bnrf

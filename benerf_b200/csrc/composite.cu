@@ -1,0 +1,241 @@
+// K6/K7: alpha compositing and inverse-CDF resampling, one warp per ray.
+//
+// composite_kernel replaces NeRF.raw2output (model/nerf.py:118-148): ~25 ATen launches over
+// [N,S] temporaries become one pass in which each lane owns S/32 consecutive samples and the
+// transmittance is an exclusive warp prefix-product (shuffle scan).
+// resample_kernel replaces sample_pdf (run_nerf_helpers.py:74-115) and the concat + sort of
+// model/nerf.py:322-326: pdf/cdf scan, binary search (searchsorted right=True), lerp, and a
+// shared-memory bitonic sort of the merged depths.
+//
+// torch's CPU cumsum/cumprod accumulate fp32 inputs in double and round each prefix to float
+// (ATen ReduceOps cumsum_cpu_kernel, acc_type<float,false> = double); both scans here do the
+// same, which keeps weights and cdf within an ulp of the reference whatever the scan order.
+#include "common.cuh"
+
+namespace bnrf {
+
+constexpr int kWarpsPerBlock = 4;
+
+__device__ inline double warp_excl_scan_mul(double v, int lane, double& total) {
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc *= t;
+    }
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    double ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    return lane == 0 ? 1.0 : ex;
+}
+__device__ inline double warp_excl_scan_add(double v, int lane, double& total) {
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    double ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    return lane == 0 ? 0.0 : ex;
+}
+__device__ inline double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// MAXK = ceil(S/32) upper bound; lane owns samples [lane*K, lane*K+K) so the scan is order preserving.
+template <int C>
+__global__ void composite_kernel(const float* __restrict__ raw, const float* __restrict__ z,
+                                 const float* __restrict__ rays_d, const float* __restrict__ noise, bnrf_rng rng,
+                                 uint32_t stream_id, int64_t n_rays, int S, float* __restrict__ rgb_map,
+                                 float* __restrict__ disp_map, float* __restrict__ acc_map, float* __restrict__ weights,
+                                 float* __restrict__ depth_map, float* __restrict__ sigma) {
+    const int lane = threadIdx.x % 32;
+    const int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + threadIdx.x / 32;
+    if (ray >= n_rays) return;
+    const int K = (S + 31) / 32;
+    const float* rd = rays_d + ray * 3;
+    // post-NDC direction norm (model/nerf.py:124)
+    const float dn = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(rd[0], rd[0]), __fmul_rn(rd[1], rd[1])), __fmul_rn(rd[2], rd[2])));
+    const float* zr = z + ray * S;
+    const float* rr = raw + ray * S * (C + 1);
+    double trans_local = 1.0;            // product of (1 - alpha + 1e-10) over this lane's samples
+    double s_rgb[3] = {0, 0, 0}, s_depth = 0, s_acc = 0;
+    // pass 1: per-lane product
+    constexpr int MAXK = kMaxSamples / 32;
+    float alpha[MAXK];
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        const int s = lane * K + k;
+        float a = 0.0f;
+        if (s < S) {
+            const float zi = zr[s];
+            float dist = (s + 1 < S) ? __fsub_rn(zr[s + 1], zi) : 1e10f;
+            dist = __fmul_rn(dist, dn);
+            float nz;
+            if (noise) {
+                nz = noise[ray * S + s];
+            } else {
+                uint32_t w[4];
+                Philox::draw(rng.seed, rng.offset, (uint64_t)ray, (uint32_t)s, stream_id, w);
+                nz = Philox::normal(w[0], w[1]);
+            }
+            const float dens = fmaxf(__fadd_rn(rr[s * (C + 1) + C], nz), 0.0f);     // relu(sigma_raw + noise)
+            if (sigma) sigma[ray * S + s] = dens;
+            a = __fsub_rn(1.0f, expf(__fmul_rn(-dens, dist)));
+            trans_local *= (double)__fadd_rn(__fsub_rn(1.0f, a), 1e-10f);
+        }
+        alpha[k] = a;
+    }
+    double total;
+    double t_run = warp_excl_scan_mul(trans_local, lane, total);   // transmittance before this lane's first sample
+    // pass 2: weights and the three reductions
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        const int s = lane * K + k;
+        if (s < S) {
+            const float a = alpha[k];
+            const float T = (float)t_run;                 // cumprod rounds every prefix to fp32
+            const float w = __fmul_rn(a, T);
+            if (weights) weights[ray * S + s] = w;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float col = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-rr[s * (C + 1) + c])));   // sigmoid
+                s_rgb[c] += (double)__fmul_rn(w, col);
+            }
+            s_depth += (double)__fmul_rn(w, zr[s]);
+            s_acc += (double)w;
+            t_run *= (double)__fadd_rn(__fsub_rn(1.0f, a), 1e-10f);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) s_rgb[c] = warp_sum(s_rgb[c]);
+    s_depth = warp_sum(s_depth);
+    s_acc = warp_sum(s_acc);
+    if (lane == 0) {
+        const float depth = (float)s_depth, acc = (float)s_acc;
+        if (rgb_map)
+            for (int c = 0; c < C; ++c) rgb_map[ray * C + c] = (float)s_rgb[c];
+        if (depth_map) depth_map[ray] = depth;
+        if (acc_map) acc_map[ray] = acc;
+        if (disp_map) {                                   // 1 / max(1e-10, depth / acc); NaN when acc == 0 (Q14)
+            const float r = __fdiv_rn(depth, acc);
+            const float m = (r != r) ? r : fmaxf(1e-10f, r);
+            disp_map[ray] = __fdiv_rn(1.0f, m);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// resample: S coarse depths + weights -> K new depths by inverse CDF over the S-1 mid-points
+// (S-2 bins, weights[1:-1]), then sort(concat).  Per warp shared memory: cdf[S-1], bins[S-1],
+// sort buffer of next_pow2(S+K).
+__global__ void resample_kernel(const float* __restrict__ z_c, const float* __restrict__ w_c,
+                                const float* __restrict__ u_in, bnrf_rng rng, int64_t n_rays, int S, int K,
+                                int sort_n, float* __restrict__ z_f) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+    const int per_warp = 2 * S + sort_n;
+    float* cdf = smem + warp * per_warp;      // [S-1]
+    float* bins = cdf + S;                    // [S-1]
+    float* buf = bins + S;                    // [sort_n]
+    if (ray >= n_rays) return;
+    const float* zr = z_c + ray * S;
+    const float* wr = w_c + ray * S;
+    const int nb = S - 2;                     // number of pdf bins
+    // bins = mid-points of consecutive coarse depths (model/nerf.py:321)
+    for (int i = lane; i < S - 1; i += 32) bins[i] = __fmul_rn(0.5f, __fadd_rn(zr[i + 1], zr[i]));
+    // weights + 1e-5, their sum (double), pdf, inclusive scan in double rounded per prefix
+    const int per = (nb + 31) / 32;
+    double local = 0.0;
+    for (int k = 0; k < per; ++k) {
+        const int i = lane * per + k;
+        if (i < nb) local += (double)__fadd_rn(wr[i + 1], 1e-5f);
+    }
+    const float wsum = (float)warp_sum(local);
+    double run = 0.0, tot;
+    double pre_local = 0.0;
+    for (int k = 0; k < per; ++k) {
+        const int i = lane * per + k;
+        if (i < nb) pre_local += (double)__fdiv_rn(__fadd_rn(wr[i + 1], 1e-5f), wsum);
+    }
+    run = warp_excl_scan_add(pre_local, lane, tot);
+    if (lane == 0) cdf[0] = 0.0f;
+    for (int k = 0; k < per; ++k) {
+        const int i = lane * per + k;
+        if (i < nb) {
+            run += (double)__fdiv_rn(__fadd_rn(wr[i + 1], 1e-5f), wsum);
+            cdf[i + 1] = (float)run;
+        }
+    }
+    for (int i = lane; i < S; i += 32) buf[i] = zr[i];
+    for (int i = S + K + lane; i < sort_n; i += 32) buf[i] = __int_as_float(0x7f800000);   // +inf padding
+    __syncwarp();
+    const int nc = S - 1;                     // cdf / bins length
+    for (int j = lane; j < K; j += 32) {
+        float u;
+        if (u_in) {
+            u = u_in[ray * K + j];
+        } else {
+            uint32_t w[4];
+            Philox::draw(rng.seed, rng.offset, (uint64_t)ray, (uint32_t)j, kStreamU, w);
+            u = Philox::uniform(w[0]);
+        }
+        // searchsorted(cdf, u, right=True): first index with cdf[idx] > u
+        int lo = 0, hi = nc;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+        }
+        const int below = max(lo - 1, 0), above = min(lo, nc - 1);
+        float denom = __fsub_rn(cdf[above], cdf[below]);
+        if (denom < 1e-5f) denom = 1.0f;
+        const float t = __fdiv_rn(__fsub_rn(u, cdf[below]), denom);
+        buf[S + j] = __fadd_rn(bins[below], __fmul_rn(t, __fsub_rn(bins[above], bins[below])));
+    }
+    __syncwarp();
+    // bitonic sort of buf[0, sort_n)
+    for (int size = 2; size <= sort_n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = lane; t < sort_n / 2; t += 32) {
+                const int i = 2 * t - (t & (stride - 1));     // lower index of the pair
+                const int j = i + stride;
+                const bool up = ((i & size) == 0);
+                const float a = buf[i], b = buf[j];
+                if ((a > b) == up) { buf[i] = b; buf[j] = a; }
+            }
+            __syncwarp();
+        }
+    }
+    for (int i = lane; i < S + K; i += 32) z_f[ray * (S + K) + i] = buf[i];
+}
+
+int launch_composite(bnrf_ctx* ctx, const float* raw, const float* z, const float* d, const float* noise,
+                     const bnrf_rng* rng, uint32_t stream_id, int64_t n, int S, float* rgb, float* disp, float* acc,
+                     float* weights, float* depth, float* sigma, cudaStream_t st) {
+    if (!raw || !z || !d || n <= 0 || S < 2 || S > kMaxSamples) return fail(ctx, BNRF_ERR_ARG, "composite: bad argument (2 <= S <= %d)", kMaxSamples);
+    bnrf_rng r = rng ? *rng : bnrf_rng{};
+    const unsigned grid = (unsigned)ceil_div(n, kWarpsPerBlock);
+    if (ctx->cfg.channels == 3)
+        composite_kernel<3><<<grid, 32 * kWarpsPerBlock, 0, st>>>(raw, z, d, noise, r, stream_id, n, S, rgb, disp, acc, weights, depth, sigma);
+    else
+        composite_kernel<1><<<grid, 32 * kWarpsPerBlock, 0, st>>>(raw, z, d, noise, r, stream_id, n, S, rgb, disp, acc, weights, depth, sigma);
+    BNRF_LAUNCH_CHECK(ctx);
+    return BNRF_OK;
+}
+
+int launch_resample(bnrf_ctx* ctx, const float* zc, const float* w, const float* u, const bnrf_rng* rng, int64_t n,
+                    int S, int K, float* zf, cudaStream_t st) {
+    if (!zc || !w || !zf || n <= 0 || S < 3 || K < 1 || S + K > kMaxSamples) return fail(ctx, BNRF_ERR_ARG, "resample: bad argument (S >= 3, S + K <= %d)", kMaxSamples);
+    int sort_n = 1;
+    while (sort_n < S + K) sort_n <<= 1;
+    bnrf_rng r = rng ? *rng : bnrf_rng{};
+    const size_t smem = (size_t)kWarpsPerBlock * (2 * S + sort_n) * sizeof(float);
+    resample_kernel<<<(unsigned)ceil_div(n, kWarpsPerBlock), 32 * kWarpsPerBlock, smem, st>>>(zc, w, u, r, n, S, K, sort_n, zf);
+    BNRF_LAUNCH_CHECK(ctx);
+    return BNRF_OK;
+}
+
+}  // namespace bnrf

@@ -1,0 +1,550 @@
+// K4/K5: positional encoding + the 8x256 NeRF MLP on tcgen05 tensor cores (sm_100a).
+//
+// One persistent CTA per SM processes tiles of 128 samples (rows).  The hidden state of a tile
+// never leaves the SM: accumulators live in TMEM (2 x 256 fp32 columns, ping-pong between
+// consecutive layers), the A operand of the next layer is written by the epilogue warps
+// straight into shared memory in the canonical SWIZZLE_128B K-major layout, and the weights
+// stream through a shared-memory ring filled by the TMA bulk-copy engine (cp.async.bulk)
+// from an L2-resident, pre-swizzled image built once per optimiser step.
+//
+// Precision: the reference is fp32 (SGEMM).  A single 16-bit tensor-core pass misses the 1e-4
+// parity bound (hard part 1), so every operand is split x = hi + lo into two fp16
+// values and each K=16 slice issues three MMAs, hi*hi + lo*hi + hi*lo, accumulated in fp32 in
+// TMEM (the lo*lo term is below 2^-22 relative).  Weights are pre-scaled by a per-layer power
+// of two so that their lo halves stay in the fp16 normal range; the epilogue undoes it.
+//
+// Warp roles (384 threads):
+//   warp 0      TMA producer: weight tiles -> smem ring (mbarrier complete_tx)
+//   warp 1      MMA issuer: one thread issues tcgen05.mma, commits to mbarriers; owns TMEM alloc
+//   warps 4-7   epilogue: tcgen05.ld -> scale/bias/ReLU -> fp16 hi/lo -> next layer's A tile;
+//               sigma head (256->1) and rgb head (128->C) as fp32 FFMA on the way through
+//   warps 8-11  front end: pts = o + d*z, sin/cos encoding -> A tile of layer 0 / skip layer,
+//               one tile ahead of the MMA
+// Layer boundaries are pipelined per 64-column K-block: the MMA of layer l+1 starts on K-block
+// 0 as soon as the epilogue of layer l has produced it, while the epilogue continues.
+//
+// Replaces model/embedder.py:9-34 + model/nerf.py:67-116 (12 cuBLAS SGEMMs + ~40 elementwise
+// launches per network call, every activation through HBM).
+#include "common.cuh"
+
+namespace bnrf {
+namespace tc {
+
+constexpr int TILE_M = 128;
+constexpr int NUM_THREADS = 384;
+constexpr int NS = 2;                              // weight ring depth
+constexpr uint32_t STAGE_BYTES = 32768;            // one [256 x 64] fp16 SW128 tile
+constexpr uint32_t KBLOCK_BYTES = 16384;           // one [128 x 64] fp16 SW128 A tile
+constexpr uint32_t OFF_A_HI = 0;
+constexpr uint32_t OFF_A_LO = 4 * KBLOCK_BYTES;
+constexpr uint32_t OFF_PE_HI = 8 * KBLOCK_BYTES;
+constexpr uint32_t OFF_PE_LO = 9 * KBLOCK_BYTES;
+constexpr uint32_t OFF_W = 10 * KBLOCK_BYTES;
+constexpr uint32_t OFF_BAR = OFF_W + NS * STAGE_BYTES;
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
+constexpr int STAGES_PER_TILE = 76;                // 38 K-blocks x (hi, lo)
+constexpr int N256_STAGES = 68;
+constexpr uint32_t TMEM_COLS = 512;
+
+// barrier slots (8 bytes each) inside the barrier block
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = BAR_W_FULL + NS, BAR_PE_FULL = BAR_W_EMPTY + NS, BAR_PE_EMPTY,
+       BAR_A_READY, BAR_ACC_FULL = BAR_A_READY + 4, BAR_COUNT = BAR_ACC_FULL + 2 };
+
+// ---------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (-> cudaErrorLaunchFailure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* err_flag, unsigned int code) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            if (err_flag) atomicExch(err_flag, code);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// SWIZZLE_128B K-major shared-memory descriptor: rows of 128 B, 8-row atoms 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_field) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);      // start address, 16-byte units      [0,14)
+    d |= (uint64_t)(lbo_field & 0x3FFFu) << 16;    // leading byte offset (unused for swizzled K-major) [16,30)
+    d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset = 8 rows x 128 B [32,46)
+    d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)     [46,48)
+    d |= (uint64_t)2 << 61;                        // layout type SWIZZLE_128B           [61,64)
+    return d;
+}
+// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// byte offset of element (row, k) inside a [rows x 64] fp16 SW128 tile
+__host__ __device__ constexpr uint32_t sw128_offset(int row, int k) {
+    return (uint32_t)row * 128u + ((((uint32_t)k >> 3) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)k & 7u) * 2u;
+}
+
+__device__ __forceinline__ void split_store8(const float* v, unsigned char* hi_dst, unsigned char* lo_dst) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        const float2 back = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(v[2 * i] - back.x, v[2 * i + 1] - back.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+struct TcParams {
+    const __half* stream;      // weight tiles in consumption order
+    const float* inv_scale;    // [10]
+    const float* bias[10];
+    const float* w_alpha; const float* b_alpha;
+    const float* w_rgb; const float* b_rgb;
+};
+
+__host__ __device__ inline size_t stage_offset_bytes(int i) {
+    return i < N256_STAGES ? (size_t)i * STAGE_BYTES : (size_t)N256_STAGES * STAGE_BYTES + (size_t)(i - N256_STAGES) * (STAGE_BYTES / 2);
+}
+
+// ---------------------------------------------------------------------------- the kernel
+template <int C>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+              const float* __restrict__ viewbias, const float* __restrict__ z, int64_t rows, int S, int num_tiles,
+              float* __restrict__ raw, unsigned int* err_flag) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar0 = base + OFF_BAR;
+    auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 8 * BAR_COUNT);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) { mbar_init(bar(BAR_W_FULL + i), 1); mbar_init(bar(BAR_W_EMPTY + i), 1); }
+        mbar_init(bar(BAR_PE_FULL), 128);
+        mbar_init(bar(BAR_PE_EMPTY), 1);
+        for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_A_READY + i), 128);
+        for (int i = 0; i < 2; ++i) mbar_init(bar(BAR_ACC_FULL + i), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int my_tiles = (num_tiles > (int)blockIdx.x) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(p.stream);
+            uint32_t cnt = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                for (int i = 0; i < STAGES_PER_TILE; ++i, ++cnt) {
+                    const uint32_t slot = cnt % NS, ph = (cnt / NS) & 1u;
+                    mbar_wait(bar(BAR_W_EMPTY + slot), ph ^ 1u, err_flag, 1);
+                    const uint32_t bytes = i < N256_STAGES ? STAGE_BYTES : STAGE_BYTES / 2;
+                    mbar_expect_tx(bar(BAR_W_FULL + slot), bytes);
+                    tma_bulk_load(base + OFF_W + slot * STAGE_BYTES, src + stage_offset_bytes(i), bytes, bar(BAR_W_FULL + slot));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t wcnt = 0;           // weight stages consumed
+            uint32_t agen = 0;           // generation of the a_ready barriers (one per producing epilogue)
+            for (int it = 0; it < my_tiles; ++it) {
+                for (int t = 0; t < 10; ++t) {
+                    const int N = (t == 9) ? 128 : 256;
+                    const uint32_t idesc = make_idesc(TILE_M, N);
+                    const uint32_t d_tmem = tmem + (uint32_t)(t & 1) * 256u;
+                    const bool has_pe = (t == 0 || t == 5);
+                    const int n_act = (t == 0) ? 0 : 4;
+                    uint32_t accumulate = 0;
+                    for (int kb = has_pe ? -1 : 0; kb < n_act; ++kb) {
+                        uint32_t a_hi, a_lo;
+                        if (kb < 0) {
+                            if (t == 0) mbar_wait(bar(BAR_PE_FULL), (uint32_t)it & 1u, err_flag, 2);
+                            a_hi = base + OFF_PE_HI; a_lo = base + OFF_PE_LO;
+                        } else {
+                            mbar_wait(bar(BAR_A_READY + kb), agen & 1u, err_flag, 3);
+                            a_hi = base + OFF_A_HI + kb * KBLOCK_BYTES; a_lo = base + OFF_A_LO + kb * KBLOCK_BYTES;
+                        }
+                        tc_fence_after();
+                        // hi tile of the weights: A_hi * W_hi and A_lo * W_hi
+                        {
+                            const uint32_t slot = wcnt % NS, ph = (wcnt / NS) & 1u;
+                            mbar_wait(bar(BAR_W_FULL + slot), ph, err_flag, 4);
+                            tc_fence_after();
+                            const uint32_t w = base + OFF_W + slot * STAGE_BYTES;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const uint64_t bd = make_desc(w + kk * 32, 0);
+                                tc_mma_f16(d_tmem, make_desc(a_hi + kk * 32, 0), bd, idesc, accumulate);
+                                accumulate = 1;
+                                tc_mma_f16(d_tmem, make_desc(a_lo + kk * 32, 0), bd, idesc, 1);
+                            }
+                            tc_commit(bar(BAR_W_EMPTY + slot));
+                            ++wcnt;
+                        }
+                        // lo tile of the weights: A_hi * W_lo
+                        {
+                            const uint32_t slot = wcnt % NS, ph = (wcnt / NS) & 1u;
+                            mbar_wait(bar(BAR_W_FULL + slot), ph, err_flag, 5);
+                            tc_fence_after();
+                            const uint32_t w = base + OFF_W + slot * STAGE_BYTES;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                tc_mma_f16(d_tmem, make_desc(a_hi + kk * 32, 0), make_desc(w + kk * 32, 0), idesc, 1);
+                            tc_commit(bar(BAR_W_EMPTY + slot));
+                            ++wcnt;
+                        }
+                        if (kb < 0 && t == 5) tc_commit(bar(BAR_PE_EMPTY));   // encoded tile no longer needed
+                    }
+                    tc_commit(bar(BAR_ACC_FULL + (t & 1)));
+                    if (t >= 1) ++agen;                                        // steps 1..9 each consumed one generation
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ================= epilogue =================
+        const int q = warp - 4;
+        const int r = q * 32 + lane;                        // row in tile == TMEM lane
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t acc_uses[2] = {0, 0};
+        for (int it = 0; it < my_tiles; ++it) {
+            const int64_t row = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TILE_M + r;
+            float sigma_acc = 0.0f;
+            for (int t = 0; t < 10; ++t) {
+                const int b = t & 1;
+                mbar_wait(bar(BAR_ACC_FULL + b), acc_uses[b] & 1u, err_flag, 6);
+                ++acc_uses[b];
+                tc_fence_after();
+                const float inv_scale = __ldg(p.inv_scale + t);
+                const uint32_t acc_addr = lane_addr + (uint32_t)b * 256u;
+                if (t < 9) {
+                    const float* bias = p.bias[t];
+                    for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            float v[32];
+                            tc_ld32(acc_addr + kb * 64 + h * 32, v);
+                            const int col0 = kb * 64 + h * 32;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+                                v[j] = fmaf(v[j], inv_scale, bv.x); v[j + 1] = fmaf(v[j + 1], inv_scale, bv.y);
+                                v[j + 2] = fmaf(v[j + 2], inv_scale, bv.z); v[j + 3] = fmaf(v[j + 3], inv_scale, bv.w);
+                            }
+                            if (t != 8) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], 0.0f), 65504.0f);      // ReLU (+ fp16 range guard)
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -65504.0f), 65504.0f);  // feature head: linear
+                            }
+                            if (t == 7) {                                      // sigma head on h7 (model/nerf.py:101)
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4) {
+                                    const float4 wa = __ldg(reinterpret_cast<const float4*>(p.w_alpha + col0 + j));
+                                    sigma_acc = fmaf(v[j], wa.x, sigma_acc); sigma_acc = fmaf(v[j + 1], wa.y, sigma_acc);
+                                    sigma_acc = fmaf(v[j + 2], wa.z, sigma_acc); sigma_acc = fmaf(v[j + 3], wa.w, sigma_acc);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t off = kb * KBLOCK_BYTES + sw128_offset(r, h * 32 + j * 8);
+                                split_store8(v + 8 * j, sm + OFF_A_HI + off, sm + OFF_A_LO + off);
+                            }
+                        }
+                        tc_fence_before();
+                        fence_proxy_async();
+                        mbar_arrive(bar(BAR_A_READY + kb));
+                    }
+                } else {
+                    // view layer output (128 cols) -> ReLU -> rgb head; write cat([rgb, sigma]) (model/nerf.py:103-110)
+                    const int64_t ray = (row < rows) ? row / S : 0;
+                    const float* vb = viewbias + ray * kHalf;
+                    float rgb[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+                    for (int h = 0; h < 4; ++h) {
+                        float v[32];
+                        tc_ld32(acc_addr + h * 32, v);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const int col = h * 32 + j;
+                            const float4 bv = __ldg(reinterpret_cast<const float4*>(vb + col));
+                            const float x0 = fmaxf(fmaf(v[j], inv_scale, bv.x), 0.0f), x1 = fmaxf(fmaf(v[j + 1], inv_scale, bv.y), 0.0f);
+                            const float x2 = fmaxf(fmaf(v[j + 2], inv_scale, bv.z), 0.0f), x3 = fmaxf(fmaf(v[j + 3], inv_scale, bv.w), 0.0f);
+#pragma unroll
+                            for (int c = 0; c < C; ++c) {
+                                const float4 wr = __ldg(reinterpret_cast<const float4*>(p.w_rgb + c * kHalf + col));
+                                rgb[c] = fmaf(x0, wr.x, rgb[c]); rgb[c] = fmaf(x1, wr.y, rgb[c]);
+                                rgb[c] = fmaf(x2, wr.z, rgb[c]); rgb[c] = fmaf(x3, wr.w, rgb[c]);
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    if (row < rows) {
+                        const float sg = sigma_acc + __ldg(p.b_alpha);
+                        if (C == 3) {
+                            *reinterpret_cast<float4*>(raw + row * 4) =
+                                make_float4(rgb[0] + __ldg(p.b_rgb), rgb[1] + __ldg(p.b_rgb + 1), rgb[2] + __ldg(p.b_rgb + 2), sg);
+                        } else {
+                            *reinterpret_cast<float2*>(raw + row * 2) = make_float2(rgb[0] + __ldg(p.b_rgb), sg);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // ================= front end: encode the next tile =================
+        const int r = threadIdx.x - 256;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int64_t row = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TILE_M + r;
+            float enc[64];
+            float x[3] = {0.f, 0.f, 0.f};
+            const bool live = row < rows;
+            if (live) {
+                const int64_t ray = row / S;
+                const float zz = __ldg(z + row);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(__ldg(rays_o + ray * 3 + c), __fmul_rn(__ldg(rays_d + ray * 3 + c), zz));
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) enc[c] = x[c];
+#pragma unroll
+            for (int k = 0; k < kPtsFreqs; ++k)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float s, co;
+                    sincosf(x[c] * (float)(1 << k), &s, &co);
+                    enc[3 + 6 * k + c] = live ? s : 0.0f;
+                    enc[3 + 6 * k + 3 + c] = live ? co : 0.0f;
+                }
+            enc[63] = 0.0f;
+            mbar_wait(bar(BAR_PE_EMPTY), ((uint32_t)it & 1u) ^ 1u, err_flag, 7);
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                const uint32_t off = sw128_offset(r, c8 * 8);
+                split_store8(enc + 8 * c8, sm + OFF_PE_HI + off, sm + OFF_PE_LO + off);
+            }
+            fence_proxy_async();
+            mbar_arrive(bar(BAR_PE_FULL));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+    }
+}
+
+// ---------------------------------------------------------------------------- weight stream
+// Stage i of a tile = (GEMM step t, K-block kb, half) in MMA consumption order; the encoded-point
+// K-block comes first for steps 0 and 5.
+struct StageInfo { int step, k0, n, lo; };
+__host__ __device__ inline StageInfo stage_info(int i) {
+    int kbi = i / 2, lo = i & 1, t = 0;
+    const int kbs[10] = {1, 4, 4, 4, 4, 5, 4, 4, 4, 4};
+    while (kbi >= kbs[t]) { kbi -= kbs[t]; ++t; }
+    return {t, kbi * 64, t == 9 ? 128 : 256, lo};          // wt[t] rows are already ordered [pe64 | h256]
+}
+
+__global__ void absmax_kernel(const float* __restrict__ w, int n, unsigned int* out) {
+    float m = 0.0f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x % 32 == 0) atomicMax(out, __float_as_uint(m));
+}
+// scale[t] = 2^s with max|W| * 2^s in [1024, 2048); inv_scale[t] = 2^-s
+__global__ void scale_kernel(const unsigned int* __restrict__ absmax, float* __restrict__ scale, float* __restrict__ inv_scale) {
+    const int t = threadIdx.x;
+    if (t >= 10) return;
+    const float m = __uint_as_float(absmax[t]);
+    int s = 0;
+    if (m > 0.0f && isfinite(m)) s = 10 - ilogbf(m);
+    s = max(-24, min(24, s));
+    scale[t] = exp2f((float)s);
+    inv_scale[t] = exp2f((float)-s);
+}
+__global__ void pack_stream_kernel(const float* const* __restrict__ wt, const float* __restrict__ scale, __half* __restrict__ stream) {
+    const int i = blockIdx.x;                               // stage
+    const StageInfo si = stage_info(i);
+    const float* w = wt[si.step];
+    const float sc = scale[si.step];
+    unsigned char* dst = reinterpret_cast<unsigned char*>(stream) + stage_offset_bytes(i);
+    for (int e = threadIdx.x; e < si.n * 64; e += blockDim.x) {
+        const int k = e / si.n, n = e % si.n;               // coalesced over n in the k-major source
+        const float v = w[(size_t)(si.k0 + k) * si.n + n] * sc;
+        const __half hi = __float2half_rn(v);
+        const __half out = si.lo ? __float2half_rn(v - __half2float(hi)) : hi;
+        *reinterpret_cast<__half*>(dst + sw128_offset(n, k)) = out;
+    }
+}
+
+}  // namespace tc
+
+size_t tc_stream_halfs() { return tc::stage_offset_bytes(tc::STAGES_PER_TILE) / sizeof(__half); }
+
+int pack_tc_stream(bnrf_ctx* ctx, int net, cudaStream_t st) {
+    using namespace tc;
+    NetParams& np = ctx->net[net];
+    // scratch inside tc_scale: [0,10) inv_scale (read by the kernel), then absmax bits / scale / pointer table live in
+    // a small side allocation made once per context.
+    static_assert(sizeof(unsigned int) == sizeof(float), "");
+    float* inv_scale = np.tc_scale;
+    unsigned int* absmax = nullptr;
+    float* scale = nullptr;
+    const float** table = nullptr;
+    BNRF_CUDA(ctx, cudaMallocAsync(&absmax, 16 * sizeof(unsigned int), st));
+    BNRF_CUDA(ctx, cudaMallocAsync(&scale, 16 * sizeof(float), st));
+    BNRF_CUDA(ctx, cudaMallocAsync(&table, 10 * sizeof(float*), st));
+    BNRF_CUDA(ctx, cudaMemsetAsync(absmax, 0, 16 * sizeof(unsigned int), st));
+    for (int t = 0; t < 10; ++t) absmax_kernel<<<32, 256, 0, st>>>(np.wt[t], gemm_k(t) * gemm_n(t), absmax + t);
+    scale_kernel<<<1, 32, 0, st>>>(absmax, scale, inv_scale);
+    BNRF_CUDA(ctx, cudaMemcpyAsync(table, np.wt, 10 * sizeof(float*), cudaMemcpyHostToDevice, st));
+    pack_stream_kernel<<<STAGES_PER_TILE, 256, 0, st>>>(table, scale, np.tc_stream);
+    BNRF_LAUNCH_CHECK(ctx);
+    BNRF_CUDA(ctx, cudaFreeAsync(absmax, st));
+    BNRF_CUDA(ctx, cudaFreeAsync(scale, st));
+    BNRF_CUDA(ctx, cudaFreeAsync(table, st));
+    return BNRF_OK;
+}
+
+int launch_mlp_tc(bnrf_ctx* ctx, int net, const float* o, const float* d, const float* vb, const float* z,
+                  int64_t n, int S, float* raw, cudaStream_t st) {
+    using namespace tc;
+    const NetParams& np = ctx->net[net];
+    TcParams p;
+    p.stream = np.tc_stream; p.inv_scale = np.tc_scale;
+    for (int i = 0; i < 10; ++i) p.bias[i] = np.bias[i];
+    p.w_alpha = np.w_alpha; p.b_alpha = np.b_alpha; p.w_rgb = np.w_rgb; p.b_rgb = np.b_rgb;
+    const int64_t rows = n * S;
+    const int64_t tiles64 = ceil_div(rows, TILE_M);
+    if (tiles64 > 0x7fffffff) return fail(ctx, BNRF_ERR_ARG, "mlp: too many rows");
+    const int tiles = (int)tiles64;
+    const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+    if (ctx->cfg.channels == 3) {
+        BNRF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        mlp_tc_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p, o, d, vb, z, rows, S, tiles, raw, ctx->err_flag);
+    } else {
+        BNRF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        mlp_tc_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p, o, d, vb, z, rows, S, tiles, raw, ctx->err_flag);
+    }
+    BNRF_LAUNCH_CHECK(ctx);
+    return BNRF_OK;
+}
+
+// ---------------------------------------------------------------------------- UMMA probe
+// D[128 x N] = A[128 x 64] * B[N x 64]^T for fp16 inputs given in plain row-major global memory.
+// Uses the same swizzle, descriptor, MMA and TMEM-load helpers as the MLP kernel so that the
+// layout conventions can be validated in isolation (tests/test_gpu_probe.py).
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const __half* __restrict__ A, const __half* __restrict__ B, int N, uint32_t lbo_field, float* __restrict__ D) {
+    using namespace tc;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - smem_u32(smem_raw));
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(8) uint64_t done_bar;
+    const int warp = threadIdx.x / 32;
+    for (int e = threadIdx.x; e < 128 * 64; e += 128) *reinterpret_cast<__half*>(sm + sw128_offset(e / 64, e % 64)) = A[e];
+    for (int e = threadIdx.x; e < N * 64; e += 128) *reinterpret_cast<__half*>(sm + KBLOCK_BYTES + sw128_offset(e / 64, e % 64)) = B[e];
+    if (threadIdx.x == 0) { mbar_init(smem_u32(&done_bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc(128, N);
+        for (int kk = 0; kk < 4; ++kk)
+            tc_mma_f16(tmem, make_desc(base + kk * 32, lbo_field), make_desc(base + KBLOCK_BYTES + kk * 32, lbo_field), idesc, kk > 0);
+        tc_commit(smem_u32(&done_bar));
+    }
+    mbar_wait(smem_u32(&done_bar), 0, nullptr, 0);
+    tc_fence_after();
+    const int r = threadIdx.x;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32];
+        tc_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        for (int j = 0; j < 32; ++j) D[(size_t)r * N + c0 + j] = v[j];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u));
+    }
+}
+
+}  // namespace bnrf
+
+extern "C" int bnrf_debug_umma_probe(const void* A_half, const void* B_half, int N, int lbo_field, float* D, void* stream) {
+    using namespace bnrf;
+    if (!A_half || !B_half || !D || N < 16 || N > 256 || N % 16) return BNRF_ERR_ARG;
+    const size_t smem = tc::KBLOCK_BYTES + 32768 + 1024;
+    if (cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return BNRF_ERR_CUDA;
+    umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __half*)A_half, (const __half*)B_half, N, (uint32_t)lbo_field, D);
+    return cudaGetLastError() == cudaSuccess ? BNRF_OK : BNRF_ERR_CUDA;
+}

@@ -1,0 +1,142 @@
+// K2/K3: pixels x poses -> NDC rays, view directions, stratified depths, per-ray view bias.
+//
+// Replaces run_nerf_helpers.py:35-71 (get_specific_rays / get_rays, ndc_rays) and
+// model/nerf.py:241-308 (pose-major expansion, viewdirs before NDC, jittered depths).
+// The reference materialises [N,3,4] repeated poses and ~25 temporaries; here a thread owns a
+// ray and keeps everything in registers.  Built with -fmad=false and written with explicit
+// round-to-nearest intrinsics in the reference's operation order: these values sit upstream
+// of the 2^9 positional-encoding frequency, so a 1-ulp difference becomes 3e-5 in sin/cos.
+#include "common.cuh"
+
+namespace bnrf {
+
+__global__ void rays_kernel(const float* __restrict__ poses, const int64_t* __restrict__ ray_idx, int P, int R,
+                            int H, int W, float fx, float fy, float cx, float cy, const float* __restrict__ remap,
+                            int ndc, float* __restrict__ out_o, float* __restrict__ out_d, float* __restrict__ out_v) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (int64_t)P * R) return;
+    const int p = (int)(n / R);
+    const int64_t pix = ray_idx[n % R];
+    float fi = (float)(pix % W), fj = (float)(pix / W);
+    if (remap) {                                   // TUM-VIE LUT (model/nerf.py:247-250)
+        const float* e = remap + 2 * pix;
+        fi = e[0]; fj = e[1];
+    }
+    const float* c2w = poses + (size_t)p * 12;
+    // camera-frame direction (run_nerf_helpers.py:36-38)
+    const float dx = __fdiv_rn(__fsub_rn(fi, cx), fx);
+    const float dy = -__fdiv_rn(__fsub_rn(fj, cy), fy);
+    const float dz = -1.0f;
+    float d[3], o[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {                  // sum over the last dim of dirs * c2w[:3,:3]
+        const float a = __fmul_rn(dx, c2w[r * 4 + 0]), b = __fmul_rn(dy, c2w[r * 4 + 1]), c = __fmul_rn(dz, c2w[r * 4 + 2]);
+        d[r] = __fadd_rn(__fadd_rn(a, b), c);
+        o[r] = c2w[r * 4 + 3];
+    }
+    // unit view direction from the PRE-ndc direction (model/nerf.py:272-275)
+    const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+    out_v[n * 3 + 0] = __fdiv_rn(d[0], nrm);
+    out_v[n * 3 + 1] = __fdiv_rn(d[1], nrm);
+    out_v[n * 3 + 2] = __fdiv_rn(d[2], nrm);
+    if (ndc) {                                     // run_nerf_helpers.py:46-71 with near = 1, focal = K[0][0]
+        const float near = 1.0f;
+        const float t = __fdiv_rn(-__fadd_rn(near, o[2]), d[2]);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) o[r] = __fadd_rn(o[r], __fmul_rn(t, d[r]));
+        const float sx = __fdiv_rn(-1.0f, __fdiv_rn((float)W, __fmul_rn(2.0f, fx)));
+        const float sy = __fdiv_rn(-1.0f, __fdiv_rn((float)H, __fmul_rn(2.0f, fx)));
+        const float o0 = __fdiv_rn(__fmul_rn(sx, o[0]), o[2]);
+        const float o1 = __fdiv_rn(__fmul_rn(sy, o[1]), o[2]);
+        const float o2 = __fadd_rn(1.0f, __fdiv_rn(2.0f * near, o[2]));
+        const float d0 = __fmul_rn(sx, __fsub_rn(__fdiv_rn(d[0], d[2]), __fdiv_rn(o[0], o[2])));
+        const float d1 = __fmul_rn(sy, __fsub_rn(__fdiv_rn(d[1], d[2]), __fdiv_rn(o[1], o[2])));
+        const float d2 = __fdiv_rn(-2.0f * near, o[2]);
+        o[0] = o0; o[1] = o1; o[2] = o2; d[0] = d0; d[1] = d1; d[2] = d2;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { out_o[n * 3 + r] = o[r]; out_d[n * 3 + r] = d[r]; }
+}
+
+// z = lower + (upper - lower) * t_rand over the S strata of [near, far]  (model/nerf.py:285-307)
+__global__ void stratified_kernel(const float* __restrict__ t_vals, const float* __restrict__ t_rand, bnrf_rng rng,
+                                  int64_t total, int S, float near, float far, float* __restrict__ z) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int s = (int)(e % S);
+    auto grid = [&](int i) {   // near * (1 - t) + far * t
+        const float t = t_vals[i];
+        return __fadd_rn(__fmul_rn(near, __fsub_rn(1.0f, t)), __fmul_rn(far, t));
+    };
+    const float zc = grid(s);
+    const float lower = (s == 0) ? zc : __fmul_rn(0.5f, __fadd_rn(zc, grid(s - 1)));
+    const float upper = (s == S - 1) ? zc : __fmul_rn(0.5f, __fadd_rn(grid(s + 1), zc));
+    float r;
+    if (t_rand) {
+        r = t_rand[e];
+    } else {
+        uint32_t w[4];
+        Philox::draw(rng.seed, rng.offset, (uint64_t)(e / S), (uint32_t)s, kStreamTRand, w);
+        r = Philox::uniform(w[0]);
+    }
+    z[e] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), r));
+}
+
+// Per-ray constant part of views_linears.0: vb[n][j] = b[j] + sum_i W[j][256+i] * enc(viewdir)[i].
+// All samples of a ray share the view direction, so the 27 direction features never enter the
+// per-sample GEMM (model/nerf.py:80-88,103 concatenates them onto every sample instead).
+__global__ void viewbias_kernel(const float* __restrict__ view, const float* __restrict__ w_dir /*[27][128]*/,
+                                const float* __restrict__ bias /*[128]*/, int64_t n_rays, float* __restrict__ vb) {
+    const int64_t ray = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (ray >= n_rays) return;
+    float enc[kDirCh];
+    const float v[3] = {view[ray * 3], view[ray * 3 + 1], view[ray * 3 + 2]};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) enc[c] = v[c];
+#pragma unroll
+    for (int k = 0; k < kDirFreqs; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float s, co;
+            sincosf(v[c] * (float)(1 << k), &s, &co);
+            enc[3 + 6 * k + c] = s;
+            enc[3 + 6 * k + 3 + c] = co;
+        }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int j = lane + 32 * q;
+        float acc = bias[j];
+#pragma unroll
+        for (int i = 0; i < kDirCh; ++i) acc = fmaf(w_dir[i * kHalf + j], enc[i], acc);
+        vb[ray * kHalf + j] = acc;
+    }
+}
+
+int launch_rays(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W, const float* K,
+                const float* remap, float* o, float* d, float* view, cudaStream_t st) {
+    if (!poses || !ray_idx || !K || !o || !d || !view || P <= 0 || R <= 0) return fail(ctx, BNRF_ERR_ARG, "rays: bad argument");
+    const int64_t n = (int64_t)P * R;
+    rays_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(poses, ray_idx, P, R, H, W, K[0], K[4], K[2], K[5], remap,
+                                                           ctx->cfg.ndc, o, d, view);
+    BNRF_LAUNCH_CHECK(ctx);
+    return BNRF_OK;
+}
+
+int launch_stratified(bnrf_ctx* ctx, const float* t_rand, const bnrf_rng* rng, int64_t n, int S, float* z, cudaStream_t st) {
+    if (!z || n <= 0 || S != ctx->cfg.n_samples) return fail(ctx, BNRF_ERR_ARG, "stratified: bad argument (S must equal cfg.n_samples)");
+    bnrf_rng r = rng ? *rng : bnrf_rng{};
+    stratified_kernel<<<(unsigned)ceil_div(n * S, 256), 256, 0, st>>>(ctx->t_vals, t_rand, r, n * S, S, ctx->cfg.near_,
+                                                                     ctx->cfg.far_, z);
+    BNRF_LAUNCH_CHECK(ctx);
+    return BNRF_OK;
+}
+
+int launch_viewbias(bnrf_ctx* ctx, int net, const float* view, int64_t n, float* vb, cudaStream_t st) {
+    const NetParams& np = ctx->net[net];
+    viewbias_kernel<<<(unsigned)ceil_div(n, 4), 128, 0, st>>>(view, np.w_dir, np.bias[9], n, vb);
+    BNRF_LAUNCH_CHECK(ctx);
+    return BNRF_OK;
+}
+
+}  // namespace bnrf

@@ -1,0 +1,206 @@
+"""Thin host wrapper over the C ABI: owns one bnrf_ctx, passes raw device pointers.
+
+PyTorch is used for device memory and streams only; every number on the render path is
+produced by libbenerf_b200.so.  All calls are enqueued on torch's current CUDA stream.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import BnrfError
+
+TRAJ = {"spline": 0, "linear": 1}
+LOG_MODE = {"BeNeRF_Blender": 0, "BeNeRF_Unreal": 0, "E2NeRF_Synthetic": 1, "E2NeRF_Real": 1, "safelog": 0, "linlog": 1}
+MLP_MODES = {"tc": _lib.MLP_TC_FP16X2, "simt": _lib.MLP_SIMT_FP32}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, dtype=torch.float32, device=None, name="tensor"):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise BnrfError(f"{name}: expected a CUDA tensor")
+    if t.dtype != dtype or not t.is_contiguous():
+        raise BnrfError(f"{name}: expected contiguous {dtype}, got {t.dtype} contiguous={t.is_contiguous()}")
+    if device is not None and t.device != device:
+        raise BnrfError(f"{name}: tensor on {t.device}, engine on {device}")
+    return C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One context per (process, device) -- SURVEY 8-b conventions."""
+
+    def __init__(self, n_samples=64, n_importance=64, channels=3, ndc=True, near=0.0, far=1.0, mlp_mode="tc", device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise BnrfError("benerf_b200 needs a CUDA (sm_100a) device; there is no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else torch.device(device).index or 0)
+        self.cfg = _lib.Cfg(n_samples, n_importance, channels, int(bool(ndc)), near, far, MLP_MODES[mlp_mode], 0)
+        self.n_samples, self.n_importance, self.channels = n_samples, n_importance, channels
+        self._ctx = C.c_void_p()
+        rc = self.lib.bnrf_create(C.byref(self._ctx), self.device.index, C.byref(self.cfg))
+        if rc != _lib.OK:
+            raise BnrfError(f"bnrf_create failed ({rc}): {self.lib.bnrf_last_error(None).decode()}")
+        self._workspace = None
+        self._weights_version = [None, None]
+
+    # -- lifetime -----------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self.lib.bnrf_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != _lib.OK:
+            raise BnrfError(f"{what} failed ({rc}): {self.lib.bnrf_last_error(self._ctx).decode()}")
+
+    # -- parameters ---------------------------------------------------------------------
+    def set_weights(self, net, params):
+        """params: {'pts_linears.0.weight': tensor, ...} (reference state-dict names) or an nn.Module."""
+        if hasattr(params, "state_dict"):
+            params = dict(params.named_parameters())
+        ws, bs, keep = (C.c_void_p * 12)(), (C.c_void_p * 12)(), []
+        for i, name in enumerate(_lib.LINEAR_NAMES):
+            w = params[name + ".weight"].detach()
+            b = params[name + ".bias"].detach()
+            keep += [w, b]
+            ws[i] = _ptr(w, device=self.device, name=name + ".weight")
+            bs[i] = _ptr(b, device=self.device, name=name + ".bias")
+        self._check(self.lib.bnrf_set_weights(self._ctx, int(net), ws, bs, _stream()), "bnrf_set_weights")
+
+    def sync_weights(self, net, module):
+        """Repack only when an optimiser step (or load_state_dict) touched the module's parameters."""
+        version = tuple((p.data_ptr(), p._version) for p in module.parameters())
+        if version != self._weights_version[net]:
+            self.set_weights(net, module)
+            self._weights_version[net] = version
+
+    def set_sample_grid(self, t_vals):
+        t = torch.as_tensor(t_vals, dtype=torch.float32).cpu().contiguous()
+        arr = (C.c_float * t.numel())(*t.tolist())
+        self._check(self.lib.bnrf_set_sample_grid(self._ctx, arr, t.numel(), _stream()), "bnrf_set_sample_grid")
+
+    # -- a1/a2 ----------------------------------------------------------------------------
+    def spline_poses(self, knots, transform, ts, traj="spline"):
+        P = ts.numel()
+        out = torch.empty(P, 3, 4, device=self.device, dtype=torch.float32)
+        self._check(self.lib.bnrf_spline_poses(self._ctx, _ptr(knots, name="knots"), _ptr(transform, name="transform"),
+                                               _ptr(ts, name="ts"), P, TRAJ[traj], _ptr(out), _stream()), "bnrf_spline_poses")
+        return out
+
+    # -- a3-a10 -----------------------------------------------------------------------------
+    def _K(self, K):
+        flat = [float(v) for v in torch.as_tensor(K, dtype=torch.float32).reshape(-1).tolist()]
+        return (C.c_float * 9)(*flat)
+
+    def render(self, poses, ray_idx, H, W, K, remap=None, rng=None, seed=0, offset=0, want_sigma=True, want_depth=False):
+        """Graph.render (model/nerf.py:236-343).  rng: dict of the four draws (parity mode) or None (Philox)."""
+        P, R = poses.shape[0], ray_idx.numel()
+        n = P * R
+        Sf = self.n_samples + self.n_importance
+        C_ = self.channels
+        new = lambda *s: torch.empty(*s, device=self.device, dtype=torch.float32)
+        ret = {"rgb_map": new(n, C_), "disp_map": new(n), "acc_map": new(n)}
+        if self.n_importance > 0:
+            ret.update({"rgb0": new(n, C_), "disp0": new(n), "acc0": new(n)})
+            if want_sigma:
+                ret["sigma"] = new(n, Sf)
+        depth = new(n) if want_depth else None
+        outs = _lib.Outputs(*[_ptr(ret.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0", "sigma")], _ptr(depth))
+        r = _lib.Rng(None, None, None, None, int(seed), int(offset))
+        if rng is not None:
+            r.t_rand, r.noise_c = _ptr(rng["t_rand"], name="t_rand"), _ptr(rng["noise_c"], name="noise_c")
+            if self.n_importance > 0:
+                r.u, r.noise_f = _ptr(rng["u"], name="u"), _ptr(rng["noise_f"], name="noise_f")
+        need = self.lib.bnrf_workspace_bytes(self._ctx, n)
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.empty(need, device=self.device, dtype=torch.uint8)
+        self._check(self.lib.bnrf_render_forward(
+            self._ctx, _ptr(poses, name="poses"), _ptr(ray_idx, torch.int64, name="ray_idx"), P, R, int(H), int(W),
+            self._K(K), _ptr(remap, name="remap"), C.byref(r), C.byref(outs), C.c_void_p(self._workspace.data_ptr()),
+            self._workspace.numel(), _stream()), "bnrf_render_forward")
+        if want_depth:
+            ret["depth_map"] = depth
+        return ret
+
+    # -- stage operators ------------------------------------------------------------------
+    def op_rays(self, poses, ray_idx, H, W, K, remap=None):
+        n = poses.shape[0] * ray_idx.numel()
+        o, d, v = (torch.empty(n, 3, device=self.device) for _ in range(3))
+        self._check(self.lib.bnrf_op_rays(self._ctx, _ptr(poses), _ptr(ray_idx, torch.int64), poses.shape[0], ray_idx.numel(),
+                                          int(H), int(W), self._K(K), _ptr(remap), _ptr(o), _ptr(d), _ptr(v), _stream()), "bnrf_op_rays")
+        return o, d, v
+
+    def op_stratified(self, t_rand):
+        z = torch.empty_like(t_rand)
+        self._check(self.lib.bnrf_op_stratified(self._ctx, _ptr(t_rand), t_rand.shape[0], t_rand.shape[1], _ptr(z), _stream()), "bnrf_op_stratified")
+        return z
+
+    def op_mlp(self, net, rays_o, rays_d, viewdirs, z):
+        n, S = z.shape
+        raw = torch.empty(n, S, self.channels + 1, device=self.device)
+        self._check(self.lib.bnrf_op_mlp(self._ctx, int(net), _ptr(rays_o), _ptr(rays_d), _ptr(viewdirs), _ptr(z), n, S, _ptr(raw), _stream()), "bnrf_op_mlp")
+        return raw
+
+    def op_composite(self, raw, z, rays_d, noise):
+        n, S = z.shape
+        new = lambda *s: torch.empty(*s, device=self.device)
+        out = {"rgb_map": new(n, self.channels), "disp_map": new(n), "acc_map": new(n), "weights": new(n, S),
+               "depth_map": new(n), "sigma": new(n, S)}
+        self._check(self.lib.bnrf_op_composite(self._ctx, _ptr(raw), _ptr(z), _ptr(rays_d), _ptr(noise), n, S,
+                                               *[_ptr(out[k]) for k in ("rgb_map", "disp_map", "acc_map", "weights", "depth_map", "sigma")],
+                                               _stream()), "bnrf_op_composite")
+        return out
+
+    def op_resample(self, z_coarse, weights, u):
+        n, S = z_coarse.shape
+        K = u.shape[1]
+        zf = torch.empty(n, S + K, device=self.device)
+        self._check(self.lib.bnrf_op_resample(self._ctx, _ptr(z_coarse), _ptr(weights), _ptr(u), n, S, K, _ptr(zf), _stream()), "bnrf_op_resample")
+        return zf
+
+
+# -- image formation: context-free entry points ---------------------------------------------
+def _rc(rc, what):
+    if rc != _lib.OK:
+        raise BnrfError(f"{what} failed ({rc})")
+
+
+def blur_mean(rgb, n_poses):
+    """[P*R, C] pose-major (or [P,R,C]) -> [R, C]   (train.py:299-318)."""
+    lib = _lib.load()
+    C_ = rgb.shape[-1]
+    R = rgb.numel() // (n_poses * C_)
+    out = torch.empty(R, C_, device=rgb.device, dtype=torch.float32)
+    _rc(lib.bnrf_blur_mean(_ptr(rgb, name="rgb"), int(n_poses), R, C_, _ptr(out), _stream()), "bnrf_blur_mean")
+    return out
+
+
+def event_logdiff(rgb, n_bins, dataset_or_mode):
+    """[(B+1)*R, C] pose-major -> [B, R] log-brightness differences of consecutive poses (train.py:205-292)."""
+    lib = _lib.load()
+    C_ = rgb.shape[-1]
+    R = rgb.numel() // ((n_bins + 1) * C_)
+    out = torch.empty(n_bins, R, device=rgb.device, dtype=torch.float32)
+    _rc(lib.bnrf_event_logdiff(_ptr(rgb, name="rgb"), int(n_bins), R, C_, LOG_MODE[dataset_or_mode], _ptr(out), _stream()), "bnrf_event_logdiff")
+    return out
+
+
+def accumulate_events(x, y, pol, H, W, out=None):
+    """int32 x, y, float pol (device) -> float64 [H, W] polarity image (utils/event_utils.py:247-259)."""
+    lib = _lib.load()
+    if out is None:
+        out = torch.zeros(H, W, device=x.device, dtype=torch.float64)
+    _rc(lib.bnrf_accumulate_events(_ptr(x, torch.int32, name="x"), _ptr(y, torch.int32, name="y"), _ptr(pol, name="pol"),
+                                   x.numel(), int(H), int(W), _ptr(out, torch.float64), _stream()), "bnrf_accumulate_events")
+    return out

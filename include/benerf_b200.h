@@ -1,0 +1,181 @@
+/*
+ * benerf_b200 -- C ABI of the Blackwell-native BeNeRF render-and-image-formation engine.
+ *
+ * The reference (WU-CVGL/BeNeRF) has no FFI of its own: the drop-in boundary is the
+ * Python call surface of model/nerf.py + model/optimize.py + spline.py.
+ * benerf_b200/ (Python) keeps that surface and forwards every arithmetic step to the
+ * entry points below; each one names the reference lines it replaces.
+ *
+ * Conventions
+ *   - every function returns BNRF_OK (0) or a negative bnrf_status; nothing throws
+ *     across the ABI; bnrf_last_error() gives the text of the last failure;
+ *   - all pointers marked "device" are CUDA device pointers owned by the CALLER
+ *     (PyTorch allocations in practice); the library never frees or retains them
+ *     beyond the call, except its packed-weight cache inside the context;
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*),
+ *     with no internal synchronisation and no host allocation on the hot path;
+ *   - one context per (process, device); not thread-safe across concurrent calls on
+ *     the same context (the reference is a single Python loop, train.py:153);
+ *   - tensors are fp32 row-major, ray order is POSE-MAJOR: ray n = pose n / R,
+ *     pixel n % R (model/nerf.py:242-243);
+ *   - there is no CPU fallback: on a machine without an sm_100 device bnrf_create
+ *     fails with BNRF_ERR_DEVICE.
+ */
+#ifndef BENERF_B200_H
+#define BENERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNRF_ABI_VERSION 1
+
+typedef enum {
+    BNRF_OK = 0,
+    BNRF_ERR_ARG = -1,        /* bad argument (null pointer, unsupported size) */
+    BNRF_ERR_DEVICE = -2,     /* no usable sm_100 device / wrong device */
+    BNRF_ERR_CUDA = -3,       /* a CUDA runtime call or kernel launch failed */
+    BNRF_ERR_STATE = -4,      /* weights not set, workspace too small, ... */
+    BNRF_ERR_NCCL = -5
+} bnrf_status;
+
+/* MLP arithmetic (cfg.mlp_mode).  Both run on the GPU; there is no host path. */
+#define BNRF_MLP_TC_FP16X2 0  /* tcgen05.mma kind::f16, 2-term split operands (hi*hi + lo*hi + hi*lo), fp32 TMEM accumulate */
+#define BNRF_MLP_SIMT_FP32 1  /* plain fp32 FFMA; on-device cross-check of the tensor-core path */
+
+/* Order of the 12 linears in bnrf_set_weights (the reference's state-dict order). */
+enum {
+    BNRF_L_PTS0 = 0, /* .. BNRF_L_PTS0 + 7 : pts_linears.0-7  (256,63) (256,256)x4 (256,319) (256,256)x2 */
+    BNRF_L_VIEWS = 8,   /* views_linears.0 (128,283) */
+    BNRF_L_FEATURE = 9, /* feature_linear  (256,256) */
+    BNRF_L_ALPHA = 10,  /* alpha_linear    (1,256)   */
+    BNRF_L_RGB = 11,    /* rgb_linear      (C,128)   */
+    BNRF_NUM_LINEARS = 12
+};
+
+typedef struct bnrf_ctx bnrf_ctx;
+
+/* Static configuration of the render path (args.* the reference reads on this path). */
+typedef struct {
+    int32_t n_samples;     /* args.N_samples   (64)                       model/nerf.py:297 */
+    int32_t n_importance;  /* args.N_importance (64; 0 = coarse only)     model/nerf.py:319 */
+    int32_t channels;      /* args.channels, 1 or 3                       model/nerf.py:64  */
+    int32_t ndc;           /* args.ndc (always 1 in the reference, Q3)    model/nerf.py:278 */
+    float near_, far_;     /* sampling range, Graph.render defaults 0, 1  model/nerf.py:239 */
+    int32_t mlp_mode;      /* BNRF_MLP_*                                                    */
+    int32_t reserved;
+} bnrf_cfg;
+
+/* The four random draws of one Graph.render.  Parity mode: device pointers to
+ * pre-generated tensors.  Production mode: all four NULL and (seed, offset) key an in-kernel
+ * Philox4x32-10 stream (statistically equivalent, not bit-equal to torch's generator). */
+typedef struct {
+    const float* t_rand;   /* device [N, S_c]       U[0,1)  model/nerf.py:305 */
+    const float* noise_c;  /* device [N, S_c]       N(0,1)  model/nerf.py:135 */
+    const float* u;        /* device [N, N_i]       U[0,1)  run_nerf_helpers.py:86 */
+    const float* noise_f;  /* device [N, S_c + N_i] N(0,1)  model/nerf.py:135 */
+    uint64_t seed, offset;
+} bnrf_rng;
+
+/* Outputs of Graph.render (model/nerf.py:336-343); any pointer may be NULL to skip it. */
+typedef struct {
+    float* rgb_map;   /* device [N, C]   */
+    float* disp_map;  /* device [N]      */
+    float* acc_map;   /* device [N]      */
+    float* rgb0;      /* device [N, C]   coarse (n_importance > 0) */
+    float* disp0;     /* device [N]      */
+    float* acc0;      /* device [N]      */
+    float* sigma;     /* device [N, S_f] relu(raw_sigma + noise) of the last network */
+    float* depth_map; /* device [N]      (raw2output returns it; Graph.render drops it) */
+} bnrf_outputs;
+
+/* -------------------------------------------------------------------------------------- */
+/* context                                                                                */
+
+int bnrf_abi_version(void);
+/* Replaces Graph.__init__ (model/nerf.py:152-158) as far as device state goes. */
+int bnrf_create(bnrf_ctx** ctx, int device, const bnrf_cfg* cfg);
+void bnrf_destroy(bnrf_ctx* ctx);
+const char* bnrf_last_error(const bnrf_ctx* ctx);   /* ctx may be NULL: last create() error */
+
+/* Borrow the 12 weight + 12 bias tensors of one network (0 coarse, 1 fine) in PyTorch
+ * (out,in) row-major fp32 and repack them into the library's private tensor-core layout.
+ * Call after every optimiser step.  Replaces the nn.Linear reads of model/nerf.py:93-112. */
+int bnrf_set_weights(bnrf_ctx* ctx, int net, const float* const* weights /*[12] device*/,
+                     const float* const* biases /*[12] device*/, void* stream);
+
+/* Override the coarse sampling grid t_vals (host float[S], S == cfg.n_samples).  Default is
+ * torch.linspace(0, 1, S) as the reference's CUDA device evaluates it (model/nerf.py:297); the
+ * CPU build of torch.linspace differs from it by an ulp depending on the host's vector width,
+ * so parity harnesses pass the oracle's own grid. */
+int bnrf_set_sample_grid(bnrf_ctx* ctx, const float* t_vals_host, int S, void* stream);
+
+/* -------------------------------------------------------------------------------------- */
+/* a1/a2: pose interpolation -- spline.py:247-331 via model/optimize.py:58-111             */
+
+/* knots device [4,6]; transform device [6] or NULL (added in se(3), optimize.py:86-89);
+ * ts device [P] in [0,1] (0 and 1 are nudged by 1e-6, spline.py:249-252, without writing ts);
+ * traj 0 = cubic B-spline, 1 = linear between knots 0 and 3; poses_out device [P,3,4]. */
+int bnrf_spline_poses(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts,
+                      int P, int traj, float* poses_out, void* stream);
+
+/* -------------------------------------------------------------------------------------- */
+/* a3-a10: Graph.render -- model/nerf.py:236-343                                            */
+
+/* Bytes of caller-provided scratch needed by bnrf_render_forward for n_rays = P*R rays. */
+size_t bnrf_workspace_bytes(const bnrf_ctx* ctx, int64_t n_rays);
+
+/* poses device [P,3,4]; ray_idx device int64 [R] (flat pixel index j*W+i); K host float[9]
+ * row-major; remap device [H,W,2] or NULL (TUM-VIE LUT, model/nerf.py:247-250). */
+int bnrf_render_forward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R,
+                        int H, int W, const float* K, const float* remap, const bnrf_rng* rng,
+                        const bnrf_outputs* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stage-level operators (the same kernels bnrf_render_forward chains; exported so each can be
+ * checked 1:1 against the reference function it replaces). */
+
+/* run_nerf_helpers.py:35-71 + model/nerf.py:241-279: rays_o/rays_d (NDC if cfg.ndc) and the
+ * pre-NDC unit view directions, all device [N,3]. */
+int bnrf_op_rays(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W,
+                 const float* K, const float* remap, float* rays_o, float* rays_d, float* viewdirs, void* stream);
+/* model/nerf.py:285-307: stratified depths z device [N,S] from t_rand device [N,S]. */
+int bnrf_op_stratified(bnrf_ctx* ctx, const float* t_rand, int64_t n_rays, int S, float* z, void* stream);
+/* model/embedder.py:9-34 + model/nerf.py:67-116: raw device [N,S,C+1] for pts = o + d*z. */
+int bnrf_op_mlp(bnrf_ctx* ctx, int net, const float* rays_o, const float* rays_d, const float* viewdirs,
+                const float* z, int64_t n_rays, int S, float* raw, void* stream);
+/* model/nerf.py:118-148 (raw2output).  weights/depth/sigma may be NULL. */
+int bnrf_op_composite(bnrf_ctx* ctx, const float* raw, const float* z, const float* rays_d, const float* noise,
+                      int64_t n_rays, int S, float* rgb_map, float* disp_map, float* acc_map,
+                      float* weights, float* depth_map, float* sigma, void* stream);
+/* run_nerf_helpers.py:74-115 + model/nerf.py:322-326: z_fine device [N, S+K] sorted. */
+int bnrf_op_resample(bnrf_ctx* ctx, const float* z_coarse, const float* weights, const float* u,
+                     int64_t n_rays, int S, int K, float* z_fine, void* stream);
+
+/* -------------------------------------------------------------------------------------- */
+/* a11, a13, a14: image formation -- train.py:163-177,205-331, utils/event_utils.py:247-259 */
+
+/* Blur model: out[r,c] = (sum_j rgb[j,r,c]) / P, summed j = 0..P-1 (train.py:307-318). */
+int bnrf_blur_mean(const float* rgb /*device [P,R,C]*/, int P, int64_t R, int C, float* out /*device [R,C]*/, void* stream);
+/* Event model: out[b,r] = L(rgb[b+1,r,:]) - L(rgb[b,r,:]) for b < B, L = log-brightness of the
+ * gray value (C==3: 0.299/0.587/0.114, utils/img_utils.py:13-16); log_mode 0 = log(x+1e-9)
+ * (BeNeRF_*), 1 = lin-log on 255x (E2NeRF_*), utils/math_utils.py:4-23.  B = 1 is the training
+ * pair of train.py:166-173; B > 1 serves get_pose_evt(..., seg_num=B+1) renders. */
+int bnrf_event_logdiff(const float* rgb /*device [B+1,R,C]*/, int B, int64_t R, int C, int log_mode,
+                       float* out /*device [B,R]*/, void* stream);
+/* Scatter-add polarities into a float64 image (utils/event_utils.py:247-259; float64 per Q10).
+ * x, y device int32 [E]; pol device float [E]; out device double [H,W], NOT cleared here. */
+int bnrf_accumulate_events(const int32_t* x, const int32_t* y, const float* pol, int64_t E,
+                           int H, int W, double* out, void* stream);
+
+/* Bring-up probe (tests only): D[128,N] = A[128,64] * B[N,64]^T through the same shared-memory
+ * swizzle, UMMA descriptors, tcgen05.mma and tcgen05.ld helpers as the MLP kernel.  A, B device
+ * fp16 row-major; D device fp32 [128,N]; lbo_field = raw 14-bit leading-byte-offset field. */
+int bnrf_debug_umma_probe(const void* A_half, const void* B_half, int N, int lbo_field, float* D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BENERF_B200_H */

@@ -1,0 +1,140 @@
+"""Stage-level parity: each C-ABI operator against the oracle function / golden vector it replaces.
+
+Tolerances (fp32 path, north_star bound is 1e-4 max-abs on the rendered tensors):
+  poses 2e-6, rays 1e-6, depths exact-ish 1e-7, raw MLP outputs 2e-5 (tensor cores, 3-MMA fp16 split)
+  / 5e-6 (SIMT fp32), composites 1e-5.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pose, rays, mlp, composite, resample
+from tests.cases import CASES, make_inputs, load_golden
+from tests.gpu_util import DEV, to_dev, make_engine, max_abs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fn():
+    return load_golden("functions")
+
+
+@pytest.fixture(scope="module")
+def eng3():
+    return make_engine(CASES["unreal_rgb"], "simt")
+
+
+def test_spline_poses_match_reference_vectors(fn, eng3):
+    ts = fn["spline_ts"].to(DEV)
+    for s in range(3):
+        knots = fn[f"spline_knots_{s}"].to(DEV).contiguous()
+        got = eng3.spline_poses(knots, None, ts, "spline")
+        assert max_abs(got, fn[f"spline_cubic_{s}"]) < 2e-6
+        got = eng3.spline_poses(knots, None, ts, "linear")
+        assert max_abs(got, fn[f"spline_linear_{s}"]) < 2e-6
+    assert torch.equal(ts.cpu(), fn["spline_ts"]), "ts must not be modified in place"
+
+
+def test_spline_transform_is_added_in_se3(eng3):
+    case = CASES["e2nerf_syn"]
+    inp, gold = make_inputs(case), load_golden("e2nerf_syn")
+    ts = torch.linspace(case.exposure[0], case.exposure[1], case.n_poses).to(DEV)
+    got = eng3.spline_poses(inp["knots"].to(DEV), inp["transform"].reshape(6).to(DEV), ts, "spline")
+    assert max_abs(got, gold["poses_rgb"]) < 2e-6
+
+
+def test_rays_ndc_viewdirs(fn, eng3):
+    H, W, f = 12, 20, 15.0
+    K = torch.tensor([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=torch.float32)
+    idx = torch.arange(H * W, device=DEV)
+    o, d, v = eng3.op_rays(fn["rays_pose"][None].to(DEV).contiguous(), idx, H, W, K)
+    assert max_abs(o, fn["rays_o_ndc"].reshape(-1, 3)) < 1e-6
+    assert max_abs(d, fn["rays_d_ndc"].reshape(-1, 3)) < 1e-6
+    want_v = fn["rays_d"].reshape(-1, 3) / fn["rays_d"].reshape(-1, 3).norm(dim=-1, keepdim=True)
+    assert max_abs(v, want_v) < 1e-6
+
+
+def test_rays_pose_major_order_and_remap(eng3):
+    case = CASES["unreal_rgb"]
+    inp = make_inputs(case)
+    poses = pose.poses_from_knots(inp["knots"], None, 0.1, 0.9, 5)
+    want_o, want_d, want_v = rays.ray_batch(poses, inp["idx_evt"], case.H, case.W, torch.tensor(case.K, dtype=torch.float32))
+    o, d, v = eng3.op_rays(poses.to(DEV).contiguous(), inp["idx_evt"].to(DEV), case.H, case.W, case.K)
+    assert max_abs(o, want_o) < 1e-6 and max_abs(d, want_d) < 1e-6 and max_abs(v, want_v) < 1e-6
+    # TUM-VIE style LUT (model/nerf.py:247-250): identity LUT shifted by half a pixel
+    jj, ii = torch.meshgrid(torch.arange(case.H), torch.arange(case.W), indexing="ij")
+    remap = torch.stack([ii + 0.5, jj - 0.25], -1).float()
+    want_o, want_d, _ = rays.ray_batch(poses, inp["idx_evt"], case.H, case.W, torch.tensor(case.K, dtype=torch.float32), remap=remap)
+    o, d, _ = eng3.op_rays(poses.to(DEV).contiguous(), inp["idx_evt"].to(DEV), case.H, case.W, case.K, remap=remap.to(DEV).contiguous())
+    assert max_abs(o, want_o) < 1e-6 and max_abs(d, want_d) < 1e-6
+
+
+def test_stratified_depths(eng3):
+    t_rand = torch.rand(37, 64, generator=torch.Generator().manual_seed(3))
+    want = rays.stratified_depths(37, 64, t_rand)
+    got = eng3.op_stratified(t_rand.to(DEV))
+    assert max_abs(got, want) <= 6e-8
+
+
+@pytest.mark.parametrize("C", [3, 1])
+def test_composite_matches_reference_vectors(fn, C):
+    case = CASES["unreal_rgb" if C == 3 else "gray_linear"]
+    eng = make_engine(case, "simt")
+    got = eng.op_composite(*[fn[f"r2o{C}_{k}"].to(DEV).contiguous() for k in ("raw", "z", "d", "noise")])
+    for key in ("rgb_map", "acc_map", "weights", "depth_map", "sigma"):
+        assert max_abs(got[key], fn[f"r2o{C}_{key}"]) < 1e-5, key
+    d_got, d_want = got["disp_map"].cpu(), fn[f"r2o{C}_disp_map"]
+    assert torch.equal(torch.isnan(d_got), torch.isnan(d_want))
+    ok = ~torch.isnan(d_want)
+    assert ((d_got[ok] - d_want[ok]).abs() / d_want[ok].abs().clamp_min(1.0)).max() < 1e-4
+
+
+def test_resample_matches_oracle_including_degenerate_rows(fn, eng3):
+    g = torch.Generator().manual_seed(5)
+    n = 48
+    z = rays.stratified_depths(n, 64, torch.rand(n, 64, generator=g))
+    w = torch.rand(n, 64, generator=g) ** 8
+    w[:4] = 0.0                      # all-zero weights: uniform pdf from the 1e-5 floor
+    w[4:8, 10:] = 0.0                # long flat tail: denom < 1e-5 guard
+    u = torch.rand(n, 64, generator=g)
+    want = resample.fine_depths(z, w, u)
+    got = eng3.op_resample(z.to(DEV), w.to(DEV).contiguous(), u.to(DEV))
+    assert got.shape == (n, 128)
+    assert bool((got[:, 1:] >= got[:, :-1]).all()), "fine depths must be sorted"
+    assert max_abs(got, want) < 2e-6
+
+
+@pytest.mark.parametrize("mode,tol", [("simt", 5e-6), ("tc", 2e-5)])
+@pytest.mark.parametrize("name", ["unreal_rgb", "gray_linear"])
+def test_mlp_raw_outputs(name, mode, tol):
+    case = CASES[name]
+    inp, gold = make_inputs(case), load_golden(name)
+    eng = make_engine(case, mode)
+    eng.set_weights(0, to_dev(inp["coarse"]))
+    eng.set_weights(1, to_dev(inp["fine"]))
+    poses = gold["poses_rgb"]
+    o, d, v = rays.ray_batch(poses, inp["idx_rgb"], case.H, case.W, torch.tensor(case.K, dtype=torch.float32))
+    for net, zkey, rkey in ((0, "rgb_z_c", "rgb_raw_c"), (1, "rgb_z_f", "rgb_raw_f")):
+        raw = eng.op_mlp(net, o.to(DEV), d.to(DEV), v.to(DEV), gold[zkey].to(DEV).contiguous())
+        err = max_abs(raw, gold[rkey])
+        print(f"{name} {mode} net{net}: raw max-abs err {err:.3e} (|raw| max {gold[rkey].abs().max():.3f})")
+        assert err < tol
+
+
+def test_mlp_tail_tile_and_odd_sample_count():
+    """rows not a multiple of the 128/64-row tiles; S = 48 (rays straddle tiles)."""
+    case = CASES["unreal_rgb"]
+    inp = make_inputs(case)
+    g = torch.Generator().manual_seed(9)
+    n, S = 7, 48
+    o = torch.rand(n, 3, generator=g) * 2 - 1
+    d = torch.rand(n, 3, generator=g) * 2 - 1
+    v = d / d.norm(dim=-1, keepdim=True)
+    z = torch.sort(torch.rand(n, S, generator=g), -1)[0]
+    want = mlp.mlp_forward(inp["coarse"], rays.sample_points(o, d, z), v)
+    for mode, tol in (("simt", 5e-6), ("tc", 2e-5)):
+        eng = make_engine(case, mode)
+        eng.set_weights(0, to_dev(inp["coarse"]))
+        raw = eng.op_mlp(0, o.to(DEV), d.to(DEV), v.to(DEV), z.to(DEV))
+        assert max_abs(raw, want) < tol, mode
