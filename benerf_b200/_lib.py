@@ -23,7 +23,7 @@ class Cfg(C.Structure):
 
 class Rng(C.Structure):
     _fields_ = [("t_rand", C.c_void_p), ("noise_c", C.c_void_p), ("u", C.c_void_p), ("noise_f", C.c_void_p),
-                ("seed", C.c_uint64), ("offset", C.c_uint64)]
+                ("z_fine", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64)]
 
 
 class Outputs(C.Structure):
@@ -54,6 +54,8 @@ PROTOTYPES = {
     "bnrf_blur_mean": (_I, [_P, _I, _L, _I, _P, _P]),
     "bnrf_event_logdiff": (_I, [_P, _I, _L, _I, _I, _P, _P]),
     "bnrf_accumulate_events": (_I, [_P, _P, _P, _L, _I, _I, _P, _P]),
+    "bnrf_profile": (_I, [_P, _I]),
+    "bnrf_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "bnrf_debug_umma_probe": (_I, [_P, _P, _I, _I, _P, _P]),
 }
 

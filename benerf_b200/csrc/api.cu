@@ -122,6 +122,8 @@ static Workspace carve(const bnrf_cfg& c, int64_t n, void* base) {
 static int run_mlp(bnrf_ctx* ctx, int net, const float* o, const float* d, const float* vb, const float* z, int64_t n,
                    int S, float* raw, cudaStream_t st) {
     if (!ctx->net[net].ready) return fail(ctx, BNRF_ERR_STATE, "weights of network %d not set (bnrf_set_weights)", net);
+    const double macs = 63.0 * 256 + 4 * 65536.0 + 319.0 * 256 + 2 * 65536.0 + 256 + 65536.0 + 283.0 * 128 + 128.0 * ctx->cfg.channels;
+    MlpTimer timer(ctx, st, 2.0 * macs * (double)n * (double)S);
     if (ctx->cfg.mlp_mode == BNRF_MLP_SIMT_FP32) return launch_mlp_simt(ctx, net, o, d, vb, z, n, S, raw, st);
     return launch_mlp_tc(ctx, net, o, d, vb, z, n, S, raw, st);
 }
@@ -183,7 +185,33 @@ void bnrf_destroy(bnrf_ctx* ctx) {
     cudaSetDevice(ctx->device);
     for (int n = 0; n < 2; ++n) free_net(ctx, n);
     cudaFree(ctx->t_vals); cudaFree(ctx->tile_counter); cudaFree(ctx->err_flag);
+    if (ctx->prof_ev[0]) for (int i = 0; i < 2 * 512; ++i) cudaEventDestroy(ctx->prof_ev[i]);
     delete ctx;
+}
+
+int bnrf_profile(bnrf_ctx* ctx, int enable) {
+    if (!ctx) return BNRF_ERR_ARG;
+    if (enable && !ctx->prof_ev[0])
+        for (int i = 0; i < 2 * 512; ++i) BNRF_CUDA(ctx, cudaEventCreate(&ctx->prof_ev[i]));
+    ctx->prof_enabled = enable ? 1 : 0;
+    if (enable) { ctx->prof_used = 0; ctx->prof_flops = 0.0; ctx->launches = 0; }
+    return BNRF_OK;
+}
+
+int bnrf_profile_read(bnrf_ctx* ctx, double* mlp_ms, int64_t* mlp_timed, double* mlp_flops, int64_t* launches) {
+    if (!ctx) return BNRF_ERR_ARG;
+    double total = 0.0;
+    for (int i = 0; i < ctx->prof_used; ++i) {
+        BNRF_CUDA(ctx, cudaEventSynchronize(ctx->prof_ev[2 * i + 1]));
+        float ms = 0.f;
+        BNRF_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+        total += ms;
+    }
+    if (mlp_ms) *mlp_ms = total;
+    if (mlp_timed) *mlp_timed = ctx->prof_used;
+    if (mlp_flops) *mlp_flops = ctx->prof_flops;
+    if (launches) *launches = ctx->launches;
+    return BNRF_OK;
 }
 
 int bnrf_set_sample_grid(bnrf_ctx* ctx, const float* t_vals_host, int S, void* stream) {
@@ -235,7 +263,11 @@ int bnrf_render_forward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_id
                                fine ? out->acc0 : out->acc_map, w.w_c, fine ? nullptr : out->depth_map,
                                fine ? nullptr : out->sigma, st))) return rc;
     if (!fine) return BNRF_OK;
-    if ((rc = launch_resample(ctx, w.z_c, w.w_c, r.u, &r, n, Sc, c.n_importance, w.z_f, st))) return rc;
+    if (r.z_fine) {
+        BNRF_CUDA(ctx, cudaMemcpyAsync(w.z_f, r.z_fine, (size_t)n * Sf * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else if ((rc = launch_resample(ctx, w.z_c, w.w_c, r.u, &r, n, Sc, c.n_importance, w.z_f, st))) {
+        return rc;
+    }
     if ((rc = launch_viewbias(ctx, 1, w.view, n, w.vb, st))) return rc;
     if ((rc = run_mlp(ctx, 1, w.o, w.d, w.vb, w.z_f, n, Sf, w.raw, st))) return rc;
     return launch_composite(ctx, w.raw, w.z_f, w.d, r.noise_f, &r, kStreamNoiseF, n, Sf, out->rgb_map, out->disp_map,

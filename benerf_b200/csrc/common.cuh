@@ -49,6 +49,12 @@ struct bnrf_ctx {
     float* t_vals;            // device [n_samples] sampling grid (linspace(0,1,S) by default)
     int* tile_counter;        // device scratch for the persistent tile scheduler
     unsigned int* err_flag;   // device: set by kernels on watchdog timeout
+    // measurement hooks (bnrf_profile)
+    int prof_enabled;
+    int prof_used;
+    cudaEvent_t prof_ev[2 * 512];
+    double prof_flops;
+    long long launches;
     char err[512];
 };
 
@@ -66,7 +72,19 @@ int fail(bnrf_ctx* ctx, int code, const char* fmt, ...);
                               cudaGetErrorString(e__), __FILE__, __LINE__);               \
     } while (0)
 
-#define BNRF_LAUNCH_CHECK(ctx) BNRF_CUDA(ctx, cudaGetLastError())
+#define BNRF_LAUNCH_CHECK(ctx) do { (ctx)->launches++; BNRF_CUDA(ctx, cudaGetLastError()); } while (0)
+
+struct MlpTimer {      // brackets one MLP launch with events when profiling is on
+    bnrf_ctx* ctx; cudaStream_t st; int slot;
+    MlpTimer(bnrf_ctx* c, cudaStream_t s, double flops) : ctx(c), st(s), slot(-1) {
+        if (c->prof_enabled && c->prof_used < 512) {
+            slot = c->prof_used++;
+            c->prof_flops += flops;
+            cudaEventRecord(c->prof_ev[2 * slot], st);
+        }
+    }
+    ~MlpTimer() { if (slot >= 0) cudaEventRecord(ctx->prof_ev[2 * slot + 1], st); }
+};
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -90,6 +90,15 @@ class Engine:
         arr = (C.c_float * t.numel())(*t.tolist())
         self._check(self.lib.bnrf_set_sample_grid(self._ctx, arr, t.numel(), _stream()), "bnrf_set_sample_grid")
 
+    # -- measurement hooks --------------------------------------------------------------
+    def profile(self, enable=True):
+        self._check(self.lib.bnrf_profile(self._ctx, int(enable)), "bnrf_profile")
+
+    def profile_read(self):
+        ms, timed, flops, launches = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
+        self._check(self.lib.bnrf_profile_read(self._ctx, C.byref(ms), C.byref(timed), C.byref(flops), C.byref(launches)), "bnrf_profile_read")
+        return {"mlp_ms": ms.value, "mlp_timed": timed.value, "mlp_flops": flops.value, "launches": launches.value}
+
     # -- a1/a2 ----------------------------------------------------------------------------
     def spline_poses(self, knots, transform, ts, traj="spline"):
         P = ts.numel()
@@ -117,11 +126,12 @@ class Engine:
                 ret["sigma"] = new(n, Sf)
         depth = new(n) if want_depth else None
         outs = _lib.Outputs(*[_ptr(ret.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0", "sigma")], _ptr(depth))
-        r = _lib.Rng(None, None, None, None, int(seed), int(offset))
+        r = _lib.Rng(None, None, None, None, None, int(seed), int(offset))
         if rng is not None:
             r.t_rand, r.noise_c = _ptr(rng["t_rand"], name="t_rand"), _ptr(rng["noise_c"], name="noise_c")
             if self.n_importance > 0:
                 r.u, r.noise_f = _ptr(rng["u"], name="u"), _ptr(rng["noise_f"], name="noise_f")
+                r.z_fine = _ptr(rng.get("z_fine"), name="z_fine")        # parity-only override, see benerf_b200.h
         need = self.lib.bnrf_workspace_bytes(self._ctx, n)
         if self._workspace is None or self._workspace.numel() < need:
             self._workspace = torch.empty(need, device=self.device, dtype=torch.uint8)

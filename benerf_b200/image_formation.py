@@ -1,0 +1,34 @@
+"""Image formation of the blur and event models (train.py:163-177,205-331) on the CUDA library.
+
+blur_mean / event_logdiff / accumulate_events are the C-ABI kernels (csrc/image_formation.cu).
+The two scalar losses are tiny reductions over [R] tensors done with torch ops on the device,
+laid out exactly as the reference's loss block so a training loop can call them in its place.
+"""
+import torch
+
+from .engine import blur_mean, event_logdiff, accumulate_events, LOG_MODE  # noqa: F401
+
+
+def mse(a, b):
+    """loss/imgloss.py:3-5."""
+    return torch.mean((a - b) ** 2)
+
+
+def event_loss(diff, target, event_threshold, event_coeff_syn=0.1, event_coeff_real=2.0):
+    """One level of train.py:207-292.  diff [R,1] fp32, target [R,1] float64 (Q10)."""
+    if event_threshold > 0:
+        return mse(diff, target * event_threshold) * event_coeff_syn
+    dn = diff / (torch.linalg.norm(diff, dim=0, keepdim=True) + 1e-9)
+    tn = target / (torch.linalg.norm(target, dim=0, keepdim=True) + 1e-9)
+    return mse(dn, tn) * event_coeff_real
+
+
+def accumulate_events_on_gpu(out, xs, ys, ps, device="cuda"):
+    """Signature of utils/event_utils.py:247-259: numpy x/y/polarity of the window -> float64 [H,W]."""
+    import numpy as np
+    H, W = out.shape
+    x = torch.as_tensor(np.asarray(xs), dtype=torch.int32, device=device)
+    y = torch.as_tensor(np.asarray(ys), dtype=torch.int32, device=device)
+    p = torch.as_tensor(np.asarray(ps), dtype=torch.float32, device=device)
+    base = torch.as_tensor(out, dtype=torch.float64, device=device).clone()
+    return accumulate_events(x, y, p, H, W, out=base)

@@ -1,0 +1,176 @@
+"""Mirror of model/nerf.py: NeRF (parameter holder), Graph (forward / render / render_video).
+
+The modules own the same parameters under the same names as the reference, so state dicts,
+optimisers and init_nerf work unchanged; the arithmetic of NeRF.forward / raw2output /
+Graph.render is not here but in libbenerf_b200.so (bnrf_render_forward).
+"""
+import abc
+from datetime import datetime
+
+import numpy as np
+import torch
+from torch import nn
+
+from .engine import Engine
+from . import image_formation
+
+
+class Model:
+    @abc.abstractmethod
+    def build_network(self, args, poses=None, event_poses=None):
+        pass
+
+    @abc.abstractmethod
+    def setup_optimizer(self, args):
+        pass
+
+    def after_train(self):
+        print(f"Successfully finished model on {datetime.now()}")
+
+
+class NeRF(nn.Module):
+    """model/nerf.py:40-64: the 12 linears.  forward()/raw2output() live in the CUDA library."""
+
+    def __init__(self, D=8, W=256, input_ch=63, input_ch_views=27, output_ch=4, skips=[4], use_viewdirs=False, channels=3):
+        super().__init__()
+        if (D, W, input_ch, input_ch_views, list(skips), use_viewdirs) != (8, 256, 63, 27, [4], True):
+            raise ValueError("benerf_b200 implements the architecture Graph hard-codes (model/optimize.py:9): "
+                             "D=8, W=256, input_ch=63, input_ch_views=27, skips=[4], use_viewdirs=True")
+        self.D, self.W, self.input_ch, self.input_ch_views = D, W, input_ch, input_ch_views
+        self.skips, self.use_viewdirs, self.channels = skips, use_viewdirs, channels
+        self.pts_linears = nn.ModuleList(
+            [nn.Linear(input_ch, W)] + [nn.Linear(W, W) if i not in skips else nn.Linear(W + input_ch, W) for i in range(D - 1)])
+        self.views_linears = nn.ModuleList([nn.Linear(input_ch_views + W, W // 2)])
+        self.feature_linear = nn.Linear(W, W)
+        self.alpha_linear = nn.Linear(W, 1)
+        self.rgb_linear = nn.Linear(W // 2, channels)
+
+    def forward(self, *a, **k):
+        raise RuntimeError("NeRF.forward is fused into bnrf_render_forward; call Graph.render")
+
+
+class Graph(nn.Module):
+    def __init__(self, args, D=8, W=256, input_ch=63, input_ch_views=27, output_ch=4, skips=[4], use_viewdirs=False):
+        super().__init__()
+        self.nerf = NeRF(D, W, input_ch, input_ch_views, output_ch, skips, use_viewdirs, args.channels)
+        self.channels = args.channels
+        if args.N_importance > 0:
+            self.nerf_fine = NeRF(D, W, input_ch, input_ch_views, output_ch, skips, use_viewdirs, args.channels)
+        self.pose_eye = torch.eye(3, 4)
+        self._engine = None
+        self._render_calls = 0
+        self._seed = int(getattr(args, "seed", 0) or 0)
+        self._events_dev = None
+
+    # ------------------------------------------------------------------------------------
+    def engine(self, args):
+        if self._engine is None:
+            if not getattr(args, "ndc", True) or not args.use_viewdirs or getattr(args, "use_barf_c2f", False):
+                raise ValueError("benerf_b200 covers the configuration every shipped config uses: ndc=True, "
+                                 "use_viewdirs=True, use_barf_c2f=False")
+            self._engine = Engine(n_samples=args.N_samples, n_importance=args.N_importance, channels=args.channels,
+                                  mlp_mode=getattr(args, "mlp_mode", "tc"))
+        return self._engine
+
+    def _sync(self, eng):
+        eng.sync_weights(0, self.nerf)
+        if hasattr(self, "nerf_fine"):
+            eng.sync_weights(1, self.nerf_fine)
+
+    # ------------------------------------------------------------------------------------
+    def forward(self, iter_step, events, rgb_exp_ts, H, W, K, K_event, args, img_xy_remap, evt_xy_remap):
+        """model/nerf.py:160-234: pick an event window, accumulate it, interpolate the two pose sets,
+        render the event pair and the N-pose blur batch."""
+        dev = self.engine(args).device
+        ts_all = events["ts"]
+        if args.event_time_window:
+            window_t = args.accumulate_time_length
+            if args.random_sampling_window:
+                low_t = np.random.rand(1) * (1 - window_t)
+                upper_t = low_t + window_t
+            else:
+                low_t = np.random.randint((1 - window_t) // window_t) * window_t
+                upper_t = np.min((low_t + window_t, 1.0))
+            # events are time-sorted: the closed window [low, up] (Q16) is one contiguous slice
+            lo = int(np.searchsorted(ts_all, float(np.asarray(low_t).reshape(-1)[0]), side="left"))
+            hi = int(np.searchsorted(ts_all, float(np.asarray(upper_t).reshape(-1)[0]), side="right"))
+            events_ts = np.stack((low_t, upper_t)).reshape(2)
+        else:
+            num = len(events["pol"])
+            N_window = round(num * args.accumulate_time_length)
+            if args.random_sampling_window:
+                lo = np.random.randint(num - N_window)
+            else:
+                lo = np.random.randint((num - N_window) // N_window) * N_window
+            hi = int(lo + N_window)
+            events_ts = ts_all[np.array([lo, hi - 1])]
+        ev = self._device_events(events, dev, args)
+        events_accu = image_formation.accumulate_events(ev["x"][lo:hi], ev["y"][lo:hi], ev["pol"][lo:hi],
+                                                        args.event_height, args.event_width)
+        spline_evt_poses = self.get_pose_evt(args, torch.tensor(events_ts, dtype=torch.float32))
+        spline_rgb_poses = self.get_pose_rgb(args, torch.tensor(rgb_exp_ts, dtype=torch.float32))
+        ray_idx_event = torch.randperm(args.event_height * args.event_width, device=dev)[:args.sampling_event_rays]
+        ret_event = self.render(iter_step, spline_evt_poses, ray_idx_event, args.event_height, args.event_width,
+                                K_event, args, enable_crf=True, sensor_type="event", remap=evt_xy_remap, training=True)
+        ray_idx_rgb = torch.randperm(H * W, device=dev)[:args.sampling_rgb_rays // args.num_interpolated_pose]
+        ret_rgb = self.render(iter_step, spline_rgb_poses, ray_idx_rgb, H, W, K, args, enable_crf=True,
+                              sensor_type="rgb", remap=img_xy_remap, training=True)
+        return ret_event, ret_rgb, ray_idx_event, ray_idx_rgb, events_accu
+
+    def _device_events(self, events, dev, args):
+        """Keep the (sorted) event arrays resident on the device instead of masking + uploading the
+        window every iteration (model/nerf.py:162-199)."""
+        key = id(events["ts"])
+        if self._events_dev is None or self._events_dev[0] != key:
+            pol = np.asarray(events["pol"], dtype=np.float32).copy()
+            if args.dataset == "TUM_VIE":
+                pol[pol == 0] = -1                      # 0 = negative polarity in TUM-VIE (model/nerf.py:194-196)
+            self._events_dev = (key, {
+                "x": torch.as_tensor(np.asarray(events["x"]), dtype=torch.int32, device=dev),
+                "y": torch.as_tensor(np.asarray(events["y"]), dtype=torch.int32, device=dev),
+                "pol": torch.as_tensor(pol, device=dev)})
+        return self._events_dev[1]
+
+    # ------------------------------------------------------------------------------------
+    def render(self, iter_step, poses, ray_idx, H, W, K, args, enable_crf: bool, sensor_type: str, remap,
+               near=0., far=1., training=False, rng=None):
+        """model/nerf.py:236-343.  Returns {'rgb_map','disp_map','acc_map'} (+ 'rgb0','disp0','acc0','sigma'
+        when N_importance > 0), pose-major.  training/eval produce identical rays upstream and
+        share one path here.  enable_crf / sensor_type are accepted and ignored exactly as upstream
+        (model/nerf.py:127-131).  rng (keyword-only extension): dict of the four draws for parity runs."""
+        eng = self.engine(args)
+        if (near, far) != (0., 1.):
+            raise ValueError("Graph.render is only ever called with near=0, far=1 upstream (model/nerf.py:239)")
+        self._sync(eng)
+        dev = eng.device
+        poses = poses[:, :3, :4].to(device=dev, dtype=torch.float32).contiguous()
+        ray_idx = torch.as_tensor(ray_idx).reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
+        use_remap = args.dataset == "TUM_VIE" and remap is not None
+        remap_t = torch.as_tensor(remap, dtype=torch.float32, device=dev).contiguous() if use_remap else None
+        self._render_calls += 1
+        return eng.render(poses, ray_idx, H, W, np.asarray(K.cpu() if isinstance(K, torch.Tensor) else K, dtype=np.float32),
+                          remap=remap_t, rng=rng, seed=self._seed, offset=self._render_calls)
+
+    @torch.no_grad()
+    def render_video(self, iter_step, poses, H, W, K, args, remap, type):
+        """model/nerf.py:353-390: full-image render, chunked by args.chunk rays; returns [H,W,...] maps."""
+        all_ret = {}
+        ray_idx = torch.arange(0, H * W)
+        if str(type) not in ("radience", "rgb"):
+            raise ValueError(type)
+        for i in range(0, ray_idx.shape[0], args.chunk):
+            ret = self.render(iter_step, poses, ray_idx[i:i + args.chunk], H, W, K, args, enable_crf=(str(type) == "rgb"),
+                              sensor_type=("rgb" if str(type) == "rgb" else None), remap=remap, training=False)
+            for k in ret:
+                all_ret.setdefault(k, []).append(ret[k])
+        for k in all_ret:
+            all_ret[k] = torch.cat(all_ret[k], 0).reshape([H, W] + list(all_ret[k][0].shape[1:]))
+        return all_ret
+
+    @abc.abstractmethod
+    def get_pose_evt(self, args, events_ts, seg_num=None):
+        pass
+
+    @abc.abstractmethod
+    def get_pose_rgb(self, args, exposure_ts, seg_num=None):
+        pass

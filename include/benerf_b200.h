@@ -77,6 +77,12 @@ typedef struct {
     const float* noise_c;  /* device [N, S_c]       N(0,1)  model/nerf.py:135 */
     const float* u;        /* device [N, N_i]       U[0,1)  run_nerf_helpers.py:86 */
     const float* noise_f;  /* device [N, S_c + N_i] N(0,1)  model/nerf.py:135 */
+    /* Parity-only override: device [N, S_c + N_i] sorted fine depths to use INSTEAD of resampling
+     * (model/nerf.py:322-326).  The reference's inverse-CDF step divides fp32 rounding noise of its
+     * cdf by the bin mass, so two valid fp32 evaluations of the coarse pass pick fine depths that
+     * differ by up to 1e-4 in near-empty bins (DESIGN.md "conditioning"); injecting the reference's
+     * depths lets the fine network be compared on identical samples.  NULL in production. */
+    const float* z_fine;
     uint64_t seed, offset;
 } bnrf_rng;
 
@@ -169,6 +175,19 @@ int bnrf_event_logdiff(const float* rgb /*device [B+1,R,C]*/, int B, int64_t R, 
  * x, y device int32 [E]; pol device float [E]; out device double [H,W], NOT cleared here. */
 int bnrf_accumulate_events(const int32_t* x, const int32_t* y, const float* pol, int64_t E,
                            int H, int W, double* out, void* stream);
+
+/* -------------------------------------------------------------------------------------- */
+/* measurement hooks (bench.py): CUDA-event timing of the dominant kernel on its own stream */
+
+/* enable != 0: every MLP kernel launched through this context is bracketed by a cudaEvent pair
+ * on the launching stream (up to 512 launches; later ones are counted but not timed).  Resets the
+ * counters.  enable == 0 stops recording. */
+int bnrf_profile(bnrf_ctx* ctx, int enable);
+/* Synchronises the recorded events and returns: summed device time of the timed MLP launches (ms),
+ * how many were timed, their summed ALGORITHMIC flops (2 * MACs of the reference's linears, SURVEY
+ * 8-d: 593,408 MAC/sample for C=3), and the number of kernel launches of any kind issued through
+ * the context since bnrf_profile(ctx, 1). */
+int bnrf_profile_read(bnrf_ctx* ctx, double* mlp_ms, int64_t* mlp_timed, double* mlp_flops, int64_t* launches);
 
 /* Bring-up probe (tests only): D[128,N] = A[128,64] * B[N,64]^T through the same shared-memory
  * swizzle, UMMA descriptors, tcgen05.mma and tcgen05.ld helpers as the MLP kernel.  A, B device

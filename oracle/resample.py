@@ -32,3 +32,25 @@ def fine_depths(z_coarse, weights, u):
     extra = inverse_cdf_samples(mids, weights[..., 1:-1], u).detach()
     z, _ = torch.sort(torch.cat([z_coarse, extra], -1), -1)
     return z
+
+
+def conditioning(z_coarse, weights, u):
+    """Per new sample: (bin mass, bin width) of the inverse-CDF bin it is drawn from.
+
+    t = (u - cdf_lo) / mass: an fp32 rounding difference eps (~6e-8, one ulp of a cdf value) between
+    two valid evaluations of the coarse pass moves the sample by eps / mass * width.  With the 1e-5
+    weight floor, empty-space bins have mass ~2e-5, i.e. an amplification of ~3000: the reference's
+    fine depths are only reproducible to ~1e-4 there (and the 2^9 positional-encoding frequency
+    multiplies that again).  Parity harnesses use this to bound / flag such samples explicitly.
+    Returns (mass [N,K], width [N,K]).
+    """
+    mids = 0.5 * (z_coarse[..., 1:] + z_coarse[..., :-1])
+    w = weights[..., 1:-1] + 1e-5
+    pdf = w / torch.sum(w, -1, keepdim=True)
+    cdf = torch.cat([torch.zeros_like(pdf[..., :1]), torch.cumsum(pdf, -1)], -1)
+    inds = torch.searchsorted(cdf, u.contiguous(), right=True)
+    below = torch.clamp(inds - 1, min=0)
+    above = torch.clamp(inds, max=cdf.shape[-1] - 1)
+    mass = torch.gather(cdf, 1, above) - torch.gather(cdf, 1, below)
+    width = torch.gather(mids, 1, above) - torch.gather(mids, 1, below)
+    return mass, width
