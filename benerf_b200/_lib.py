@@ -27,7 +27,7 @@ class Rng(C.Structure):
 
 
 class Outputs(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0", "sigma", "depth_map")]
+    _fields_ = [(k, C.c_void_p) for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0", "sigma", "depth_map", "z_vals")]
 
 
 class BackwardGrads(C.Structure):
@@ -56,6 +56,7 @@ PROTOTYPES = {
     "bnrf_accumulate_events": (_I, [_P, _P, _P, _L, _I, _I, _P, _P]),
     "bnrf_profile": (_I, [_P, _I]),
     "bnrf_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "bnrf_debug_mlp_trace": (_I, [_P, _P]),
     "bnrf_debug_umma_probe": (_I, [_P, _P, _I, _I, _P, _P]),
 }
 

@@ -214,6 +214,12 @@ int bnrf_profile_read(bnrf_ctx* ctx, double* mlp_ms, int64_t* mlp_timed, double*
     return BNRF_OK;
 }
 
+int bnrf_debug_mlp_trace(bnrf_ctx* ctx, unsigned long long* counters) {
+    if (!ctx) return BNRF_ERR_ARG;
+    ctx->trace = counters;
+    return BNRF_OK;
+}
+
 int bnrf_set_sample_grid(bnrf_ctx* ctx, const float* t_vals_host, int S, void* stream) {
     if (!ctx || !t_vals_host || S != ctx->cfg.n_samples) return fail(ctx, BNRF_ERR_ARG, "set_sample_grid: S must equal cfg.n_samples");
     BNRF_CUDA(ctx, cudaMemcpyAsync(ctx->t_vals, t_vals_host, S * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
@@ -262,12 +268,16 @@ int bnrf_render_forward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_id
                                fine ? out->rgb0 : out->rgb_map, fine ? out->disp0 : out->disp_map,
                                fine ? out->acc0 : out->acc_map, w.w_c, fine ? nullptr : out->depth_map,
                                fine ? nullptr : out->sigma, st))) return rc;
-    if (!fine) return BNRF_OK;
+    if (!fine) {
+        if (out->z_vals) BNRF_CUDA(ctx, cudaMemcpyAsync(out->z_vals, w.z_c, (size_t)n * Sc * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return BNRF_OK;
+    }
     if (r.z_fine) {
         BNRF_CUDA(ctx, cudaMemcpyAsync(w.z_f, r.z_fine, (size_t)n * Sf * sizeof(float), cudaMemcpyDeviceToDevice, st));
     } else if ((rc = launch_resample(ctx, w.z_c, w.w_c, r.u, &r, n, Sc, c.n_importance, w.z_f, st))) {
         return rc;
     }
+    if (out->z_vals) BNRF_CUDA(ctx, cudaMemcpyAsync(out->z_vals, w.z_f, (size_t)n * Sf * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if ((rc = launch_viewbias(ctx, 1, w.view, n, w.vb, st))) return rc;
     if ((rc = run_mlp(ctx, 1, w.o, w.d, w.vb, w.z_f, n, Sf, w.raw, st))) return rc;
     return launch_composite(ctx, w.raw, w.z_f, w.d, r.noise_f, &r, kStreamNoiseF, n, Sf, out->rgb_map, out->disp_map,

@@ -49,6 +49,7 @@ struct bnrf_ctx {
     float* t_vals;            // device [n_samples] sampling grid (linspace(0,1,S) by default)
     int* tile_counter;        // device scratch for the persistent tile scheduler
     unsigned int* err_flag;   // device: set by kernels on watchdog timeout
+    unsigned long long* trace; // device [sm_count][16] stall counters of the last MLP launch, or NULL (bnrf_debug_mlp_trace)
     // measurement hooks (bnrf_profile)
     int prof_enabled;
     int prof_used;

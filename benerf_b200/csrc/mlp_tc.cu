@@ -13,13 +13,15 @@
 // TMEM (the lo*lo term is below 2^-22 relative).  Weights are pre-scaled by a per-layer power
 // of two so that their lo halves stay in the fp16 normal range; the epilogue undoes it.
 //
-// Warp roles (384 threads):
+// Warp roles (512 threads):
 //   warp 0      TMA producer: weight tiles -> smem ring (mbarrier complete_tx)
 //   warp 1      MMA issuer: one thread issues tcgen05.mma, commits to mbarriers; owns TMEM alloc
-//   warps 4-7   epilogue: tcgen05.ld -> scale/bias/ReLU -> fp16 hi/lo -> next layer's A tile;
-//               sigma head (256->1) and rgb head (128->C) as fp32 FFMA on the way through
-//   warps 8-11  front end: pts = o + d*z, sin/cos encoding -> A tile of layer 0 / skip layer,
+//   warps 4-7   front end: pts = o + d*z, sin/cos encoding -> A tile of layer 0 / skip layer,
 //               one tile ahead of the MMA
+//   warps 8-15  epilogue: tcgen05.ld -> scale/bias/ReLU -> fp16 hi/lo -> next layer's A tile;
+//               sigma head (256->1) and rgb head (128->C) as fp32 FFMA on the way through.
+//               Warps w and w+4 share a TMEM lane quarter (32 rows) and split the columns, so each
+//               SM sub-partition runs two epilogue warps (the conversion is latency-bound).
 // Layer boundaries are pipelined per 64-column K-block: the MMA of layer l+1 starts on K-block
 // 0 as soon as the epilogue of layer l has produced it, while the epilogue continues.
 //
@@ -31,9 +33,9 @@ namespace bnrf {
 namespace tc {
 
 constexpr int TILE_M = 128;
-constexpr int NUM_THREADS = 384;
-constexpr int NS = 2;                              // weight ring depth
-constexpr uint32_t STAGE_BYTES = 32768;            // one [256 x 64] fp16 SW128 tile
+constexpr int NUM_THREADS = 512;
+constexpr int NS = 4;                              // weight ring depth
+constexpr uint32_t STAGE_BYTES = 16384;            // one [256 x 32] fp16 SW64 tile (half a K-block of one weight half)
 constexpr uint32_t KBLOCK_BYTES = 16384;           // one [128 x 64] fp16 SW128 A tile
 constexpr uint32_t OFF_A_HI = 0;
 constexpr uint32_t OFF_A_LO = 4 * KBLOCK_BYTES;
@@ -42,13 +44,13 @@ constexpr uint32_t OFF_PE_LO = 9 * KBLOCK_BYTES;
 constexpr uint32_t OFF_W = 10 * KBLOCK_BYTES;
 constexpr uint32_t OFF_BAR = OFF_W + NS * STAGE_BYTES;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
-constexpr int STAGES_PER_TILE = 76;                // 38 K-blocks x (hi, lo)
-constexpr int N256_STAGES = 68;
+constexpr int STAGES_PER_TILE = 152;               // 38 K-blocks x 2 K-halves x (hi, lo)
+constexpr int N256_STAGES = 136;
 constexpr uint32_t TMEM_COLS = 512;
 
 // barrier slots (8 bytes each) inside the barrier block
 enum { BAR_W_FULL = 0, BAR_W_EMPTY = BAR_W_FULL + NS, BAR_PE_FULL = BAR_W_EMPTY + NS, BAR_PE_EMPTY,
-       BAR_A_READY, BAR_ACC_FULL = BAR_A_READY + 4, BAR_COUNT = BAR_ACC_FULL + 2 };
+       BAR_A_READY, BAR_ACC_FULL = BAR_A_READY + 8, BAR_COUNT = BAR_ACC_FULL + 2 };
 
 // ---------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -71,8 +73,9 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* err_flag, unsigned int code) {
     if (mbar_try(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
+    for (uint32_t spins = 1;; ++spins) {
+        if (mbar_try(bar, parity)) return;           // try_wait itself suspends the thread for a HW-defined interval
+        if ((spins & 0xFFFu) == 0 && clock64() - t0 > 4000000000LL) {
             if (err_flag) atomicExch(err_flag, code);
             __trap();
         }
@@ -108,6 +111,41 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Split issue / wait of a 32-column TMEM load: the wait names the registers so that no use can be scheduled above it.
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld16_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
 // SWIZZLE_128B K-major shared-memory descriptor: rows of 128 B, 8-row atoms 1024 B apart.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_field) {
     uint64_t d = 0;
@@ -116,6 +154,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_field
     d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset = 8 rows x 128 B [32,46)
     d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)     [46,48)
     d |= (uint64_t)2 << 61;                        // layout type SWIZZLE_128B           [61,64)
+    return d;
+}
+// SWIZZLE_64B K-major descriptor (weight ring): rows of 64 B, 8-row atoms 512 B apart.
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(512u >> 4) << 32;              // stride byte offset = 8 rows x 64 B
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                        // layout type SWIZZLE_64B
     return d;
 }
 // kind::f16 instruction descriptor: fp16 x fp16 -> fp32, both K-major, M x N
@@ -127,15 +174,19 @@ __host__ __device__ constexpr uint32_t sw128_offset(int row, int k) {
     return (uint32_t)row * 128u + ((((uint32_t)k >> 3) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)k & 7u) * 2u;
 }
 
+// byte offset of element (row, k) inside a [rows x 32] fp16 SW64 tile (16-byte chunk index ^= bits 7-8 of the address)
+__host__ __device__ constexpr uint32_t sw64_offset(int row, int k) {
+    return (uint32_t)row * 64u + ((((uint32_t)k >> 3) ^ (((uint32_t)row >> 1) & 3u)) << 4) + ((uint32_t)k & 7u) * 2u;
+}
+
 __device__ __forceinline__ void split_store8(const float* v, unsigned char* hi_dst, unsigned char* lo_dst) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-        const float2 back = __half22float2(hh);
-        const __half2 ll = __floats2half2_rn(v[2 * i] - back.x, v[2 * i + 1] - back.y);
-        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+        // hi = fp16(v) saturated to the finite range (one F2FP.SATFINITE per pair), lo = fp16(v - hi)
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+        const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l[i]) : "f"(v[2 * i + 1] - back.y), "f"(v[2 * i] - back.x));
     }
     *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -158,7 +209,21 @@ template <int C>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
               const float* __restrict__ viewbias, const float* __restrict__ z, int64_t rows, int S, int num_tiles,
-              float* __restrict__ raw, unsigned int* err_flag) {
+              float* __restrict__ raw, unsigned int* err_flag, unsigned long long* __restrict__ trace) {
+    // trace (debug, normally NULL): per-CTA stall accounting, 16 counters of clock64 cycles --
+    //   0 kernel total   1 mma: wait PE_FULL   2 mma: wait A_READY   3 mma: wait W_FULL   4 mma: loop total
+    //   5 tma: wait W_EMPTY   6 epilogue(warp 4): wait ACC_FULL   7 epilogue: loop total
+    //   8 front end(warp 8): wait PE_EMPTY   9 front end: loop total
+    const long long k_t0 = clock64();
+    auto timed_wait = [&](uint32_t b, uint32_t parity, unsigned int code, unsigned long long& acc) {
+        if (trace) {
+            const long long t = clock64();
+            mbar_wait(b, parity, err_flag, code);
+            acc += (unsigned long long)(clock64() - t);
+        } else {
+            mbar_wait(b, parity, err_flag, code);
+        }
+    };
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -171,7 +236,7 @@ mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restr
         for (int i = 0; i < NS; ++i) { mbar_init(bar(BAR_W_FULL + i), 1); mbar_init(bar(BAR_W_EMPTY + i), 1); }
         mbar_init(bar(BAR_PE_FULL), 128);
         mbar_init(bar(BAR_PE_EMPTY), 1);
-        for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_A_READY + i), 128);
+        for (int i = 0; i < 8; ++i) mbar_init(bar(BAR_A_READY + i), 256);
         for (int i = 0; i < 2; ++i) mbar_init(bar(BAR_ACC_FULL + i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -191,21 +256,25 @@ mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restr
         if (lane == 0) {
             const unsigned char* src = reinterpret_cast<const unsigned char*>(p.stream);
             uint32_t cnt = 0;
+            unsigned long long w_empty = 0;
             for (int it = 0; it < my_tiles; ++it) {
                 for (int i = 0; i < STAGES_PER_TILE; ++i, ++cnt) {
                     const uint32_t slot = cnt % NS, ph = (cnt / NS) & 1u;
-                    mbar_wait(bar(BAR_W_EMPTY + slot), ph ^ 1u, err_flag, 1);
+                    timed_wait(bar(BAR_W_EMPTY + slot), ph ^ 1u, 1, w_empty);
                     const uint32_t bytes = i < N256_STAGES ? STAGE_BYTES : STAGE_BYTES / 2;
                     mbar_expect_tx(bar(BAR_W_FULL + slot), bytes);
                     tma_bulk_load(base + OFF_W + slot * STAGE_BYTES, src + stage_offset_bytes(i), bytes, bar(BAR_W_FULL + slot));
                 }
             }
+            if (trace) trace[blockIdx.x * 16 + 5] = w_empty;
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
             uint32_t wcnt = 0;           // weight stages consumed
             uint32_t agen = 0;           // generation of the a_ready barriers (one per producing epilogue)
+            unsigned long long w_pe = 0, w_a = 0, w_w = 0;
+            const long long m_t0 = clock64();
             for (int it = 0; it < my_tiles; ++it) {
                 for (int t = 0; t < 10; ++t) {
                     const int N = (t == 9) ? 128 : 256;
@@ -217,142 +286,202 @@ mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restr
                     for (int kb = has_pe ? -1 : 0; kb < n_act; ++kb) {
                         uint32_t a_hi, a_lo;
                         if (kb < 0) {
-                            if (t == 0) mbar_wait(bar(BAR_PE_FULL), (uint32_t)it & 1u, err_flag, 2);
+                            if (t == 0) timed_wait(bar(BAR_PE_FULL), (uint32_t)it & 1u, 2, w_pe);
                             a_hi = base + OFF_PE_HI; a_lo = base + OFF_PE_LO;
                         } else {
-                            mbar_wait(bar(BAR_A_READY + kb), agen & 1u, err_flag, 3);
                             a_hi = base + OFF_A_HI + kb * KBLOCK_BYTES; a_lo = base + OFF_A_LO + kb * KBLOCK_BYTES;
                         }
-                        tc_fence_after();
-                        // hi tile of the weights: A_hi * W_hi and A_lo * W_hi
-                        {
-                            const uint32_t slot = wcnt % NS, ph = (wcnt / NS) & 1u;
-                            mbar_wait(bar(BAR_W_FULL + slot), ph, err_flag, 4);
-                            tc_fence_after();
-                            const uint32_t w = base + OFF_W + slot * STAGE_BYTES;
+                        // per K-half (32 columns of the A K-block): the hi weight stage feeds A_hi * W_hi and
+                        // A_lo * W_hi, the lo stage feeds A_hi * W_lo
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                const uint64_t bd = make_desc(w + kk * 32, 0);
-                                tc_mma_f16(d_tmem, make_desc(a_hi + kk * 32, 0), bd, idesc, accumulate);
-                                accumulate = 1;
-                                tc_mma_f16(d_tmem, make_desc(a_lo + kk * 32, 0), bd, idesc, 1);
+                        for (int hk = 0; hk < 2; ++hk) {
+                            if (kb >= 0) {
+                                timed_wait(bar(BAR_A_READY + kb * 2 + hk), agen & 1u, 3, w_a);
+                                if (trace && blockIdx.x == 0 && it == 5 && hk == 0) trace[148 * 16 + t * 8 + 1 + kb] = (unsigned long long)clock64();
                             }
-                            tc_commit(bar(BAR_W_EMPTY + slot));
-                            ++wcnt;
-                        }
-                        // lo tile of the weights: A_hi * W_lo
-                        {
-                            const uint32_t slot = wcnt % NS, ph = (wcnt / NS) & 1u;
-                            mbar_wait(bar(BAR_W_FULL + slot), ph, err_flag, 5);
                             tc_fence_after();
-                            const uint32_t w = base + OFF_W + slot * STAGE_BYTES;
+                            {
+                                const uint32_t slot = wcnt % NS, ph = (wcnt / NS) & 1u;
+                                timed_wait(bar(BAR_W_FULL + slot), ph, 4, w_w);
+                                tc_fence_after();
+                                const uint32_t w = base + OFF_W + slot * STAGE_BYTES;
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                tc_mma_f16(d_tmem, make_desc(a_hi + kk * 32, 0), make_desc(w + kk * 32, 0), idesc, 1);
-                            tc_commit(bar(BAR_W_EMPTY + slot));
-                            ++wcnt;
+                                for (int kk = 0; kk < 2; ++kk) {
+                                    const uint64_t bd = make_desc_sw64(w + kk * 32);
+                                    tc_mma_f16(d_tmem, make_desc(a_hi + (hk * 2 + kk) * 32, 0), bd, idesc, accumulate);
+                                    accumulate = 1;
+                                    tc_mma_f16(d_tmem, make_desc(a_lo + (hk * 2 + kk) * 32, 0), bd, idesc, 1);
+                                }
+                                tc_commit(bar(BAR_W_EMPTY + slot));
+                                ++wcnt;
+                            }
+                            {
+                                const uint32_t slot = wcnt % NS, ph = (wcnt / NS) & 1u;
+                                timed_wait(bar(BAR_W_FULL + slot), ph, 5, w_w);
+                                tc_fence_after();
+                                const uint32_t w = base + OFF_W + slot * STAGE_BYTES;
+#pragma unroll
+                                for (int kk = 0; kk < 2; ++kk)
+                                    tc_mma_f16(d_tmem, make_desc(a_hi + (hk * 2 + kk) * 32, 0), make_desc_sw64(w + kk * 32), idesc, 1);
+                                tc_commit(bar(BAR_W_EMPTY + slot));
+                                ++wcnt;
+                            }
                         }
                         if (kb < 0 && t == 5) tc_commit(bar(BAR_PE_EMPTY));   // encoded tile no longer needed
                     }
                     tc_commit(bar(BAR_ACC_FULL + (t & 1)));
+                    if (trace && blockIdx.x == 0 && it == 5) trace[148 * 16 + t * 8 + 5] = (unsigned long long)clock64();
                     if (t >= 1) ++agen;                                        // steps 1..9 each consumed one generation
                 }
             }
+            if (trace) {
+                trace[blockIdx.x * 16 + 1] = w_pe; trace[blockIdx.x * 16 + 2] = w_a; trace[blockIdx.x * 16 + 3] = w_w;
+                trace[blockIdx.x * 16 + 4] = (unsigned long long)(clock64() - m_t0);
+            }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ================= epilogue =================
-        const int q = warp - 4;
+    } else if (warp >= 8) {
+        // ================= epilogue: 8 warps, warp pair (w, w+4) shares TMEM lane quarter q and splits the columns =================
+        const int q = warp & 3;                             // TMEM lane quarter this warp may access
+        const int ch = (warp - 8) >> 2;                     // column half: 32 of every 64-column K-block
         const int r = q * 32 + lane;                        // row in tile == TMEM lane
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        float* xchg = reinterpret_cast<float*>(sm + OFF_A_HI + q * 4096);   // [32 rows][4] partial heads, inside this pair's own rows of A kb0
         uint32_t acc_uses[2] = {0, 0};
+        unsigned long long w_acc = 0;
+        const long long e_t0 = clock64();
         for (int it = 0; it < my_tiles; ++it) {
             const int64_t row = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TILE_M + r;
             float sigma_acc = 0.0f;
             for (int t = 0; t < 10; ++t) {
                 const int b = t & 1;
-                mbar_wait(bar(BAR_ACC_FULL + b), acc_uses[b] & 1u, err_flag, 6);
+                // the smem carve-out leaves no L1: every __ldg is an L2 round trip, so the per-layer constants of the first
+                // chunk are fetched BEFORE blocking on the accumulator and later chunks prefetch one chunk ahead
+                const float inv_scale = __ldg(p.inv_scale + t);
+                const float* bias = p.bias[t < 9 ? t : 0] + ch * 16;
+                float4 bq[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(bias) + j);
+                timed_wait(bar(BAR_ACC_FULL + b), acc_uses[b] & 1u, 6, w_acc);
                 ++acc_uses[b];
                 tc_fence_after();
-                const float inv_scale = __ldg(p.inv_scale + t);
-                const uint32_t acc_addr = lane_addr + (uint32_t)b * 256u;
+                const bool tl = trace && blockIdx.x == 0 && it == 5 && threadIdx.x == 256;
+                if (tl) trace[148 * 16 + 128 + t * 8 + 0] = (unsigned long long)clock64();
+                const uint32_t acc_addr = lane_addr + (uint32_t)b * 256u + (uint32_t)ch * (t < 9 ? 16u : 32u);
                 if (t < 9) {
-                    const float* bias = p.bias[t];
-                    for (int kb = 0; kb < 4; ++kb) {
+                    // hand-off granularity = one K-half (32 columns, what one weight stage multiplies): every warp converts
+                    // 16 columns of each K-half, so the MMA of the next layer can start after 1/8 of the epilogue.
+                    uint32_t va[16], vb[16];
+                    tc_ld16_issue(acc_addr, va);
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            float v[32];
-                            tc_ld32(acc_addr + kb * 64 + h * 32, v);
-                            const int col0 = kb * 64 + h * 32;
+                    for (int kh = 0; kh < 8; ++kh) {
+                        uint32_t (&cur)[16] = (kh & 1) ? vb : va;
+                        uint32_t (&nxt)[16] = (kh & 1) ? va : vb;
+                        tc_ld16_wait(cur);
+                        if (tl && kh == 0) trace[148 * 16 + 128 + t * 8 + 5] = (unsigned long long)clock64();
+                        float4 bn[4];
+                        if (kh < 7) {
+                            tc_ld16_issue(acc_addr + (kh + 1) * 32, nxt);   // next K-half's accumulators in flight while this one is converted
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
-                                v[j] = fmaf(v[j], inv_scale, bv.x); v[j + 1] = fmaf(v[j + 1], inv_scale, bv.y);
-                                v[j + 2] = fmaf(v[j + 2], inv_scale, bv.z); v[j + 3] = fmaf(v[j + 3], inv_scale, bv.w);
-                            }
-                            if (t != 8) {
+                            for (int j = 0; j < 4; ++j) bn[j] = __ldg(reinterpret_cast<const float4*>(bias + (kh + 1) * 32) + j);
+                        }
+                        const int col0 = kh * 32;
+                        float v[16];
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], 0.0f), 65504.0f);      // ReLU (+ fp16 range guard)
-                            } else {
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 bv = bq[j >> 2];
+                            v[j] = fmaf(__uint_as_float(cur[j]), inv_scale, bv.x);
+                            v[j + 1] = fmaf(__uint_as_float(cur[j + 1]), inv_scale, bv.y);
+                            v[j + 2] = fmaf(__uint_as_float(cur[j + 2]), inv_scale, bv.z);
+                            v[j + 3] = fmaf(__uint_as_float(cur[j + 3]), inv_scale, bv.w);
+                        }
+                        if (t != 8) {
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -65504.0f), 65504.0f);  // feature head: linear
-                            }
-                            if (t == 7) {                                      // sigma head on h7 (model/nerf.py:101)
+                            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);                             // ReLU
+                        }
+                        if (t == 7) {                                          // sigma head on h7 (model/nerf.py:101)
 #pragma unroll
-                                for (int j = 0; j < 32; j += 4) {
-                                    const float4 wa = __ldg(reinterpret_cast<const float4*>(p.w_alpha + col0 + j));
-                                    sigma_acc = fmaf(v[j], wa.x, sigma_acc); sigma_acc = fmaf(v[j + 1], wa.y, sigma_acc);
-                                    sigma_acc = fmaf(v[j + 2], wa.z, sigma_acc); sigma_acc = fmaf(v[j + 3], wa.w, sigma_acc);
-                                }
-                            }
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const uint32_t off = kb * KBLOCK_BYTES + sw128_offset(r, h * 32 + j * 8);
-                                split_store8(v + 8 * j, sm + OFF_A_HI + off, sm + OFF_A_LO + off);
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 wa = __ldg(reinterpret_cast<const float4*>(p.w_alpha + ch * 16 + col0 + j));
+                                sigma_acc = fmaf(v[j], wa.x, sigma_acc); sigma_acc = fmaf(v[j + 1], wa.y, sigma_acc);
+                                sigma_acc = fmaf(v[j + 2], wa.z, sigma_acc); sigma_acc = fmaf(v[j + 3], wa.w, sigma_acc);
                             }
                         }
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint32_t off = (kh >> 1) * KBLOCK_BYTES + sw128_offset(r, (kh & 1) * 32 + ch * 16 + j * 8);
+                            split_store8(v + 8 * j, sm + OFF_A_HI + off, sm + OFF_A_LO + off);
+                        }
+                        if (tl && kh == 0) trace[148 * 16 + 128 + t * 8 + 6] = (unsigned long long)clock64();
                         tc_fence_before();
                         fence_proxy_async();
-                        mbar_arrive(bar(BAR_A_READY + kb));
+                        mbar_arrive(bar(BAR_A_READY + kh));
+                        if (tl && (kh & 1) == 0) trace[148 * 16 + 128 + t * 8 + 1 + (kh >> 1)] = (unsigned long long)clock64();
+                        if (kh < 7) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) bq[j] = bn[j];
+                        }
                     }
                 } else {
-                    // view layer output (128 cols) -> ReLU -> rgb head; write cat([rgb, sigma]) (model/nerf.py:103-110)
+                    // view layer output (128 cols, 64 per warp of the pair) -> ReLU -> rgb head; write cat([rgb, sigma]) (model/nerf.py:103-110)
                     const int64_t ray = (row < rows) ? row / S : 0;
-                    const float* vb = viewbias + ray * kHalf;
+                    const float* vbp = viewbias + ray * kHalf + ch * 32;
                     float rgb[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-                    for (int h = 0; h < 4; ++h) {
-                        float v[32];
-                        tc_ld32(acc_addr + h * 32, v);
+                    uint32_t va[32], vb[32];
+                    tc_ld32_issue(acc_addr, va);
+                    tc_ld32_issue(acc_addr + 64, vb);
+                    tc_ld_wait(va);
+                    tc_ld_wait(vb);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t (&cur)[32] = h ? vb : va;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const int col = h * 32 + j;
-                            const float4 bv = __ldg(reinterpret_cast<const float4*>(vb + col));
-                            const float x0 = fmaxf(fmaf(v[j], inv_scale, bv.x), 0.0f), x1 = fmaxf(fmaf(v[j + 1], inv_scale, bv.y), 0.0f);
-                            const float x2 = fmaxf(fmaf(v[j + 2], inv_scale, bv.z), 0.0f), x3 = fmaxf(fmaf(v[j + 3], inv_scale, bv.w), 0.0f);
+                            const int col = h * 64 + j;                          // relative to this warp's first column
+                            const float4 bv = __ldg(reinterpret_cast<const float4*>(vbp + col));
+                            const float x0 = fmaxf(fmaf(__uint_as_float(cur[j]), inv_scale, bv.x), 0.0f);
+                            const float x1 = fmaxf(fmaf(__uint_as_float(cur[j + 1]), inv_scale, bv.y), 0.0f);
+                            const float x2 = fmaxf(fmaf(__uint_as_float(cur[j + 2]), inv_scale, bv.z), 0.0f);
+                            const float x3 = fmaxf(fmaf(__uint_as_float(cur[j + 3]), inv_scale, bv.w), 0.0f);
 #pragma unroll
                             for (int c = 0; c < C; ++c) {
-                                const float4 wr = __ldg(reinterpret_cast<const float4*>(p.w_rgb + c * kHalf + col));
+                                const float4 wr = __ldg(reinterpret_cast<const float4*>(p.w_rgb + c * kHalf + ch * 32 + col));
                                 rgb[c] = fmaf(x0, wr.x, rgb[c]); rgb[c] = fmaf(x1, wr.y, rgb[c]);
                                 rgb[c] = fmaf(x2, wr.z, rgb[c]); rgb[c] = fmaf(x3, wr.w, rgb[c]);
                             }
                         }
                     }
                     tc_fence_before();
-                    if (row < rows) {
-                        const float sg = sigma_acc + __ldg(p.b_alpha);
-                        if (C == 3) {
-                            *reinterpret_cast<float4*>(raw + row * 4) =
-                                make_float4(rgb[0] + __ldg(p.b_rgb), rgb[1] + __ldg(p.b_rgb + 1), rgb[2] + __ldg(p.b_rgb + 2), sg);
-                        } else {
-                            *reinterpret_cast<float2*>(raw + row * 2) = make_float2(rgb[0] + __ldg(p.b_rgb), sg);
+                    // combine the two column halves of each row: the upper-half warp parks its partial sums in the pair's own
+                    // rows of the (idle between t = 9 and the next tile's first epilogue) A tile, the lower-half warp adds and writes.
+                    if (ch == 1) {
+                        *reinterpret_cast<float4*>(xchg + lane * 4) = make_float4(rgb[0], rgb[1], rgb[2], sigma_acc);
+                        named_bar_arrive(1 + q, 64);
+                        named_bar_sync(5 + q, 64);            // partner has read: the A rows may be overwritten again
+                    } else {
+                        named_bar_sync(1 + q, 64);
+                        const float4 o = *reinterpret_cast<const float4*>(xchg + lane * 4);
+                        named_bar_arrive(5 + q, 64);
+                        if (row < rows) {
+                            const float sg = sigma_acc + o.w + __ldg(p.b_alpha);
+                            if (C == 3) {
+                                *reinterpret_cast<float4*>(raw + row * 4) =
+                                    make_float4(rgb[0] + o.x + __ldg(p.b_rgb), rgb[1] + o.y + __ldg(p.b_rgb + 1), rgb[2] + o.z + __ldg(p.b_rgb + 2), sg);
+                            } else {
+                                *reinterpret_cast<float2*>(raw + row * 2) = make_float2(rgb[0] + o.x + __ldg(p.b_rgb), sg);
+                            }
                         }
                     }
                 }
             }
         }
-    } else if (warp >= 8) {
+        if (trace && threadIdx.x == 256) {
+            trace[blockIdx.x * 16 + 6] = w_acc; trace[blockIdx.x * 16 + 7] = (unsigned long long)(clock64() - e_t0);
+        }
+    } else if (warp >= 4) {
         // ================= front end: encode the next tile =================
-        const int r = threadIdx.x - 256;
+        const int r = threadIdx.x - 128;
+        unsigned long long w_pee = 0;
+        const long long f_t0 = clock64();
         for (int it = 0; it < my_tiles; ++it) {
             const int64_t row = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TILE_M + r;
             float enc[64];
@@ -376,7 +505,7 @@ mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restr
                     enc[3 + 6 * k + 3 + c] = live ? co : 0.0f;
                 }
             enc[63] = 0.0f;
-            mbar_wait(bar(BAR_PE_EMPTY), ((uint32_t)it & 1u) ^ 1u, err_flag, 7);
+            timed_wait(bar(BAR_PE_EMPTY), ((uint32_t)it & 1u) ^ 1u, 7, w_pee);
 #pragma unroll
             for (int c8 = 0; c8 < 8; ++c8) {
                 const uint32_t off = sw128_offset(r, c8 * 8);
@@ -385,10 +514,14 @@ mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restr
             fence_proxy_async();
             mbar_arrive(bar(BAR_PE_FULL));
         }
+        if (trace && threadIdx.x == 128) {
+            trace[blockIdx.x * 16 + 8] = w_pee; trace[blockIdx.x * 16 + 9] = (unsigned long long)(clock64() - f_t0);
+        }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (trace && threadIdx.x == 0) trace[blockIdx.x * 16 + 0] = (unsigned long long)(clock64() - k_t0);
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
@@ -400,10 +533,10 @@ mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restr
 // K-block comes first for steps 0 and 5.
 struct StageInfo { int step, k0, n, lo; };
 __host__ __device__ inline StageInfo stage_info(int i) {
-    int kbi = i / 2, lo = i & 1, t = 0;
+    int kbi = i / 4, hk = (i >> 1) & 1, lo = i & 1, t = 0;  // order inside a K-block: (hi,k0-31) (lo,k0-31) (hi,k32-63) (lo,k32-63)
     const int kbs[10] = {1, 4, 4, 4, 4, 5, 4, 4, 4, 4};
     while (kbi >= kbs[t]) { kbi -= kbs[t]; ++t; }
-    return {t, kbi * 64, t == 9 ? 128 : 256, lo};          // wt[t] rows are already ordered [pe64 | h256]
+    return {t, kbi * 64 + hk * 32, t == 9 ? 128 : 256, lo}; // wt[t] rows are already ordered [pe64 | h256]
 }
 
 __global__ void absmax_kernel(const float* __restrict__ w, int n, unsigned int* out) {
@@ -429,12 +562,12 @@ __global__ void pack_stream_kernel(const float* const* __restrict__ wt, const fl
     const float* w = wt[si.step];
     const float sc = scale[si.step];
     unsigned char* dst = reinterpret_cast<unsigned char*>(stream) + stage_offset_bytes(i);
-    for (int e = threadIdx.x; e < si.n * 64; e += blockDim.x) {
+    for (int e = threadIdx.x; e < si.n * 32; e += blockDim.x) {
         const int k = e / si.n, n = e % si.n;               // coalesced over n in the k-major source
         const float v = w[(size_t)(si.k0 + k) * si.n + n] * sc;
         const __half hi = __float2half_rn(v);
         const __half out = si.lo ? __float2half_rn(v - __half2float(hi)) : hi;
-        *reinterpret_cast<__half*>(dst + sw128_offset(n, k)) = out;
+        *reinterpret_cast<__half*>(dst + sw64_offset(n, k)) = out;
     }
 }
 
@@ -482,10 +615,10 @@ int launch_mlp_tc(bnrf_ctx* ctx, int net, const float* o, const float* d, const 
     const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
     if (ctx->cfg.channels == 3) {
         BNRF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        mlp_tc_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p, o, d, vb, z, rows, S, tiles, raw, ctx->err_flag);
+        mlp_tc_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p, o, d, vb, z, rows, S, tiles, raw, ctx->err_flag, ctx->trace);
     } else {
         BNRF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        mlp_tc_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p, o, d, vb, z, rows, S, tiles, raw, ctx->err_flag);
+        mlp_tc_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p, o, d, vb, z, rows, S, tiles, raw, ctx->err_flag, ctx->trace);
     }
     BNRF_LAUNCH_CHECK(ctx);
     return BNRF_OK;

