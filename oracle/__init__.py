@@ -6,7 +6,7 @@ into an explicit input.  It exists so that the CUDA engine in ``benerf_b200``
 can be checked on machines where ``/root/reference`` is absent.  Only
 ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
 ``--impl reference`` legs of ``bench.py`` may import it; the product package
-never does (tests/test_layout.py greps for that).
+never does (tests/test_library.py greps for that).
 
 Parity pin: the oracle is pinned against outputs of the *unmodified* reference
 imported from ``/root/reference`` (tools/make_golden.py -> tests/golden/*.npz;
