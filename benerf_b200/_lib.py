@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libbenerf_b200.so")
 
 OK, ERR_ARG, ERR_DEVICE, ERR_CUDA, ERR_STATE, ERR_NCCL = 0, -1, -2, -3, -4, -5
-MLP_TC_FP16X2, MLP_SIMT_FP32 = 0, 1
+MLP_TC_FP16X2, MLP_SIMT_FP32, MLP_TC_1CTA = 0, 1, 2
 NUM_LINEARS = 12
 # order of the 12 linears expected by bnrf_set_weights (reference state-dict order)
 LINEAR_NAMES = [f"pts_linears.{i}" for i in range(8)] + ["views_linears.0", "feature_linear", "alpha_linear", "rgb_linear"]

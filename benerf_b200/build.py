@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libbenerf_b200.so")
-SOURCES = ["api.cu", "pose.cu", "rays.cu", "composite.cu", "image_formation.cu", "mlp_simt.cu", "mlp_tc.cu",
+SOURCES = ["api.cu", "pose.cu", "rays.cu", "composite.cu", "image_formation.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc2.cu",
            "backward.cu", "parallel.cu"]
 NO_FMAD = {"pose.cu", "rays.cu"}
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -44,6 +44,7 @@ int alloc_net(bnrf_ctx* ctx, int n) {
     BNRF_CUDA(ctx, cudaMalloc(&np.b_rgb, 3 * sizeof(float)));
     BNRF_CUDA(ctx, cudaMalloc(&np.w_dir, kDirCh * kHalf * sizeof(float)));
     BNRF_CUDA(ctx, cudaMalloc(&np.tc_stream, tc_stream_halfs() * sizeof(__half)));
+    BNRF_CUDA(ctx, cudaMalloc(&np.tc2_stream, tc2_stream_halfs() * sizeof(__half)));
     BNRF_CUDA(ctx, cudaMalloc(&np.tc_scale, 16 * sizeof(float)));
     return BNRF_OK;
 }
@@ -52,7 +53,7 @@ void free_net(bnrf_ctx* ctx, int n) {
     NetParams& np = ctx->net[n];
     for (int s = 0; s < 10; ++s) { cudaFree(np.wt[s]); cudaFree(np.bias[s]); }
     cudaFree(np.w_alpha); cudaFree(np.b_alpha); cudaFree(np.w_rgb); cudaFree(np.b_rgb); cudaFree(np.w_dir);
-    cudaFree(np.tc_stream); cudaFree(np.tc_scale);
+    cudaFree(np.tc_stream); cudaFree(np.tc2_stream); cudaFree(np.tc_scale);
     memset(&np, 0, sizeof(np));
 }
 
@@ -125,7 +126,8 @@ static int run_mlp(bnrf_ctx* ctx, int net, const float* o, const float* d, const
     const double macs = 63.0 * 256 + 4 * 65536.0 + 319.0 * 256 + 2 * 65536.0 + 256 + 65536.0 + 283.0 * 128 + 128.0 * ctx->cfg.channels;
     MlpTimer timer(ctx, st, 2.0 * macs * (double)n * (double)S);
     if (ctx->cfg.mlp_mode == BNRF_MLP_SIMT_FP32) return launch_mlp_simt(ctx, net, o, d, vb, z, n, S, raw, st);
-    return launch_mlp_tc(ctx, net, o, d, vb, z, n, S, raw, st);
+    if (ctx->cfg.mlp_mode == BNRF_MLP_TC_1CTA) return launch_mlp_tc(ctx, net, o, d, vb, z, n, S, raw, st);
+    return launch_mlp_tc2(ctx, net, o, d, vb, z, n, S, raw, st);
 }
 
 }  // namespace bnrf
@@ -144,7 +146,7 @@ int bnrf_create(bnrf_ctx** out, int device, const bnrf_cfg* cfg) {
     if (cfg->n_samples < 3 || cfg->n_importance < 0 || cfg->n_samples + cfg->n_importance > kMaxSamples)
         return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: need 3 <= n_samples and n_samples + n_importance <= %d", kMaxSamples);
     if (cfg->channels != 1 && cfg->channels != 3) return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: channels must be 1 or 3");
-    if (cfg->mlp_mode != BNRF_MLP_TC_FP16X2 && cfg->mlp_mode != BNRF_MLP_SIMT_FP32)
+    if (cfg->mlp_mode != BNRF_MLP_TC_FP16X2 && cfg->mlp_mode != BNRF_MLP_SIMT_FP32 && cfg->mlp_mode != BNRF_MLP_TC_1CTA)
         return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: unknown mlp_mode %d", cfg->mlp_mode);
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)

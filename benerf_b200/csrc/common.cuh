@@ -31,7 +31,8 @@ struct NetParams {
     float* w_dir;         // [27][128]  view-direction block of views_linears.0, transposed
     // tensor-core stream: fp16 hi/lo tiles in the SW128 K-major shared-memory image,
     // in the exact order the TMA producer consumes them (mlp_tc.cu).
-    __half* tc_stream;
+    __half* tc_stream;    // single-CTA kernel (mlp_tc.cu)
+    __half* tc2_stream;   // CTA-pair kernel (mlp_tc2.cu): [rank][stage], each CTA's half of the output columns
     float* tc_scale;      // [10] 2^-s per GEMM step undoing the fp16 weight pre-scale
     bool ready;
 };
@@ -138,5 +139,9 @@ int pack_weights(bnrf_ctx*, int net, const float* const* w, const float* const* 
 int alloc_net(bnrf_ctx*, int net);
 void free_net(bnrf_ctx*, int net);
 size_t tc_stream_halfs();
+size_t tc2_stream_halfs();
+int pack_tc2_stream(bnrf_ctx*, int net, const float* const* table_dev, const float* scale_dev, cudaStream_t);
+int launch_mlp_tc2(bnrf_ctx*, int net, const float* o, const float* d, const float* vb, const float* z,
+                   int64_t n, int S, float* raw, cudaStream_t);
 
 }  // namespace bnrf

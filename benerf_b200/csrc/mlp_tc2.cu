@@ -1,42 +1,35 @@
-// K4/K5: positional encoding + the 8x256 NeRF MLP on tcgen05 tensor cores (sm_100a).
+// K4/K5 on CTA pairs: positional encoding + the 8x256 NeRF MLP with tcgen05.mma cta_group::2 (sm_100a).
 //
-// One persistent CTA per SM processes tiles of 128 samples (rows).  The hidden state of a tile
-// never leaves the SM: accumulators live in TMEM (2 x 256 fp32 columns, ping-pong between
-// consecutive layers), the A operand of the next layer is written by the epilogue warps
-// straight into shared memory in the canonical SWIZZLE_128B K-major layout, and the weights
-// stream through a shared-memory ring filled by the TMA bulk-copy engine (cp.async.bulk)
-// from an L2-resident, pre-swizzled image built once per optimiser step.
+// Same dataflow as mlp_tc.cu (hidden state resident in shared memory / TMEM, fp16 hi/lo split
+// operands, 3 MMAs per K=16 slice, fp32 accumulation) but two CTAs of one TPC work as a pair on
+// 256 rows: each CTA owns 128 rows (its A operand and its accumulators) and HALF of every
+// weight tile (128 of the 256 output columns).  One thread of the leader CTA issues
+// tcgen05.mma.cta_group::2 with M = 256; the hardware reads A from both CTAs' shared memory, the
+// two B halves from one CTA each, and writes each CTA's 128 x N accumulator into its own TMEM.
 //
-// Precision: the reference is fp32 (SGEMM).  A single 16-bit tensor-core pass misses the 1e-4
-// parity bound (hard part 1), so every operand is split x = hi + lo into two fp16
-// values and each K=16 slice issues three MMAs, hi*hi + lo*hi + hi*lo, accumulated in fp32 in
-// TMEM (the lo*lo term is below 2^-22 relative).  Weights are pre-scaled by a per-layer power
-// of two so that their lo halves stay in the fp16 normal range; the epilogue undoes it.
+// Why: measured on the single-CTA kernel (profiles/r01_mlp_tc_stall_trace.txt) every SM re-streamed
+// the whole 2.3 MB weight image per 128-row tile -- 43 B/cycle/SM, the whole-chip L2 ceiling -- and
+// SS-mode operand reads (96 B/cycle) + TMA fills + epilogue stores exceeded the 128 B/cycle shared
+// memory port.  The pair halves both: 21 B/cycle/SM from L2, 64 B/cycle of operand reads.
 //
-// Warp roles (512 threads):
-//   warp 0      TMA producer: weight tiles -> smem ring (mbarrier complete_tx)
-//   warp 1      MMA issuer: one thread issues tcgen05.mma, commits to mbarriers; owns TMEM alloc
-//   warps 4-7   front end: pts = o + d*z, sin/cos encoding -> A tile of layer 0 / skip layer,
-//               one tile ahead of the MMA
-//   warps 8-15  epilogue: tcgen05.ld -> scale/bias/ReLU -> fp16 hi/lo -> next layer's A tile;
-//               sigma head (256->1) and rgb head (128->C) as fp32 FFMA on the way through.
-//               Warps w and w+4 share a TMEM lane quarter (32 rows) and split the columns, so each
-//               SM sub-partition runs two epilogue warps (the conversion is latency-bound).
-// Layer boundaries are pipelined per 64-column K-block: the MMA of layer l+1 starts on K-block
-// 0 as soon as the epilogue of layer l has produced it, while the epilogue continues.
+// Cross-CTA protocol (all mbarriers live at the same shared-memory offset in both CTAs):
+//   W_FULL[slot]   leader: 1 local expect_tx arrival + 1 relayed arrival from the peer (warp 2 of the
+//                  peer waits on its own W_FULL and forwards); peer: local only
+//   W_EMPTY[slot], ACC_FULL[2], PE_EMPTY   tcgen05.commit multicast to both CTAs
+//   A_READY[8], PE_FULL   on the leader only: one elected-lane arrival per producing warp of BOTH
+//                  CTAs (mapa + mbarrier.arrive.release.cluster), 16 resp. 8 per phase
 //
-// Replaces model/embedder.py:9-34 + model/nerf.py:67-116 (12 cuBLAS SGEMMs + ~40 elementwise
-// launches per network call, every activation through HBM).
+// Replaces model/embedder.py:9-34 + model/nerf.py:67-116.
 #include "tc_ptx.cuh"
 
 namespace bnrf {
-namespace tc {
+namespace tc2 {
 using namespace tcp;
 
-constexpr int TILE_M = 128;
+constexpr int TILE_M = 128;                        // rows per CTA (256 per pair)
 constexpr int NUM_THREADS = 512;
 constexpr int NS = 4;                              // weight ring depth
-constexpr uint32_t STAGE_BYTES = 16384;            // one [256 x 32] fp16 SW64 tile (half a K-block of one weight half)
+constexpr uint32_t STAGE_BYTES = 16384;            // this CTA's [128 x 64] fp16 SW128 half of one K-block of W_hi or W_lo
 constexpr uint32_t KBLOCK_BYTES = 16384;           // one [128 x 64] fp16 SW128 A tile
 constexpr uint32_t OFF_A_HI = 0;
 constexpr uint32_t OFF_A_LO = 4 * KBLOCK_BYTES;
@@ -45,29 +38,27 @@ constexpr uint32_t OFF_PE_LO = 9 * KBLOCK_BYTES;
 constexpr uint32_t OFF_W = 10 * KBLOCK_BYTES;
 constexpr uint32_t OFF_BAR = OFF_W + NS * STAGE_BYTES;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
-constexpr int STAGES_PER_TILE = 152;               // 38 K-blocks x 2 K-halves x (hi, lo)
-constexpr int N256_STAGES = 136;
+constexpr int STAGES_PER_TILE = 76;                // 38 K-blocks x (hi, lo)
+constexpr int N256_STAGES = 68;                    // stages of the nine 256-wide steps; the view layer's 8 stages are half size
 constexpr uint32_t TMEM_COLS = 512;
 
-// barrier slots (8 bytes each) inside the barrier block
 enum { BAR_W_FULL = 0, BAR_W_EMPTY = BAR_W_FULL + NS, BAR_PE_FULL = BAR_W_EMPTY + NS, BAR_PE_EMPTY,
        BAR_A_READY, BAR_ACC_FULL = BAR_A_READY + 8, BAR_COUNT = BAR_ACC_FULL + 2 };
-
 
 __host__ __device__ inline size_t stage_offset_bytes(int i) {
     return i < N256_STAGES ? (size_t)i * STAGE_BYTES : (size_t)N256_STAGES * STAGE_BYTES + (size_t)(i - N256_STAGES) * (STAGE_BYTES / 2);
 }
+__host__ __device__ inline size_t rank_stream_bytes() { return stage_offset_bytes(STAGES_PER_TILE); }
 
-// ---------------------------------------------------------------------------- the kernel
 template <int C>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-              const float* __restrict__ viewbias, const float* __restrict__ z, int64_t rows, int S, int num_tiles,
-              float* __restrict__ raw, unsigned int* err_flag, unsigned long long* __restrict__ trace) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+               const float* __restrict__ viewbias, const float* __restrict__ z, int64_t rows, int S, int num_pairs,
+               float* __restrict__ raw, unsigned int* err_flag, unsigned long long* __restrict__ trace) {
     // trace (debug, normally NULL): per-CTA stall accounting, 16 counters of clock64 cycles --
     //   0 kernel total   1 mma: wait PE_FULL   2 mma: wait A_READY   3 mma: wait W_FULL   4 mma: loop total
-    //   5 tma: wait W_EMPTY   6 epilogue(warp 4): wait ACC_FULL   7 epilogue: loop total
-    //   8 front end(warp 8): wait PE_EMPTY   9 front end: loop total
+    //   5 tma: wait W_EMPTY   6 epilogue(warp 8): wait ACC_FULL   7 epilogue: loop total
+    //   8 front end(warp 4): wait PE_EMPTY   9 front end: loop total
     const long long k_t0 = clock64();
     auto timed_wait = [&](uint32_t b, uint32_t parity, unsigned int code, unsigned long long& acc) {
         if (trace) {
@@ -78,6 +69,15 @@ mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restr
             mbar_wait(b, parity, err_flag, code);
         }
     };
+    auto timed_wait_cluster = [&](uint32_t b, uint32_t parity, unsigned int code, unsigned long long& acc) {
+        if (trace) {
+            const long long t = clock64();
+            mbar_wait_cluster(b, parity, err_flag, code);
+            acc += (unsigned long long)(clock64() - t);
+        } else {
+            mbar_wait_cluster(b, parity, err_flag, code);
+        }
+    };
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -85,33 +85,38 @@ mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restr
     auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 8 * BAR_COUNT);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const uint32_t rank = cluster_ctarank();                  // 0 = leader (issues the MMAs), 1 = peer
+    const int cluster = (int)(blockIdx.x >> 1), n_clusters = (int)(gridDim.x >> 1);
+    const uint32_t lbar0 = mapa_u32(bar0, 0);                 // the leader's barrier block, as a shared::cluster address
+    auto lbar = [&](int i) { return lbar0 + 8u * (uint32_t)i; };
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NS; ++i) { mbar_init(bar(BAR_W_FULL + i), 1); mbar_init(bar(BAR_W_EMPTY + i), 1); }
-        mbar_init(bar(BAR_PE_FULL), 128);
+        for (int i = 0; i < NS; ++i) { mbar_init(bar(BAR_W_FULL + i), rank == 0 ? 2 : 1); mbar_init(bar(BAR_W_EMPTY + i), 1); }
+        mbar_init(bar(BAR_PE_FULL), 8);                       // 4 front-end warps x 2 CTAs
         mbar_init(bar(BAR_PE_EMPTY), 1);
-        for (int i = 0; i < 8; ++i) mbar_init(bar(BAR_A_READY + i), 256);
+        for (int i = 0; i < 8; ++i) mbar_init(bar(BAR_A_READY + i), 16);   // 8 epilogue warps x 2 CTAs
         for (int i = 0; i < 2; ++i) mbar_init(bar(BAR_ACC_FULL + i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();                                       // barrier inits + TMEM of both CTAs visible before any remote arrive / MMA
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    const int my_tiles = (num_tiles > (int)blockIdx.x) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int my_iters = (num_pairs > cluster) ? (num_pairs - 1 - cluster) / n_clusters + 1 : 0;
+    auto tile_of = [&](int it) { return (int64_t)2 * ((int64_t)cluster + (int64_t)it * n_clusters) + rank; };
 
     if (warp == 0) {
-        // ================= TMA producer =================
+        // ================= TMA producer (both CTAs: own half of every weight tile) =================
         if (lane == 0) {
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(p.stream);
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(p.stream) + (size_t)rank * rank_stream_bytes();
             uint32_t cnt = 0;
             unsigned long long w_empty = 0;
-            for (int it = 0; it < my_tiles; ++it) {
+            for (int it = 0; it < my_iters; ++it) {
                 for (int i = 0; i < STAGES_PER_TILE; ++i, ++cnt) {
                     const uint32_t slot = cnt % NS, ph = (cnt / NS) & 1u;
                     timed_wait(bar(BAR_W_EMPTY + slot), ph ^ 1u, 1, w_empty);
@@ -122,17 +127,28 @@ mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restr
             }
             if (trace) trace[blockIdx.x * 16 + 5] = w_empty;
         }
+    } else if (warp == 2) {
+        // ================= peer only: forward "my half of the stage has landed" to the leader's W_FULL =================
+        if (lane == 0 && rank == 1) {
+            const uint32_t total = (uint32_t)my_iters * STAGES_PER_TILE;
+            unsigned long long dummy = 0;
+            for (uint32_t cnt = 0; cnt < total; ++cnt) {
+                const uint32_t slot = cnt % NS, ph = (cnt / NS) & 1u;
+                timed_wait(bar(BAR_W_FULL + slot), ph, 8, dummy);
+                mbar_arrive_cluster(lbar(BAR_W_FULL + slot));
+            }
+        }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer (leader CTA, one thread) =================
+        if (lane == 0 && rank == 0) {
             uint32_t wcnt = 0;           // weight stages consumed
             uint32_t agen = 0;           // generation of the a_ready barriers (one per producing epilogue)
             unsigned long long w_pe = 0, w_a = 0, w_w = 0;
             const long long m_t0 = clock64();
-            for (int it = 0; it < my_tiles; ++it) {
+            for (int it = 0; it < my_iters; ++it) {
                 for (int t = 0; t < 10; ++t) {
                     const int N = (t == 9) ? 128 : 256;
-                    const uint32_t idesc = make_idesc(TILE_M, N);
+                    const uint32_t idesc = make_idesc(2 * TILE_M, N);
                     const uint32_t d_tmem = tmem + (uint32_t)(t & 1) * 256u;
                     const bool has_pe = (t == 0 || t == 5);
                     const int n_act = (t == 0) ? 0 : 4;
@@ -140,50 +156,49 @@ mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restr
                     for (int kb = has_pe ? -1 : 0; kb < n_act; ++kb) {
                         uint32_t a_hi, a_lo;
                         if (kb < 0) {
-                            if (t == 0) timed_wait(bar(BAR_PE_FULL), (uint32_t)it & 1u, 2, w_pe);
+                            if (t == 0) timed_wait_cluster(bar(BAR_PE_FULL), (uint32_t)it & 1u, 2, w_pe);
                             a_hi = base + OFF_PE_HI; a_lo = base + OFF_PE_LO;
                         } else {
                             a_hi = base + OFF_A_HI + kb * KBLOCK_BYTES; a_lo = base + OFF_A_LO + kb * KBLOCK_BYTES;
                         }
-                        // per K-half (32 columns of the A K-block): the hi weight stage feeds A_hi * W_hi and
-                        // A_lo * W_hi, the lo stage feeds A_hi * W_lo
-#pragma unroll
-                        for (int hk = 0; hk < 2; ++hk) {
-                            if (kb >= 0) {
-                                timed_wait(bar(BAR_A_READY + kb * 2 + hk), agen & 1u, 3, w_a);
-                                if (trace && blockIdx.x == 0 && it == 5 && hk == 0) trace[148 * 16 + t * 8 + 1 + kb] = (unsigned long long)clock64();
-                            }
+                        {   // W_hi stage of this K-block: A_hi * W_hi and A_lo * W_hi
+                            const uint32_t slot = wcnt % NS, ph = (wcnt / NS) & 1u;
+                            timed_wait_cluster(bar(BAR_W_FULL + slot), ph, 4, w_w);
                             tc_fence_after();
-                            {
-                                const uint32_t slot = wcnt % NS, ph = (wcnt / NS) & 1u;
-                                timed_wait(bar(BAR_W_FULL + slot), ph, 4, w_w);
-                                tc_fence_after();
-                                const uint32_t w = base + OFF_W + slot * STAGE_BYTES;
+                            const uint32_t w = base + OFF_W + slot * STAGE_BYTES;
+#pragma unroll
+                            for (int hk = 0; hk < 2; ++hk) {
+                                if (kb >= 0) {
+                                    timed_wait_cluster(bar(BAR_A_READY + kb * 2 + hk), agen & 1u, 3, w_a);
+                                    tc_fence_after();
+                                    if (trace && blockIdx.x == 0 && it == 5 && hk == 0) trace[148 * 16 + t * 8 + 1 + kb] = (unsigned long long)clock64();
+                                }
 #pragma unroll
                                 for (int kk = 0; kk < 2; ++kk) {
-                                    const uint64_t bd = make_desc_sw64(w + kk * 32);
-                                    tc_mma_f16(d_tmem, make_desc(a_hi + (hk * 2 + kk) * 32, 0), bd, idesc, accumulate);
+                                    const uint32_t ko = (uint32_t)(hk * 2 + kk) * 32u;
+                                    const uint64_t bd = make_desc(w + ko, 0);
+                                    tc_mma_pair_f16(d_tmem, make_desc(a_hi + ko, 0), bd, idesc, accumulate);
                                     accumulate = 1;
-                                    tc_mma_f16(d_tmem, make_desc(a_lo + (hk * 2 + kk) * 32, 0), bd, idesc, 1);
+                                    tc_mma_pair_f16(d_tmem, make_desc(a_lo + ko, 0), bd, idesc, 1);
                                 }
-                                tc_commit(bar(BAR_W_EMPTY + slot));
-                                ++wcnt;
                             }
-                            {
-                                const uint32_t slot = wcnt % NS, ph = (wcnt / NS) & 1u;
-                                timed_wait(bar(BAR_W_FULL + slot), ph, 5, w_w);
-                                tc_fence_after();
-                                const uint32_t w = base + OFF_W + slot * STAGE_BYTES;
-#pragma unroll
-                                for (int kk = 0; kk < 2; ++kk)
-                                    tc_mma_f16(d_tmem, make_desc(a_hi + (hk * 2 + kk) * 32, 0), make_desc_sw64(w + kk * 32), idesc, 1);
-                                tc_commit(bar(BAR_W_EMPTY + slot));
-                                ++wcnt;
-                            }
+                            tc_commit_pair(bar(BAR_W_EMPTY + slot));
+                            ++wcnt;
                         }
-                        if (kb < 0 && t == 5) tc_commit(bar(BAR_PE_EMPTY));   // encoded tile no longer needed
+                        {   // W_lo stage: A_hi * W_lo
+                            const uint32_t slot = wcnt % NS, ph = (wcnt / NS) & 1u;
+                            timed_wait_cluster(bar(BAR_W_FULL + slot), ph, 5, w_w);
+                            tc_fence_after();
+                            const uint32_t w = base + OFF_W + slot * STAGE_BYTES;
+#pragma unroll
+                            for (int k16 = 0; k16 < 4; ++k16)
+                                tc_mma_pair_f16(d_tmem, make_desc(a_hi + k16 * 32, 0), make_desc(w + k16 * 32, 0), idesc, 1);
+                            tc_commit_pair(bar(BAR_W_EMPTY + slot));
+                            ++wcnt;
+                        }
+                        if (kb < 0 && t == 5) tc_commit_pair(bar(BAR_PE_EMPTY));   // encoded tiles no longer needed
                     }
-                    tc_commit(bar(BAR_ACC_FULL + (t & 1)));
+                    tc_commit_pair(bar(BAR_ACC_FULL + (t & 1)));
                     if (trace && blockIdx.x == 0 && it == 5) trace[148 * 16 + t * 8 + 5] = (unsigned long long)clock64();
                     if (t >= 1) ++agen;                                        // steps 1..9 each consumed one generation
                 }
@@ -196,15 +211,15 @@ mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restr
     } else if (warp >= 8) {
         // ================= epilogue: 8 warps, warp pair (w, w+4) shares TMEM lane quarter q and splits the columns =================
         const int q = warp & 3;                             // TMEM lane quarter this warp may access
-        const int ch = (warp - 8) >> 2;                     // column half: 32 of every 64-column K-block
+        const int ch = (warp - 8) >> 2;                     // column half: 16 of every 32-column K-half
         const int r = q * 32 + lane;                        // row in tile == TMEM lane
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
         float* xchg = reinterpret_cast<float*>(sm + OFF_A_HI + q * 4096);   // [32 rows][4] partial heads, inside this pair's own rows of A kb0
         uint32_t acc_uses[2] = {0, 0};
         unsigned long long w_acc = 0;
         const long long e_t0 = clock64();
-        for (int it = 0; it < my_tiles; ++it) {
-            const int64_t row = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TILE_M + r;
+        for (int it = 0; it < my_iters; ++it) {
+            const int64_t row = tile_of(it) * TILE_M + r;
             float sigma_acc = 0.0f;
             for (int t = 0; t < 10; ++t) {
                 const int b = t & 1;
@@ -222,8 +237,8 @@ mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restr
                 if (tl) trace[148 * 16 + 128 + t * 8 + 0] = (unsigned long long)clock64();
                 const uint32_t acc_addr = lane_addr + (uint32_t)b * 256u + (uint32_t)ch * (t < 9 ? 16u : 32u);
                 if (t < 9) {
-                    // hand-off granularity = one K-half (32 columns, what one weight stage multiplies): every warp converts
-                    // 16 columns of each K-half, so the MMA of the next layer can start after 1/8 of the epilogue.
+                    // hand-off granularity = one K-half (32 columns): every warp converts 16 columns of each K-half, so the
+                    // MMA of the next layer can start after 1/8 of the epilogue.
                     uint32_t va[16], vb[16];
                     tc_ld16_issue(acc_addr, va);
 #pragma unroll
@@ -268,7 +283,8 @@ mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restr
                         if (tl && kh == 0) trace[148 * 16 + 128 + t * 8 + 6] = (unsigned long long)clock64();
                         tc_fence_before();
                         fence_proxy_async();
-                        mbar_arrive(bar(BAR_A_READY + kh));
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(lbar(BAR_A_READY + kh));   // one arrival per warp, on the leader's barrier
                         if (tl && (kh & 1) == 0) trace[148 * 16 + 128 + t * 8 + 1 + (kh >> 1)] = (unsigned long long)clock64();
                         if (kh < 7) {
 #pragma unroll
@@ -336,8 +352,8 @@ mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restr
         const int r = threadIdx.x - 128;
         unsigned long long w_pee = 0;
         const long long f_t0 = clock64();
-        for (int it = 0; it < my_tiles; ++it) {
-            const int64_t row = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TILE_M + r;
+        for (int it = 0; it < my_iters; ++it) {
+            const int64_t row = tile_of(it) * TILE_M + r;
             float enc[64];
             float x[3] = {0.f, 0.f, 0.f};
             const bool live = row < rows;
@@ -366,7 +382,8 @@ mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restr
                 split_store8(enc + 8 * c8, sm + OFF_PE_HI + off, sm + OFF_PE_LO + off);
             }
             fence_proxy_async();
-            mbar_arrive(bar(BAR_PE_FULL));
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lbar(BAR_PE_FULL));
         }
         if (trace && threadIdx.x == 128) {
             trace[blockIdx.x * 16 + 8] = w_pee; trace[blockIdx.x * 16 + 9] = (unsigned long long)(clock64() - f_t0);
@@ -374,168 +391,77 @@ mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restr
     }
 
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();              // the leader's MMAs read the peer's shared memory and write its TMEM: leave together
     if (trace && threadIdx.x == 0) trace[blockIdx.x * 16 + 0] = (unsigned long long)(clock64() - k_t0);
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
     }
 }
 
-// ---------------------------------------------------------------------------- weight stream
-// Stage i of a tile = (GEMM step t, K-block kb, half) in MMA consumption order; the encoded-point
-// K-block comes first for steps 0 and 5.
-struct StageInfo { int step, k0, n, lo; };
+// ---------------------------------------------------------------------------- weight stream (two ranks)
+// Stage i of a tile = (GEMM step t, K-block, hi/lo) in MMA consumption order; the encoded-point K-block comes
+// first for steps 0 and 5.  Rank r holds output columns [r * N/2, (r+1) * N/2) of every stage.
+struct StageInfo { int step, k0, nh, lo; };
 __host__ __device__ inline StageInfo stage_info(int i) {
-    int kbi = i / 4, hk = (i >> 1) & 1, lo = i & 1, t = 0;  // order inside a K-block: (hi,k0-31) (lo,k0-31) (hi,k32-63) (lo,k32-63)
+    int kbi = i >> 1, lo = i & 1, t = 0;
     const int kbs[10] = {1, 4, 4, 4, 4, 5, 4, 4, 4, 4};
     while (kbi >= kbs[t]) { kbi -= kbs[t]; ++t; }
-    return {t, kbi * 64 + hk * 32, t == 9 ? 128 : 256, lo}; // wt[t] rows are already ordered [pe64 | h256]
+    return {t, kbi * 64, t == 9 ? 64 : 128, lo};           // wt[t] rows are already ordered [pe64 | h256]
 }
 
-__global__ void absmax_kernel(const float* __restrict__ w, int n, unsigned int* out) {
-    float m = 0.0f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (threadIdx.x % 32 == 0) atomicMax(out, __float_as_uint(m));
-}
-// scale[t] = 2^s with max|W| * 2^s in [1024, 2048); inv_scale[t] = 2^-s
-__global__ void scale_kernel(const unsigned int* __restrict__ absmax, float* __restrict__ scale, float* __restrict__ inv_scale) {
-    const int t = threadIdx.x;
-    if (t >= 10) return;
-    const float m = __uint_as_float(absmax[t]);
-    int s = 0;
-    if (m > 0.0f && isfinite(m)) s = 10 - ilogbf(m);
-    s = max(-24, min(24, s));
-    scale[t] = exp2f((float)s);
-    inv_scale[t] = exp2f((float)-s);
-}
 __global__ void pack_stream_kernel(const float* const* __restrict__ wt, const float* __restrict__ scale, __half* __restrict__ stream) {
-    const int i = blockIdx.x;                               // stage
+    const int i = blockIdx.x, rank = blockIdx.y;
     const StageInfo si = stage_info(i);
     const float* w = wt[si.step];
     const float sc = scale[si.step];
-    unsigned char* dst = reinterpret_cast<unsigned char*>(stream) + stage_offset_bytes(i);
-    for (int e = threadIdx.x; e < si.n * 32; e += blockDim.x) {
-        const int k = e / si.n, n = e % si.n;               // coalesced over n in the k-major source
-        const float v = w[(size_t)(si.k0 + k) * si.n + n] * sc;
+    const int N = 2 * si.nh;
+    unsigned char* dst = reinterpret_cast<unsigned char*>(stream) + (size_t)rank * rank_stream_bytes() + stage_offset_bytes(i);
+    for (int e = threadIdx.x; e < si.nh * 64; e += blockDim.x) {
+        const int k = e / si.nh, n = e % si.nh;             // coalesced over n in the k-major source
+        const float v = w[(size_t)(si.k0 + k) * N + rank * si.nh + n] * sc;
         const __half hi = __float2half_rn(v);
         const __half out = si.lo ? __float2half_rn(v - __half2float(hi)) : hi;
-        *reinterpret_cast<__half*>(dst + sw64_offset(n, k)) = out;
+        *reinterpret_cast<__half*>(dst + sw128_offset(n, k)) = out;
     }
 }
 
-}  // namespace tc
+}  // namespace tc2
 
-size_t tc_stream_halfs() { return tc::stage_offset_bytes(tc::STAGES_PER_TILE) / sizeof(__half); }
+size_t tc2_stream_halfs() { return 2 * tc2::rank_stream_bytes() / sizeof(__half); }
 
-int pack_tc_stream(bnrf_ctx* ctx, int net, cudaStream_t st) {
-    using namespace tc;
+// scale (device [10], computed by pack_tc_stream) -> the pair kernel's stream
+int pack_tc2_stream(bnrf_ctx* ctx, int net, const float* const* table_dev, const float* scale_dev, cudaStream_t st) {
+    using namespace tc2;
     NetParams& np = ctx->net[net];
-    // scratch inside tc_scale: [0,10) inv_scale (read by the kernel), then absmax bits / scale / pointer table live in
-    // a small side allocation made once per context.
-    static_assert(sizeof(unsigned int) == sizeof(float), "");
-    float* inv_scale = np.tc_scale;
-    unsigned int* absmax = nullptr;
-    float* scale = nullptr;
-    const float** table = nullptr;
-    BNRF_CUDA(ctx, cudaMallocAsync(&absmax, 16 * sizeof(unsigned int), st));
-    BNRF_CUDA(ctx, cudaMallocAsync(&scale, 16 * sizeof(float), st));
-    BNRF_CUDA(ctx, cudaMallocAsync(&table, 10 * sizeof(float*), st));
-    BNRF_CUDA(ctx, cudaMemsetAsync(absmax, 0, 16 * sizeof(unsigned int), st));
-    for (int t = 0; t < 10; ++t) absmax_kernel<<<32, 256, 0, st>>>(np.wt[t], gemm_k(t) * gemm_n(t), absmax + t);
-    scale_kernel<<<1, 32, 0, st>>>(absmax, scale, inv_scale);
-    BNRF_CUDA(ctx, cudaMemcpyAsync(table, np.wt, 10 * sizeof(float*), cudaMemcpyHostToDevice, st));
-    pack_stream_kernel<<<STAGES_PER_TILE, 256, 0, st>>>(table, scale, np.tc_stream);
+    pack_stream_kernel<<<dim3(STAGES_PER_TILE, 2), 256, 0, st>>>(table_dev, scale_dev, np.tc2_stream);
     BNRF_LAUNCH_CHECK(ctx);
-    {
-        const int rc2 = pack_tc2_stream(ctx, net, table, scale, st);
-        if (rc2 != BNRF_OK) return rc2;
-    }
-    BNRF_CUDA(ctx, cudaFreeAsync(absmax, st));
-    BNRF_CUDA(ctx, cudaFreeAsync(scale, st));
-    BNRF_CUDA(ctx, cudaFreeAsync(table, st));
     return BNRF_OK;
 }
 
-int launch_mlp_tc(bnrf_ctx* ctx, int net, const float* o, const float* d, const float* vb, const float* z,
-                  int64_t n, int S, float* raw, cudaStream_t st) {
-    using namespace tc;
+int launch_mlp_tc2(bnrf_ctx* ctx, int net, const float* o, const float* d, const float* vb, const float* z,
+                   int64_t n, int S, float* raw, cudaStream_t st) {
+    using namespace tc2;
     const NetParams& np = ctx->net[net];
     TcParams p;
-    p.stream = np.tc_stream; p.inv_scale = np.tc_scale;
+    p.stream = np.tc2_stream; p.inv_scale = np.tc_scale;
     for (int i = 0; i < 10; ++i) p.bias[i] = np.bias[i];
     p.w_alpha = np.w_alpha; p.b_alpha = np.b_alpha; p.w_rgb = np.w_rgb; p.b_rgb = np.b_rgb;
     const int64_t rows = n * S;
-    const int64_t tiles64 = ceil_div(rows, TILE_M);
-    if (tiles64 > 0x7fffffff) return fail(ctx, BNRF_ERR_ARG, "mlp: too many rows");
-    const int tiles = (int)tiles64;
-    const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+    const int64_t pairs64 = ceil_div(rows, 2 * TILE_M);
+    if (pairs64 > 0x3fffffff) return fail(ctx, BNRF_ERR_ARG, "mlp: too many rows");
+    const int pairs = (int)pairs64;
+    const int max_clusters = ctx->sm_count / 2;
+    const int clusters = pairs < max_clusters ? pairs : max_clusters;
     if (ctx->cfg.channels == 3) {
-        BNRF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        mlp_tc_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p, o, d, vb, z, rows, S, tiles, raw, ctx->err_flag, ctx->trace);
+        BNRF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        mlp_tc2_kernel<3><<<2 * clusters, NUM_THREADS, SMEM_BYTES, st>>>(p, o, d, vb, z, rows, S, pairs, raw, ctx->err_flag, ctx->trace);
     } else {
-        BNRF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        mlp_tc_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p, o, d, vb, z, rows, S, tiles, raw, ctx->err_flag, ctx->trace);
+        BNRF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        mlp_tc2_kernel<1><<<2 * clusters, NUM_THREADS, SMEM_BYTES, st>>>(p, o, d, vb, z, rows, S, pairs, raw, ctx->err_flag, ctx->trace);
     }
     BNRF_LAUNCH_CHECK(ctx);
     return BNRF_OK;
 }
 
-// ---------------------------------------------------------------------------- UMMA probe
-// D[128 x N] = A[128 x 64] * B[N x 64]^T for fp16 inputs given in plain row-major global memory.
-// Uses the same swizzle, descriptor, MMA and TMEM-load helpers as the MLP kernel so that the
-// layout conventions can be validated in isolation (tests/test_gpu_probe.py).
-__global__ void __launch_bounds__(128, 1)
-umma_probe_kernel(const __half* __restrict__ A, const __half* __restrict__ B, int N, uint32_t lbo_field, float* __restrict__ D) {
-    using namespace tc;
-    extern __shared__ unsigned char smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    unsigned char* sm = smem_raw + (base - smem_u32(smem_raw));
-    __shared__ uint32_t tmem_slot;
-    __shared__ __align__(8) uint64_t done_bar;
-    const int warp = threadIdx.x / 32;
-    for (int e = threadIdx.x; e < 128 * 64; e += 128) *reinterpret_cast<__half*>(sm + sw128_offset(e / 64, e % 64)) = A[e];
-    for (int e = threadIdx.x; e < N * 64; e += 128) *reinterpret_cast<__half*>(sm + KBLOCK_BYTES + sw128_offset(e / 64, e % 64)) = B[e];
-    if (threadIdx.x == 0) { mbar_init(smem_u32(&done_bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = tmem_slot;
-    if (threadIdx.x == 0) {
-        const uint32_t idesc = make_idesc(128, N);
-        for (int kk = 0; kk < 4; ++kk)
-            tc_mma_f16(tmem, make_desc(base + kk * 32, lbo_field), make_desc(base + KBLOCK_BYTES + kk * 32, lbo_field), idesc, kk > 0);
-        tc_commit(smem_u32(&done_bar));
-    }
-    mbar_wait(smem_u32(&done_bar), 0, nullptr, 0);
-    tc_fence_after();
-    const int r = threadIdx.x;
-    for (int c0 = 0; c0 < N; c0 += 32) {
-        float v[32];
-        tc_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
-        for (int j = 0; j < 32; ++j) D[(size_t)r * N + c0 + j] = v[j];
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u));
-    }
-}
-
 }  // namespace bnrf
-
-extern "C" int bnrf_debug_umma_probe(const void* A_half, const void* B_half, int N, int lbo_field, float* D, void* stream) {
-    using namespace bnrf;
-    if (!A_half || !B_half || !D || N < 16 || N > 256 || N % 16) return BNRF_ERR_ARG;
-    const size_t smem = tc::KBLOCK_BYTES + 32768 + 1024;
-    if (cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return BNRF_ERR_CUDA;
-    umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __half*)A_half, (const __half*)B_half, N, (uint32_t)lbo_field, D);
-    return cudaGetLastError() == cudaSuccess ? BNRF_OK : BNRF_ERR_CUDA;
-}

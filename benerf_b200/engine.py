@@ -12,7 +12,7 @@ from ._lib import BnrfError
 
 TRAJ = {"spline": 0, "linear": 1}
 LOG_MODE = {"BeNeRF_Blender": 0, "BeNeRF_Unreal": 0, "E2NeRF_Synthetic": 1, "E2NeRF_Real": 1, "safelog": 0, "linlog": 1}
-MLP_MODES = {"tc": _lib.MLP_TC_FP16X2, "simt": _lib.MLP_SIMT_FP32}
+MLP_MODES = {"tc": _lib.MLP_TC_FP16X2, "simt": _lib.MLP_SIMT_FP32, "tc1": _lib.MLP_TC_1CTA}
 
 
 def _stream():

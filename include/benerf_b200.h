@@ -45,6 +45,7 @@ typedef enum {
 /* MLP arithmetic (cfg.mlp_mode).  Both run on the GPU; there is no host path. */
 #define BNRF_MLP_TC_FP16X2 0  /* tcgen05.mma kind::f16, 2-term split operands (hi*hi + lo*hi + hi*lo), fp32 TMEM accumulate */
 #define BNRF_MLP_SIMT_FP32 1  /* plain fp32 FFMA; on-device cross-check of the tensor-core path */
+#define BNRF_MLP_TC_1CTA 2    /* same arithmetic as mode 0 on single CTAs (cta_group::1); mode 0 runs CTA pairs (cta_group::2) */
 
 /* Order of the 12 linears in bnrf_set_weights (the reference's state-dict order). */
 enum {

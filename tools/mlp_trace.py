@@ -16,7 +16,7 @@ def main():
     case = CASES["unreal_rgb"]
     inp = make_inputs(case)
     dev = "cuda"
-    eng = Engine()
+    eng = Engine(mlp_mode=os.environ.get('MLP_MODE', 'tc'))
     eng.set_weights(1, {k: v.to(dev) for k, v in inp["fine"].items()})
     g = torch.Generator().manual_seed(0)
     o = (torch.rand(n_rays, 3, generator=g) * 2 - 1).to(dev)
