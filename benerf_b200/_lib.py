@@ -30,8 +30,9 @@ class Outputs(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0", "sigma", "depth_map", "z_vals")]
 
 
-class BackwardGrads(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in ("rgb_map", "rgb0")]
+class ParamGrads(C.Structure):
+    """bnrf_param_grads: 12 weight + 12 bias gradient pointers (PyTorch layouts, accumulated into)."""
+    _fields_ = [("weights", C.c_void_p * 12), ("biases", C.c_void_p * 12)]
 
 
 _P, _I, _L, _Z = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
@@ -46,6 +47,12 @@ PROTOTYPES = {
     "bnrf_spline_poses": (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
     "bnrf_workspace_bytes": (_Z, [_P, _L]),
     "bnrf_render_forward": (_I, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(C.c_float), _P, C.POINTER(Rng), C.POINTER(Outputs), _P, _Z, _P]),
+    "bnrf_saved_bytes": (_Z, [_P, _L]),
+    "bnrf_backward_workspace_bytes": (_Z, [_P, _L]),
+    "bnrf_render_forward_train": (_I, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(C.c_float), _P, C.POINTER(Rng), C.POINTER(Outputs), _P, _Z, _P, _Z, _P]),
+    "bnrf_render_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(C.c_float), _P, _P, _P, _P, _Z, C.POINTER(ParamGrads), C.POINTER(ParamGrads), _P, _P, _Z, _P]),
+    "bnrf_spline_poses_backward": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "bnrf_debug_sgemm": (_I, [_P, _I, _I, _L, _I, _L, _P, _L, _P, _L, _P, _L, _I, _P, _L, _P, _L, _P, _P]),
     "bnrf_op_rays": (_I, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(C.c_float), _P, _P, _P, _P, _P]),
     "bnrf_op_stratified": (_I, [_P, _P, _L, _I, _P, _P]),
     "bnrf_op_mlp": (_I, [_P, _I, _P, _P, _P, _P, _L, _I, _P, _P]),
@@ -53,6 +60,8 @@ PROTOTYPES = {
     "bnrf_op_resample": (_I, [_P, _P, _P, _P, _L, _I, _I, _P, _P]),
     "bnrf_blur_mean": (_I, [_P, _I, _L, _I, _P, _P]),
     "bnrf_event_logdiff": (_I, [_P, _I, _L, _I, _I, _P, _P]),
+    "bnrf_blur_mean_backward": (_I, [_P, _I, _L, _I, _P, _P]),
+    "bnrf_event_logdiff_backward": (_I, [_P, _P, _I, _L, _I, _I, _P, _P]),
     "bnrf_accumulate_events": (_I, [_P, _P, _P, _L, _I, _I, _P, _P]),
     "bnrf_profile": (_I, [_P, _I]),
     "bnrf_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

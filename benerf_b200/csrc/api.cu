@@ -121,13 +121,15 @@ static Workspace carve(const bnrf_cfg& c, int64_t n, void* base) {
 }
 
 static int run_mlp(bnrf_ctx* ctx, int net, const float* o, const float* d, const float* vb, const float* z, int64_t n,
-                   int S, float* raw, cudaStream_t st) {
+                   int S, float* raw, float* acts, cudaStream_t st) {
     if (!ctx->net[net].ready) return fail(ctx, BNRF_ERR_STATE, "weights of network %d not set (bnrf_set_weights)", net);
     const double macs = 63.0 * 256 + 4 * 65536.0 + 319.0 * 256 + 2 * 65536.0 + 256 + 65536.0 + 283.0 * 128 + 128.0 * ctx->cfg.channels;
     MlpTimer timer(ctx, st, 2.0 * macs * (double)n * (double)S);
+    if (acts && ctx->cfg.mlp_mode != BNRF_MLP_TC_FP16X2)
+        return fail(ctx, BNRF_ERR_STATE, "training mode (saved activations) needs mlp_mode BNRF_MLP_TC_FP16X2");
     if (ctx->cfg.mlp_mode == BNRF_MLP_SIMT_FP32) return launch_mlp_simt(ctx, net, o, d, vb, z, n, S, raw, st);
     if (ctx->cfg.mlp_mode == BNRF_MLP_TC_1CTA) return launch_mlp_tc(ctx, net, o, d, vb, z, n, S, raw, st);
-    return launch_mlp_tc2(ctx, net, o, d, vb, z, n, S, raw, st);
+    return launch_mlp_tc2(ctx, net, o, d, vb, z, n, S, raw, acts, st);
 }
 
 }  // namespace bnrf
@@ -242,14 +244,23 @@ int bnrf_spline_poses(bnrf_ctx* ctx, const float* knots, const float* transform,
     return launch_spline(ctx, knots, transform, ts, P, traj, poses_out, (cudaStream_t)stream);
 }
 
+int bnrf_spline_poses_backward(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts, int P, int traj,
+                               const float* d_poses, float* d_knots, float* d_transform, void* stream) {
+    if (!ctx) return BNRF_ERR_ARG;
+    return launch_spline_backward(ctx, knots, transform, ts, P, traj, d_poses, d_knots, d_transform, (cudaStream_t)stream);
+}
+
 size_t bnrf_workspace_bytes(const bnrf_ctx* ctx, int64_t n_rays) {
     if (!ctx || n_rays <= 0) return 0;
     return carve(ctx->cfg, n_rays, nullptr).bytes;
 }
 
-int bnrf_render_forward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W,
-                        const float* K, const float* remap, const bnrf_rng* rng, const bnrf_outputs* out,
-                        void* workspace, size_t workspace_bytes, void* stream) {
+// Shared body of bnrf_render_forward / bnrf_render_forward_train.  With `saved` the per-ray tensors the backward pass
+// needs (rays, depths, raw outputs, densities) are placed in the caller's saved buffer instead of the scratch
+// workspace and the MLP kernel also writes its activations there.
+static int render_impl(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W,
+                       const float* K, const float* remap, const bnrf_rng* rng, const bnrf_outputs* out,
+                       void* workspace, size_t workspace_bytes, void* saved, size_t saved_bytes, void* stream) {
     if (!ctx) return BNRF_ERR_ARG;
     if (!poses || !ray_idx || !K || !out || !workspace || P <= 0 || R <= 0) return fail(ctx, BNRF_ERR_ARG, "render_forward: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
@@ -257,6 +268,15 @@ int bnrf_render_forward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_id
     const int64_t n = (int64_t)P * R;
     Workspace w = carve(c, n, workspace);
     if (workspace_bytes < w.bytes) return fail(ctx, BNRF_ERR_STATE, "render_forward: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
+    SavedLayout s{};
+    float* raw_c = w.raw; float* raw_f = w.raw;
+    float* sig_c = nullptr; float* sig_f = nullptr;
+    if (saved) {
+        s = carve_saved(c, n, saved);
+        if (saved_bytes < s.bytes) return fail(ctx, BNRF_ERR_STATE, "render_forward_train: saved buffer %zu < %zu bytes", saved_bytes, s.bytes);
+        w.o = s.o; w.d = s.d; w.view = s.view; w.z_c = s.z_c; w.z_f = s.z_f;
+        raw_c = s.raw_c; raw_f = s.raw_f; sig_c = s.sig_c; sig_f = s.sig_f;
+    }
     bnrf_rng r = rng ? *rng : bnrf_rng{};
     const bool fine = c.n_importance > 0;
     const int Sc = c.n_samples, Sf = c.n_samples + c.n_importance;
@@ -264,13 +284,14 @@ int bnrf_render_forward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_id
     if ((rc = launch_rays(ctx, poses, ray_idx, P, R, H, W, K, remap, w.o, w.d, w.view, st))) return rc;
     if ((rc = launch_stratified(ctx, r.t_rand, &r, n, Sc, w.z_c, st))) return rc;
     if ((rc = launch_viewbias(ctx, 0, w.view, n, w.vb, st))) return rc;
-    if ((rc = run_mlp(ctx, 0, w.o, w.d, w.vb, w.z_c, n, Sc, w.raw, st))) return rc;
+    if ((rc = run_mlp(ctx, 0, w.o, w.d, w.vb, w.z_c, n, Sc, raw_c, s.acts_c, st))) return rc;
     // coarse composite: outputs go to rgb0/disp0/acc0 when a fine pass follows (model/nerf.py:319-343)
-    if ((rc = launch_composite(ctx, w.raw, w.z_c, w.d, r.noise_c, &r, kStreamNoiseC, n, Sc,
+    float* sigma_c_out = saved ? sig_c : (fine ? nullptr : out->sigma);
+    if ((rc = launch_composite(ctx, raw_c, w.z_c, w.d, r.noise_c, &r, kStreamNoiseC, n, Sc,
                                fine ? out->rgb0 : out->rgb_map, fine ? out->disp0 : out->disp_map,
-                               fine ? out->acc0 : out->acc_map, w.w_c, fine ? nullptr : out->depth_map,
-                               fine ? nullptr : out->sigma, st))) return rc;
+                               fine ? out->acc0 : out->acc_map, w.w_c, fine ? nullptr : out->depth_map, sigma_c_out, st))) return rc;
     if (!fine) {
+        if (saved && out->sigma) BNRF_CUDA(ctx, cudaMemcpyAsync(out->sigma, sig_c, (size_t)n * Sc * sizeof(float), cudaMemcpyDeviceToDevice, st));
         if (out->z_vals) BNRF_CUDA(ctx, cudaMemcpyAsync(out->z_vals, w.z_c, (size_t)n * Sc * sizeof(float), cudaMemcpyDeviceToDevice, st));
         return BNRF_OK;
     }
@@ -281,9 +302,24 @@ int bnrf_render_forward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_id
     }
     if (out->z_vals) BNRF_CUDA(ctx, cudaMemcpyAsync(out->z_vals, w.z_f, (size_t)n * Sf * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if ((rc = launch_viewbias(ctx, 1, w.view, n, w.vb, st))) return rc;
-    if ((rc = run_mlp(ctx, 1, w.o, w.d, w.vb, w.z_f, n, Sf, w.raw, st))) return rc;
-    return launch_composite(ctx, w.raw, w.z_f, w.d, r.noise_f, &r, kStreamNoiseF, n, Sf, out->rgb_map, out->disp_map,
-                            out->acc_map, nullptr, out->depth_map, out->sigma, st);
+    if ((rc = run_mlp(ctx, 1, w.o, w.d, w.vb, w.z_f, n, Sf, raw_f, s.acts_f, st))) return rc;
+    if ((rc = launch_composite(ctx, raw_f, w.z_f, w.d, r.noise_f, &r, kStreamNoiseF, n, Sf, out->rgb_map, out->disp_map,
+                               out->acc_map, nullptr, out->depth_map, saved ? sig_f : out->sigma, st))) return rc;
+    if (saved && out->sigma) BNRF_CUDA(ctx, cudaMemcpyAsync(out->sigma, sig_f, (size_t)n * Sf * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return BNRF_OK;
+}
+
+int bnrf_render_forward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W,
+                        const float* K, const float* remap, const bnrf_rng* rng, const bnrf_outputs* out,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    return render_impl(ctx, poses, ray_idx, P, R, H, W, K, remap, rng, out, workspace, workspace_bytes, nullptr, 0, stream);
+}
+
+int bnrf_render_forward_train(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W,
+                              const float* K, const float* remap, const bnrf_rng* rng, const bnrf_outputs* out,
+                              void* workspace, size_t workspace_bytes, void* saved, size_t saved_bytes, void* stream) {
+    if (!saved) return fail(ctx, BNRF_ERR_ARG, "render_forward_train: saved buffer is null");
+    return render_impl(ctx, poses, ray_idx, P, R, H, W, K, remap, rng, out, workspace, workspace_bytes, saved, saved_bytes, stream);
 }
 
 int bnrf_op_rays(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W, const float* K,
@@ -307,7 +343,7 @@ int bnrf_op_mlp(bnrf_ctx* ctx, int net, const float* rays_o, const float* rays_d
     BNRF_CUDA(ctx, cudaMallocAsync(&vb, (size_t)n_rays * kHalf * sizeof(float), st));
     int rc = ctx->net[net].ready ? launch_viewbias(ctx, net, viewdirs, n_rays, vb, st)
                                  : fail(ctx, BNRF_ERR_STATE, "weights of network %d not set", net);
-    if (rc == BNRF_OK) rc = run_mlp(ctx, net, rays_o, rays_d, vb, z, n_rays, S, raw, st);
+    if (rc == BNRF_OK) rc = run_mlp(ctx, net, rays_o, rays_d, vb, z, n_rays, S, raw, nullptr, st);
     cudaFreeAsync(vb, st);
     return rc;
 }

@@ -1,0 +1,535 @@
+// Backward pass of Graph.render (the part of train.py:340 loss.backward() that runs through
+// model/nerf.py:236-343): d(rgb_map, rgb0) -> d(NeRF parameters of both networks), d(poses).
+//
+// The forward pass in training mode (bnrf_render_forward_train) keeps, per network, the encoded
+// points and the nine hidden activations of every sample (written by the tensor-core kernel's
+// epilogue, mlp_tc2.cu) plus raw / z / sigma.  The backward pass is layer-by-layer:
+//   composite_backward   raw2output (model/nerf.py:118-148): sigmoid, relu(sigma+noise), alpha,
+//                        exclusive cumprod, sum(w*rgb) -- one warp per ray, suffix scan
+//   heads / dgrad / wgrad the 12 linears of NeRF.forward (model/nerf.py:93-112) through sgemm.cu
+//   pe_ray_backward      sin/cos encoding (model/embedder.py:9-34) and pts = o + d*z
+//   viewdir_backward     direction encoding + the per-ray view bias
+//   rays_backward        ndc_rays + get_specific_rays + viewdirs (run_nerf_helpers.py:35-71) -> d poses
+// z_vals carry no gradient (stratified depths have no parameters; z_samples are detached,
+// model/nerf.py:324), exactly as in the reference.  d poses -> d knots is pose.cu (dual numbers).
+#include "common.cuh"
+#include "sgemm.cuh"
+
+namespace bnrf {
+
+namespace {
+
+constexpr int kWarps = 4;
+
+__device__ inline double wsum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ inline float wsumf(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------ raw2output backward
+// g_rgb [N,C] = dL/d rgb_map.  Writes d_raw [N,S,C+1]; adds dL/d|rays_d| to d_dnorm [N].
+template <int C>
+__global__ void composite_backward_kernel(const float* __restrict__ raw, const float* __restrict__ z,
+                                          const float* __restrict__ sigma, const float* __restrict__ rays_d,
+                                          const float* __restrict__ g_rgb, int64_t n_rays, int S,
+                                          float* __restrict__ d_raw, float* __restrict__ d_dnorm) {
+    const int lane = threadIdx.x % 32;
+    const int64_t ray = (int64_t)blockIdx.x * kWarps + threadIdx.x / 32;
+    if (ray >= n_rays) return;
+    const int K = (S + 31) / 32;
+    constexpr int MAXK = kMaxSamples / 32;
+    const float* rd = rays_d + ray * 3;
+    const float dn = sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]);
+    const float* zr = z + ray * S;
+    const float* rr = raw + ray * S * (C + 1);
+    const float* sg = sigma + ray * S;
+    float g[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < C; ++c) g[c] = g_rgb[ray * C + c];
+    float em[MAXK], gap[MAXK];                  // exp(-sigma*delta) = 1 - alpha; z gap (delta / |d|)
+    double prod = 1.0;
+    for (int k = 0; k < K; ++k) {
+        const int s = lane * K + k;
+        em[k] = 1.0f; gap[k] = 0.0f;
+        if (s < S) {
+            gap[k] = (s + 1 < S) ? zr[s + 1] - zr[s] : 1e10f;
+            em[k] = expf(-sg[s] * (gap[k] * dn));
+            prod *= (double)((1.0f - (1.0f - em[k])) + 1e-10f);
+        }
+    }
+    // exclusive prefix product of (1 - alpha + 1e-10) across lanes
+    double inc = prod;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc *= t;
+    }
+    double t_run = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) t_run = 1.0;
+    float Tk[MAXK], Ak[MAXK];
+    double local = 0.0;                          // sum of A_k * w_k over this lane's samples
+    for (int k = 0; k < K; ++k) {
+        const int s = lane * K + k;
+        Tk[k] = 0.f; Ak[k] = 0.f;
+        if (s < S) {
+            const float alpha = 1.0f - em[k];
+            const float T = (float)t_run;
+            float A = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) A = fmaf(g[c], 1.0f / (1.0f + expf(-rr[s * (C + 1) + c])), A);
+            Tk[k] = T; Ak[k] = A;
+            local += (double)A * (double)(alpha * T);
+            t_run *= (double)((1.0f - alpha) + 1e-10f);
+        }
+    }
+    // suffix sum over later samples: lanes after this one, then this lane's own later samples
+    double incs = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, incs, o);
+        if (lane >= o) incs += t;
+    }
+    const double total = __shfl_sync(0xffffffffu, incs, 31);
+    double after = total - incs;                 // sum over lanes > lane
+    float dn_acc = 0.f;
+    for (int k = K - 1; k >= 0; --k) {
+        const int s = lane * K + k;
+        if (s < S) {
+            const float alpha = 1.0f - em[k];
+            const float f = (1.0f - alpha) + 1e-10f;
+            const float T = Tk[k], A = Ak[k];
+            const float w = alpha * T;
+            const float dalpha = A * T - (float)(after / (double)f);
+            const float delta = gap[k] * dn;
+            const float sig = sg[s];
+            const float dsig = dalpha * delta * em[k];
+            d_raw[(ray * S + s) * (C + 1) + C] = (sig > 0.0f) ? dsig : 0.0f;
+            const float ddelta = dalpha * sig * em[k];
+            dn_acc = fmaf(ddelta, gap[k], dn_acc);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float col = 1.0f / (1.0f + expf(-rr[s * (C + 1) + c]));
+                d_raw[(ray * S + s) * (C + 1) + c] = g[c] * w * col * (1.0f - col);
+            }
+            after += (double)A * (double)w;
+        }
+    }
+    dn_acc = wsumf(dn_acc);
+    if (lane == 0) d_dnorm[ray] += dn_acc;
+}
+
+// ------------------------------------------------------------------ rgb head backward + ReLU of the view layer
+// dZ9[row][j] = (H9[row][j] > 0) * sum_c d_raw[row][c] * W_rgb[c][j]
+template <int C>
+__global__ void heads_backward_kernel(const float* __restrict__ d_raw, const float* __restrict__ h9,
+                                      const float* __restrict__ w_rgb, int64_t rows, float* __restrict__ dz9) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * kHalf) return;
+    const int64_t row = e / kHalf;
+    const int j = (int)(e % kHalf);
+    float v = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) v = fmaf(d_raw[row * (C + 1) + c], w_rgb[c * kHalf + j], v);
+    dz9[e] = (h9[e] > 0.0f) ? v : 0.0f;
+}
+
+// dvb[ray][j] = sum_s dZ9[ray*S + s][j]  (the view bias is shared by the S samples of a ray)
+__global__ void sum_samples_kernel(const float* __restrict__ dz9, int S, float* __restrict__ dvb) {
+    const int64_t ray = blockIdx.x;
+    const int j = threadIdx.x;
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc += dz9[(ray * S + s) * kHalf + j];
+    dvb[ray * kHalf + j] = acc;
+}
+
+// out[n] += sum_rows X[row*ld + n]
+__global__ void colsum_kernel(const float* __restrict__ X, int64_t rows, int N, int64_t ld, int64_t rows_per_block,
+                              float* __restrict__ out) {
+    const int n = blockIdx.y * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
+    float acc = 0.f;
+    for (int64_t r = r0; r < r1; ++r) acc += X[r * ld + n];
+    atomicAdd(out + n, acc);
+}
+
+// ------------------------------------------------------------------ view-direction branch
+// per ray: encoding of the unit view direction (27 values, padded to 32), d enc = dvb * W_dir^T, d view
+__global__ void viewdir_backward_kernel(const float* __restrict__ view, const float* __restrict__ dvb,
+                                        const float* __restrict__ w_dir /*[27][128]*/, int64_t n_rays,
+                                        float* __restrict__ pe_dir /*[N,32]*/, float* __restrict__ d_view /*[N,3] +=*/) {
+    const int lane = threadIdx.x % 32;
+    const int64_t ray = (int64_t)blockIdx.x * kWarps + threadIdx.x / 32;
+    if (ray >= n_rays) return;
+    const float v[3] = {view[ray * 3], view[ray * 3 + 1], view[ray * 3 + 2]};
+    float enc[kDirCh];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) enc[c] = v[c];
+#pragma unroll
+    for (int k = 0; k < kDirFreqs; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float s, co;
+            sincosf(v[c] * (float)(1 << k), &s, &co);
+            enc[3 + 6 * k + c] = s;
+            enc[3 + 6 * k + 3 + c] = co;
+        }
+    float g4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g4[q] = dvb[ray * kHalf + lane + 32 * q];
+    float denc[kDirCh];
+#pragma unroll
+    for (int i = 0; i < kDirCh; ++i) {
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a = fmaf(g4[q], w_dir[i * kHalf + lane + 32 * q], a);
+        denc[i] = wsumf(a);
+    }
+    if (lane < 32) {
+        float e = 0.f;
+#pragma unroll
+        for (int i = 0; i < kDirCh; ++i) if (lane == i) e = enc[i];
+        pe_dir[ray * 32 + lane] = e;            // lanes 27..31 write the zero padding
+    }
+    if (lane < 3) {
+        float dv = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (lane != c) continue;
+            dv = denc[c];
+#pragma unroll
+            for (int k = 0; k < kDirFreqs; ++k) {
+                const float f = (float)(1 << k);
+                dv += f * (enc[3 + 6 * k + 3 + c] * denc[3 + 6 * k + c] - enc[3 + 6 * k + c] * denc[3 + 6 * k + 3 + c]);
+            }
+        }
+        d_view[ray * 3 + lane] += dv;
+    }
+}
+
+// ------------------------------------------------------------------ point encoding + pts = o + d*z
+// per ray: d_o += sum_s d_pts, d_d += sum_s z * d_pts with d_pts from d_pe through the saved sin/cos
+__global__ void pe_ray_backward_kernel(const float* __restrict__ pe, const float* __restrict__ d_pe,
+                                       const float* __restrict__ z, int64_t n_rays, int S,
+                                       float* __restrict__ d_o, float* __restrict__ d_d) {
+    const int lane = threadIdx.x % 32;
+    const int64_t ray = (int64_t)blockIdx.x * kWarps + threadIdx.x / 32;
+    if (ray >= n_rays) return;
+    float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};
+    for (int s = lane; s < S; s += 32) {
+        const int64_t row = ray * S + s;
+        const float4* p4 = reinterpret_cast<const float4*>(pe + row * kPtsChPad);
+        const float4* g4 = reinterpret_cast<const float4*>(d_pe + row * kPtsChPad);
+        float p[64], g[64];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float4 a = p4[i], b = g4[i];
+            p[4 * i] = a.x; p[4 * i + 1] = a.y; p[4 * i + 2] = a.z; p[4 * i + 3] = a.w;
+            g[4 * i] = b.x; g[4 * i + 1] = b.y; g[4 * i + 2] = b.z; g[4 * i + 3] = b.w;
+        }
+        const float zz = z[row];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float dx = g[c];
+#pragma unroll
+            for (int k = 0; k < kPtsFreqs; ++k)
+                dx += (float)(1 << k) * (p[3 + 6 * k + 3 + c] * g[3 + 6 * k + c] - p[3 + 6 * k + c] * g[3 + 6 * k + 3 + c]);
+            go[c] += dx;
+            gd[c] = fmaf(zz, dx, gd[c]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { go[c] = wsumf(go[c]); gd[c] = wsumf(gd[c]); }
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { d_o[ray * 3 + c] += go[c]; d_d[ray * 3 + c] += gd[c]; }
+    }
+}
+
+// ------------------------------------------------------------------ rays: ndc, viewdirs, R*dir, origin -> d poses
+__global__ void rays_backward_kernel(const float* __restrict__ poses, const int64_t* __restrict__ ray_idx, int P, int R,
+                                     int H, int W, float fx, float fy, float cx, float cy, const float* __restrict__ remap,
+                                     int ndc, const float* __restrict__ g_o_in, const float* __restrict__ g_d_in,
+                                     const float* __restrict__ g_v_in, const float* __restrict__ g_dn_in,
+                                     float* __restrict__ d_poses /*[P,12] +=*/) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = n < (int64_t)P * R;
+    int p = 0;
+    float gp[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) gp[i] = 0.f;
+    if (live) {
+        p = (int)(n / R);
+        const int64_t pix = ray_idx[n % R];
+        float fi = (float)(pix % W), fj = (float)(pix / W);
+        if (remap) { fi = remap[2 * pix]; fj = remap[2 * pix + 1]; }
+        const float* c2w = poses + (size_t)p * 12;
+        const float dir[3] = {(fi - cx) / fx, -(fj - cy) / fy, -1.0f};
+        float d[3], o[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            d[r] = dir[0] * c2w[r * 4] + dir[1] * c2w[r * 4 + 1] + dir[2] * c2w[r * 4 + 2];
+            o[r] = c2w[r * 4 + 3];
+        }
+        float gO[3] = {g_o_in[n * 3], g_o_in[n * 3 + 1], g_o_in[n * 3 + 2]};
+        float gD[3] = {g_d_in[n * 3], g_d_in[n * 3 + 1], g_d_in[n * 3 + 2]};
+        const float gV[3] = {g_v_in[n * 3], g_v_in[n * 3 + 1], g_v_in[n * 3 + 2]};
+        const float g_dn = g_dn_in[n];
+        float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};   // w.r.t. the pre-ndc origin / direction
+        if (ndc) {
+            const float near = 1.0f;
+            const float t = -(near + o[2]) / d[2];
+            float op[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) op[r] = o[r] + t * d[r];
+            const float sx = -1.0f / ((float)W / (2.0f * fx)), sy = -1.0f / ((float)H / (2.0f * fx));
+            // post-ndc direction (for the |rays_d| term of raw2output, model/nerf.py:124)
+            const float D[3] = {sx * (d[0] / d[2] - op[0] / op[2]), sy * (d[1] / d[2] - op[1] / op[2]), -2.0f * near / op[2]};
+            const float Dn = sqrtf(D[0] * D[0] + D[1] * D[1] + D[2] * D[2]);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) gD[r] += g_dn * D[r] / Dn;
+            const float i2 = 1.0f / op[2], i22 = i2 * i2;
+            float gop[3];
+            gop[0] = sx * i2 * (gO[0] - gD[0]);
+            gop[1] = sy * i2 * (gO[1] - gD[1]);
+            gop[2] = i22 * (-sx * op[0] * gO[0] - sy * op[1] * gO[1] - 2.0f * near * gO[2]
+                            + sx * op[0] * gD[0] + sy * op[1] * gD[1] + 2.0f * near * gD[2]);
+            const float id2 = 1.0f / d[2];
+            gd[0] = sx * gD[0] * id2;
+            gd[1] = sy * gD[1] * id2;
+            gd[2] = -(sx * d[0] * gD[0] + sy * d[1] * gD[1]) * id2 * id2;
+            float gt = 0.f;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { go[r] = gop[r]; gd[r] += t * gop[r]; gt += gop[r] * d[r]; }
+            go[2] += -gt * id2;
+            gd[2] += gt * (near + o[2]) * id2 * id2;
+        } else {
+            const float Dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { go[r] = gO[r]; gd[r] = gD[r] + g_dn * d[r] / Dn; }
+        }
+        // viewdirs = d / |d| (pre-ndc, model/nerf.py:272-275)
+        const float nrm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        const float v[3] = {d[0] / nrm, d[1] / nrm, d[2] / nrm};
+        const float vg = v[0] * gV[0] + v[1] * gV[1] + v[2] * gV[2];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) gd[r] += (gV[r] - v[r] * vg) / nrm;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            gp[r * 4 + 0] = gd[r] * dir[0]; gp[r * 4 + 1] = gd[r] * dir[1]; gp[r * 4 + 2] = gd[r] * dir[2];
+            gp[r * 4 + 3] = go[r];
+        }
+    }
+    // warp-level reduction when the whole warp works on one pose (the common case in pose-major order)
+    const int p0 = __shfl_sync(0xffffffffu, p, 0);
+    const bool uniform = __all_sync(0xffffffffu, !live || p == p0);
+    const bool any_live = __any_sync(0xffffffffu, live);
+    if (uniform) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const float s = wsumf(gp[i]);
+            if ((threadIdx.x % 32) == 0 && any_live) atomicAdd(d_poses + (size_t)p0 * 12 + i, s);
+        }
+    } else if (live) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) atomicAdd(d_poses + (size_t)p * 12 + i, gp[i]);
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ per-network MLP backward
+// d_raw [rows, C+1] -> parameter gradients (PyTorch layouts, accumulated) and d_pe [rows,64], dvb [n,128].
+struct BwdBuffers {
+    float *d_raw, *buf_a, *buf_b, *d_pe, *dz9, *dvb, *pe_dir;
+};
+
+static int mlp_backward(bnrf_ctx* ctx, int net, int64_t n, int S, const float* acts, const BwdBuffers& w,
+                        float* const* dW, float* const* dB, cudaStream_t st) {
+    const NetParams& np = ctx->net[net];
+    const int C = ctx->cfg.channels;
+    const int64_t rows = n * S;
+    const float* pe = acts;
+    auto H = [&](int l) { return acts + rows * kPtsChPad + (int64_t)l * rows * kWidth; };   // l = 0..7, 8 = feature
+    const float* h9 = acts + rows * (kPtsChPad + 9 * kWidth);
+    int rc;
+    auto colsum = [&](const float* X, int N, int64_t ld, int64_t cnt, float* out) {
+        const int64_t rpb = 512;
+        colsum_kernel<<<dim3((unsigned)ceil_div(cnt, rpb), (unsigned)ceil_div(N, 128)), 128, 0, st>>>(X, cnt, N, ld, rpb, out);
+        ctx->launches++;
+    };
+    // wgrad: dW[n_out][col0 + k] += sum_rows dZ[row][n_out] * A[row][k]
+    auto wgrad = [&](const float* dZ, int n_out, int64_t ldz, const float* A, int k_in, int64_t lda, float* dWl, int64_t ldw, int col0) {
+        GemmArgs g{};
+        g.M = n_out; g.N = k_in; g.K = rows; g.A = dZ; g.lda = ldz; g.B = A; g.ldb = lda;
+        g.C = dWl + col0; g.ldc = ldw; g.epi = GEMM_ATOMIC;
+        return launch_sgemm(ctx, true, false, g, st);
+    };
+    // dgrad: out[row][k] = sum_n dZ[row][n] * Wt[k][n]   (Wt = k-major copy, [K_pad][N])
+    auto dgrad = [&](const float* dZ, int n_out, const float* Wt, int k_in, float* out, int64_t ldo, int epi,
+                     const float* mask, const float* r_row, int64_t r_stride, const float* r_col) {
+        GemmArgs g{};
+        g.M = rows; g.N = k_in; g.K = n_out; g.A = dZ; g.lda = n_out; g.B = Wt; g.ldb = n_out;
+        g.C = out; g.ldc = ldo; g.epi = epi; g.mask = mask; g.ldm = ldo; g.r_row = r_row; g.r_stride = r_stride; g.r_col = r_col;
+        return launch_sgemm(ctx, false, true, g, st);
+    };
+
+    // ---- heads: rgb_linear (128 -> C) and the ReLU of the view layer ----
+    if (C == 3) heads_backward_kernel<3><<<(unsigned)ceil_div(rows * kHalf, 256), 256, 0, st>>>(w.d_raw, h9, np.w_rgb, rows, w.dz9);
+    else heads_backward_kernel<1><<<(unsigned)ceil_div(rows * kHalf, 256), 256, 0, st>>>(w.d_raw, h9, np.w_rgb, rows, w.dz9);
+    BNRF_LAUNCH_CHECK(ctx);
+    if ((rc = wgrad(w.d_raw, C, C + 1, h9, kHalf, kHalf, dW[BNRF_L_RGB], kHalf, 0))) return rc;
+    colsum(w.d_raw, C, C + 1, rows, dB[BNRF_L_RGB]);
+    // ---- views_linears.0: feature block by GEMM, direction block + bias per ray ----
+    sum_samples_kernel<<<(unsigned)n, kHalf, 0, st>>>(w.dz9, S, w.dvb);
+    BNRF_LAUNCH_CHECK(ctx);
+    colsum(w.dvb, kHalf, kHalf, n, dB[BNRF_L_VIEWS]);
+    if ((rc = wgrad(w.dz9, kHalf, kHalf, H(8), kWidth, kWidth, dW[BNRF_L_VIEWS], kWidth + kDirCh, 0))) return rc;
+    if ((rc = dgrad(w.dz9, kHalf, np.wt[9], kWidth, w.buf_a, kWidth, GEMM_STORE, nullptr, nullptr, 0, nullptr))) return rc;   // dF
+    // ---- feature_linear (no activation) + alpha_linear; ReLU of layer 7 ----
+    if ((rc = wgrad(w.buf_a, kWidth, kWidth, H(7), kWidth, kWidth, dW[BNRF_L_FEATURE], kWidth, 0))) return rc;
+    colsum(w.buf_a, kWidth, kWidth, rows, dB[BNRF_L_FEATURE]);
+    if ((rc = wgrad(w.d_raw + C, 1, C + 1, H(7), kWidth, kWidth, dW[BNRF_L_ALPHA], kWidth, 0))) return rc;
+    colsum(w.d_raw + C, 1, C + 1, rows, dB[BNRF_L_ALPHA]);
+    if ((rc = dgrad(w.buf_a, kWidth, np.wt[8], kWidth, w.buf_b, kWidth, GEMM_MASKED, H(7), w.d_raw + C, C + 1, np.w_alpha))) return rc;   // dZ7
+    // ---- pts_linears 7 .. 0 ----
+    float* cur = w.buf_b;
+    float* nxt = w.buf_a;
+    for (int l = 7; l >= 0; --l) {
+        colsum(cur, kWidth, kWidth, rows, dB[l]);
+        if (l == 0) {
+            if ((rc = wgrad(cur, kWidth, kWidth, pe, kPtsCh, kPtsChPad, dW[0], kPtsCh, 0))) return rc;
+            if ((rc = dgrad(cur, kWidth, np.wt[0], kPtsChPad, w.d_pe, kPtsChPad, GEMM_ACCUM, nullptr, nullptr, 0, nullptr))) return rc;
+        } else if (l == 5) {                      // input = cat([encoded pts (63), h4 (256)])  (model/nerf.py:98)
+            if ((rc = wgrad(cur, kWidth, kWidth, pe, kPtsCh, kPtsChPad, dW[5], kPtsCh + kWidth, 0))) return rc;
+            if ((rc = wgrad(cur, kWidth, kWidth, H(4), kWidth, kWidth, dW[5], kPtsCh + kWidth, kPtsCh))) return rc;
+            if ((rc = dgrad(cur, kWidth, np.wt[5], kPtsChPad, w.d_pe, kPtsChPad, GEMM_STORE, nullptr, nullptr, 0, nullptr))) return rc;
+            if ((rc = dgrad(cur, kWidth, np.wt[5] + (size_t)kPtsChPad * kWidth, kWidth, nxt, kWidth, GEMM_MASKED, H(4), nullptr, 0, nullptr))) return rc;
+        } else {
+            if ((rc = wgrad(cur, kWidth, kWidth, H(l - 1), kWidth, kWidth, dW[l], kWidth, 0))) return rc;
+            if ((rc = dgrad(cur, kWidth, np.wt[l], kWidth, nxt, kWidth, GEMM_MASKED, H(l - 1), nullptr, 0, nullptr))) return rc;
+        }
+        float* t = cur; cur = nxt; nxt = t;
+    }
+    return BNRF_OK;
+}
+
+// ------------------------------------------------------------------ saved-tensor and workspace carve-ups
+SavedLayout carve_saved(const bnrf_cfg& c, int64_t n, void* base) {
+    SavedLayout s;
+    size_t off = 0;
+    auto take = [&](size_t floats) {
+        float* p = base ? reinterpret_cast<float*>(static_cast<char*>(base) + off) : nullptr;
+        off += (floats * sizeof(float) + 255) / 256 * 256;
+        return p;
+    };
+    const int Sc = c.n_samples, Sf = c.n_samples + c.n_importance;
+    const bool fine = c.n_importance > 0;
+    s.o = take(n * 3); s.d = take(n * 3); s.view = take(n * 3);
+    s.z_c = take(n * Sc); s.raw_c = take(n * Sc * (c.channels + 1)); s.sig_c = take(n * Sc);
+    s.acts_c = take((size_t)n * Sc * kActFloatsPerRow);
+    s.z_f = take(fine ? n * Sf : 0); s.raw_f = take(fine ? n * Sf * (c.channels + 1) : 0); s.sig_f = take(fine ? n * Sf : 0);
+    s.acts_f = take(fine ? (size_t)n * Sf * kActFloatsPerRow : 0);
+    s.bytes = off;
+    return s;
+}
+
+struct BwdWorkspace { BwdBuffers b; float *g_o, *g_d, *g_v, *g_dn; size_t bytes; };
+static BwdWorkspace carve_bwd(const bnrf_cfg& c, int64_t n, void* base) {
+    BwdWorkspace w;
+    size_t off = 0;
+    auto take = [&](size_t floats) {
+        float* p = base ? reinterpret_cast<float*>(static_cast<char*>(base) + off) : nullptr;
+        off += (floats * sizeof(float) + 255) / 256 * 256;
+        return p;
+    };
+    const int64_t rows = n * (c.n_samples + c.n_importance);
+    w.b.d_raw = take(rows * (c.channels + 1));
+    w.b.buf_a = take(rows * kWidth); w.b.buf_b = take(rows * kWidth);
+    w.b.d_pe = take(rows * kPtsChPad); w.b.dz9 = take(rows * kHalf);
+    w.b.dvb = take(n * kHalf); w.b.pe_dir = take(n * 32);
+    w.g_o = take(n * 3); w.g_d = take(n * 3); w.g_v = take(n * 3); w.g_dn = take(n);
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace bnrf
+
+using namespace bnrf;
+
+extern "C" {
+
+size_t bnrf_saved_bytes(const bnrf_ctx* ctx, int64_t n_rays) {
+    if (!ctx || n_rays <= 0) return 0;
+    return carve_saved(ctx->cfg, n_rays, nullptr).bytes;
+}
+
+size_t bnrf_backward_workspace_bytes(const bnrf_ctx* ctx, int64_t n_rays) {
+    if (!ctx || n_rays <= 0) return 0;
+    return carve_bwd(ctx->cfg, n_rays, nullptr).bytes;
+}
+
+int bnrf_render_backward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W,
+                         const float* K, const float* remap, const float* d_rgb_map, const float* d_rgb0,
+                         const void* saved, size_t saved_bytes, const bnrf_param_grads* grads_coarse,
+                         const bnrf_param_grads* grads_fine, float* d_poses, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+    if (!ctx) return BNRF_ERR_ARG;
+    if (!poses || !ray_idx || !K || !saved || !workspace || !d_poses || P <= 0 || R <= 0)
+        return fail(ctx, BNRF_ERR_ARG, "render_backward: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bnrf_cfg& c = ctx->cfg;
+    const int64_t n = (int64_t)P * R;
+    const bool fine = c.n_importance > 0;
+    const int Sc = c.n_samples, Sf = c.n_samples + c.n_importance;
+    const SavedLayout s = carve_saved(c, n, const_cast<void*>(saved));
+    if (saved_bytes < s.bytes) return fail(ctx, BNRF_ERR_STATE, "render_backward: saved buffer %zu < %zu bytes", saved_bytes, s.bytes);
+    BwdWorkspace w = carve_bwd(c, n, workspace);
+    if (workspace_bytes < w.bytes) return fail(ctx, BNRF_ERR_STATE, "render_backward: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
+    // with a fine pass, rgb_map comes from the fine network and rgb0 from the coarse one (model/nerf.py:319-343)
+    const float* g_fine = fine ? d_rgb_map : nullptr;
+    const float* g_coarse = fine ? d_rgb0 : d_rgb_map;
+    if ((g_fine && !grads_fine) || (g_coarse && !grads_coarse)) return fail(ctx, BNRF_ERR_ARG, "render_backward: gradient tables missing");
+    BNRF_CUDA(ctx, cudaMemsetAsync(w.g_o, 0, (size_t)n * 3 * sizeof(float), st));
+    BNRF_CUDA(ctx, cudaMemsetAsync(w.g_d, 0, (size_t)n * 3 * sizeof(float), st));
+    BNRF_CUDA(ctx, cudaMemsetAsync(w.g_v, 0, (size_t)n * 3 * sizeof(float), st));
+    BNRF_CUDA(ctx, cudaMemsetAsync(w.g_dn, 0, (size_t)n * sizeof(float), st));
+    int rc;
+    for (int net = 1; net >= 0; --net) {
+        const float* g = net ? g_fine : g_coarse;
+        if (!g) continue;
+        const int S = net ? Sf : Sc;
+        const float *raw = net ? s.raw_f : s.raw_c, *z = net ? s.z_f : s.z_c, *sig = net ? s.sig_f : s.sig_c;
+        const float* acts = net ? s.acts_f : s.acts_c;
+        const bnrf_param_grads* pg = net ? grads_fine : grads_coarse;
+        const unsigned grid = (unsigned)ceil_div(n, kWarps);
+        if (c.channels == 3) composite_backward_kernel<3><<<grid, 32 * kWarps, 0, st>>>(raw, z, sig, s.d, g, n, S, w.b.d_raw, w.g_dn);
+        else composite_backward_kernel<1><<<grid, 32 * kWarps, 0, st>>>(raw, z, sig, s.d, g, n, S, w.b.d_raw, w.g_dn);
+        BNRF_LAUNCH_CHECK(ctx);
+        if ((rc = mlp_backward(ctx, net, n, S, acts, w.b, pg->weights, pg->biases, st))) return rc;
+        // view-direction block of views_linears.0 and d viewdirs
+        viewdir_backward_kernel<<<grid, 32 * kWarps, 0, st>>>(s.view, w.b.dvb, ctx->net[net].w_dir, n, w.b.pe_dir, w.g_v);
+        BNRF_LAUNCH_CHECK(ctx);
+        {
+            GemmArgs g2{};
+            g2.M = kHalf; g2.N = kDirCh; g2.K = n; g2.A = w.b.dvb; g2.lda = kHalf; g2.B = w.b.pe_dir; g2.ldb = 32;
+            g2.C = pg->weights[BNRF_L_VIEWS] + kWidth; g2.ldc = kWidth + kDirCh; g2.epi = GEMM_ATOMIC;
+            if ((rc = launch_sgemm(ctx, true, false, g2, st))) return rc;
+        }
+        pe_ray_backward_kernel<<<grid, 32 * kWarps, 0, st>>>(acts, w.b.d_pe, z, n, S, w.g_o, w.g_d);
+        BNRF_LAUNCH_CHECK(ctx);
+    }
+    rays_backward_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(poses, ray_idx, P, R, H, W, K[0], K[4], K[2], K[5], remap,
+                                                                    c.ndc, w.g_o, w.g_d, w.g_v, w.g_dn, d_poses);
+    BNRF_LAUNCH_CHECK(ctx);
+    return BNRF_OK;
+}
+
+}  // extern "C"

@@ -122,6 +122,8 @@ enum : uint32_t { kStreamTRand = 1, kStreamNoiseC = 2, kStreamU = 3, kStreamNois
 // ---- launchers implemented in the individual .cu files ---------------------------------
 int launch_spline(bnrf_ctx*, const float* knots, const float* transform, const float* ts, int P, int traj,
                   float* poses, cudaStream_t);
+int launch_spline_backward(bnrf_ctx*, const float* knots, const float* transform, const float* ts, int P, int traj,
+                           const float* d_poses, float* d_knots, float* d_transform, cudaStream_t);
 int launch_rays(bnrf_ctx*, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W, const float* K,
                 const float* remap, float* o, float* d, float* view, cudaStream_t);
 int launch_stratified(bnrf_ctx*, const float* t_rand, const bnrf_rng* rng, int64_t n, int S, float* z, cudaStream_t);
@@ -142,6 +144,17 @@ size_t tc_stream_halfs();
 size_t tc2_stream_halfs();
 int pack_tc2_stream(bnrf_ctx*, int net, const float* const* table_dev, const float* scale_dev, cudaStream_t);
 int launch_mlp_tc2(bnrf_ctx*, int net, const float* o, const float* d, const float* vb, const float* z,
-                   int64_t n, int S, float* raw, cudaStream_t);
+                   int64_t n, int S, float* raw, float* acts /*NULL unless training*/, cudaStream_t);
+
+// Tensors the forward pass keeps for the backward pass (bnrf_render_forward_train), carved from the caller's buffer.
+constexpr int kActFloatsPerRow = kPtsChPad + 9 * kWidth + kHalf;   // encoding | h0..h7 | feature | view layer
+struct SavedLayout {
+    float *o, *d, *view;            // [N,3] NDC origin / direction, pre-NDC unit view direction
+    float *z_c, *raw_c, *sig_c;     // [N,S_c], [N,S_c,C+1], [N,S_c] relu(raw_sigma + noise)
+    float *z_f, *raw_f, *sig_f;     // fine network
+    float *acts_c, *acts_f;         // [rows * kActFloatsPerRow]
+    size_t bytes;
+};
+SavedLayout carve_saved(const bnrf_cfg& c, int64_t n, void* base);
 
 }  // namespace bnrf

@@ -99,6 +99,40 @@ __global__ void event_logdiff_generic(const float* __restrict__ rgb, int B, int6
     }
 }
 
+// ---- backward of the two image-formation operators (train.py:340 through train.py:163-177, 205-318) ----
+// d rgb[p][e] = g[e] / P for every pose p
+__global__ void blur_mean_backward_kernel(const float* __restrict__ g, int P, int64_t L, float den, float* __restrict__ d_rgb) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < L; e += stride) {
+        const float v = g[e] / den;
+        for (int p = 0; p < P; ++p) d_rgb[(int64_t)p * L + e] = v;
+    }
+}
+__device__ inline float log_brightness_grad(float x, int mode) {           // d log_brightness / d x
+    if (mode == 0) return 1.0f / (x + 1e-9f);
+    const float c = x * 255.0f;
+    const float slope = logf(20.0f + 1e-9f) / 20.0f;
+    return (c < 20.0f) ? slope * 255.0f : 255.0f / (c + 1e-9f);
+}
+// frame f of rgb contributes +L to difference f-1 and -L to difference f
+__global__ void event_logdiff_backward_kernel(const float* __restrict__ rgb, const float* __restrict__ g, int B, int64_t R, int C,
+                                              int mode, float* __restrict__ d_rgb) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += stride) {
+        for (int f = 0; f <= B; ++f) {
+            const float* px = rgb + ((int64_t)f * R + r) * C;
+            const float gval = (C == 3) ? gray3(px[0], px[1], px[2]) : px[0];
+            float go = 0.f;
+            if (f > 0) go += g[(int64_t)(f - 1) * R + r];
+            if (f < B) go -= g[(int64_t)f * R + r];
+            const float gl = go * log_brightness_grad(gval, mode);
+            float* dp = d_rgb + ((int64_t)f * R + r) * C;
+            if (C == 3) { dp[0] = gl * 0.299f; dp[1] = gl * 0.587f; dp[2] = gl * 0.114f; }
+            else dp[0] = gl;
+        }
+    }
+}
+
 __global__ void accumulate_events_kernel(const int32_t* __restrict__ x, const int32_t* __restrict__ y,
                                          const float* __restrict__ pol, int64_t E, int H, int W, double* __restrict__ out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -137,6 +171,19 @@ extern "C" int bnrf_event_logdiff(const float* rgb, int B, int64_t R, int C, int
     const bool vec = (C == 3) && (R % 4 == 0) && (((uintptr_t)rgb | (uintptr_t)out) % 16 == 0);
     if (vec) event_logdiff_rgb4<<<stream_grid(R / 4, 256), 256, 0, st>>>((const float4*)rgb, B, R / 4, log_mode, (float4*)out);
     else event_logdiff_generic<<<stream_grid(R, 256), 256, 0, st>>>(rgb, B, R, C, log_mode, out);
+    return cudaGetLastError() == cudaSuccess ? BNRF_OK : BNRF_ERR_CUDA;
+}
+
+extern "C" int bnrf_blur_mean_backward(const float* g, int P, int64_t R, int C, float* d_rgb, void* stream) {
+    if (!g || !d_rgb || P <= 0 || R <= 0 || C <= 0) return BNRF_ERR_ARG;
+    blur_mean_backward_kernel<<<stream_grid(R * C, 256), 256, 0, (cudaStream_t)stream>>>(g, P, R * C, (float)P, d_rgb);
+    return cudaGetLastError() == cudaSuccess ? BNRF_OK : BNRF_ERR_CUDA;
+}
+
+extern "C" int bnrf_event_logdiff_backward(const float* rgb, const float* g, int B, int64_t R, int C, int log_mode, float* d_rgb,
+                                           void* stream) {
+    if (!rgb || !g || !d_rgb || B <= 0 || R <= 0 || (C != 1 && C != 3) || (log_mode != 0 && log_mode != 1)) return BNRF_ERR_ARG;
+    event_logdiff_backward_kernel<<<stream_grid(R, 256), 256, 0, (cudaStream_t)stream>>>(rgb, g, B, R, C, log_mode, d_rgb);
     return cudaGetLastError() == cudaSuccess ? BNRF_OK : BNRF_ERR_CUDA;
 }
 

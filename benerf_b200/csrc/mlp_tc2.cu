@@ -50,11 +50,13 @@ __host__ __device__ inline size_t stage_offset_bytes(int i) {
 }
 __host__ __device__ inline size_t rank_stream_bytes() { return stage_offset_bytes(STAGES_PER_TILE); }
 
-template <int C>
+// TRAIN: the epilogue / front end also write the encoded points and every hidden activation (fp32, as computed) to
+// `acts` for the backward pass: [rows,64] encoding | 8 x [rows,256] h0..h7 | [rows,256] feature | [rows,128] view layer.
+template <int C, bool TRAIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                const float* __restrict__ viewbias, const float* __restrict__ z, int64_t rows, int S, int num_pairs,
-               float* __restrict__ raw, unsigned int* err_flag, unsigned long long* __restrict__ trace) {
+               float* __restrict__ raw, float* __restrict__ acts, unsigned int* err_flag, unsigned long long* __restrict__ trace) {
     // trace (debug, normally NULL): per-CTA stall accounting, 16 counters of clock64 cycles --
     //   0 kernel total   1 mma: wait PE_FULL   2 mma: wait A_READY   3 mma: wait W_FULL   4 mma: loop total
     //   5 tma: wait W_EMPTY   6 epilogue(warp 8): wait ACC_FULL   7 epilogue: loop total
@@ -275,6 +277,11 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
                                 sigma_acc = fmaf(v[j + 2], wa.z, sigma_acc); sigma_acc = fmaf(v[j + 3], wa.w, sigma_acc);
                             }
                         }
+                        if (TRAIN && row < rows) {                             // h_t (t < 8) or the feature vector (t == 8)
+                            float4* dst = reinterpret_cast<float4*>(acts + rows * kPtsChPad + (int64_t)t * rows * kWidth + row * kWidth + col0 + ch * 16);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        }
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             const uint32_t off = (kh >> 1) * KBLOCK_BYTES + sw128_offset(r, (kh & 1) * 32 + ch * 16 + j * 8);
@@ -312,6 +319,8 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
                             const float x1 = fmaxf(fmaf(__uint_as_float(cur[j + 1]), inv_scale, bv.y), 0.0f);
                             const float x2 = fmaxf(fmaf(__uint_as_float(cur[j + 2]), inv_scale, bv.z), 0.0f);
                             const float x3 = fmaxf(fmaf(__uint_as_float(cur[j + 3]), inv_scale, bv.w), 0.0f);
+                            if (TRAIN && row < rows)
+                                *reinterpret_cast<float4*>(acts + rows * (kPtsChPad + 9 * kWidth) + row * kHalf + ch * 32 + col) = make_float4(x0, x1, x2, x3);
 #pragma unroll
                             for (int c = 0; c < C; ++c) {
                                 const float4 wr = __ldg(reinterpret_cast<const float4*>(p.w_rgb + c * kHalf + ch * 32 + col));
@@ -375,6 +384,11 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
                     enc[3 + 6 * k + 3 + c] = live ? co : 0.0f;
                 }
             enc[63] = 0.0f;
+            if (TRAIN && live) {
+                float4* dst = reinterpret_cast<float4*>(acts + row * kPtsChPad);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dst[j] = make_float4(enc[4 * j], enc[4 * j + 1], enc[4 * j + 2], enc[4 * j + 3]);
+            }
             timed_wait(bar(BAR_PE_EMPTY), ((uint32_t)it & 1u) ^ 1u, 7, w_pee);
 #pragma unroll
             for (int c8 = 0; c8 < 8; ++c8) {
@@ -439,8 +453,18 @@ int pack_tc2_stream(bnrf_ctx* ctx, int net, const float* const* table_dev, const
     return BNRF_OK;
 }
 
+template <int C, bool TRAIN>
+static int launch_one(bnrf_ctx* ctx, const tcp::TcParams& p, int clusters, const float* o, const float* d, const float* vb,
+                      const float* z, int64_t rows, int S, int pairs, float* raw, float* acts, cudaStream_t st) {
+    using namespace tc2;
+    BNRF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<C, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    mlp_tc2_kernel<C, TRAIN><<<2 * clusters, NUM_THREADS, SMEM_BYTES, st>>>(p, o, d, vb, z, rows, S, pairs, raw, acts, ctx->err_flag, ctx->trace);
+    BNRF_LAUNCH_CHECK(ctx);
+    return BNRF_OK;
+}
+
 int launch_mlp_tc2(bnrf_ctx* ctx, int net, const float* o, const float* d, const float* vb, const float* z,
-                   int64_t n, int S, float* raw, cudaStream_t st) {
+                   int64_t n, int S, float* raw, float* acts, cudaStream_t st) {
     using namespace tc2;
     const NetParams& np = ctx->net[net];
     TcParams p;
@@ -453,15 +477,11 @@ int launch_mlp_tc2(bnrf_ctx* ctx, int net, const float* o, const float* d, const
     const int pairs = (int)pairs64;
     const int max_clusters = ctx->sm_count / 2;
     const int clusters = pairs < max_clusters ? pairs : max_clusters;
-    if (ctx->cfg.channels == 3) {
-        BNRF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        mlp_tc2_kernel<3><<<2 * clusters, NUM_THREADS, SMEM_BYTES, st>>>(p, o, d, vb, z, rows, S, pairs, raw, ctx->err_flag, ctx->trace);
-    } else {
-        BNRF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        mlp_tc2_kernel<1><<<2 * clusters, NUM_THREADS, SMEM_BYTES, st>>>(p, o, d, vb, z, rows, S, pairs, raw, ctx->err_flag, ctx->trace);
-    }
-    BNRF_LAUNCH_CHECK(ctx);
-    return BNRF_OK;
+    const bool c3 = ctx->cfg.channels == 3;
+    if (acts) return c3 ? launch_one<3, true>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, acts, st)
+                        : launch_one<1, true>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, acts, st);
+    return c3 ? launch_one<3, false>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, acts, st)
+              : launch_one<1, false>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, acts, st);
 }
 
 }  // namespace bnrf

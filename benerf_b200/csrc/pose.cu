@@ -26,6 +26,29 @@ __device__ inline float s_powi(float a, int n) {       // torch.pow(x, n): n=0 -
     return powf(a, (float)n);
 }
 
+// Forward-mode dual number: value and one directional derivative.  interpolate_pose<Dual> seeded on knot element j
+// yields d pose / d knot_j, which spline_backward_kernel contracts with d L / d pose.
+struct Dual {
+    float v, d;
+    __device__ Dual() : v(0.f), d(0.f) {}
+    __device__ Dual(float a) : v(a), d(0.f) {}
+    __device__ Dual(float a, float b) : v(a), d(b) {}
+};
+__device__ inline Dual operator+(Dual a, Dual b) { return {a.v + b.v, a.d + b.d}; }
+__device__ inline Dual operator-(Dual a, Dual b) { return {a.v - b.v, a.d - b.d}; }
+__device__ inline Dual operator*(Dual a, Dual b) { return {a.v * b.v, a.d * b.v + a.v * b.d}; }
+__device__ inline Dual operator/(Dual a, Dual b) { const float q = a.v / b.v; return {q, (a.d - q * b.d) / b.v}; }
+__device__ inline Dual s_sqrt(Dual a) { const float r = sqrtf(a.v); return {r, a.d * 0.5f / r}; }
+__device__ inline Dual s_sin(Dual a) { return {sinf(a.v), cosf(a.v) * a.d}; }
+__device__ inline Dual s_cos(Dual a) { return {cosf(a.v), -sinf(a.v) * a.d}; }
+__device__ inline Dual s_atan(Dual a) { return {atanf(a.v), a.d / (1.0f + a.v * a.v)}; }
+__device__ inline float s_val(Dual a) { return a.v; }
+__device__ inline Dual s_powi(Dual a, int n) {
+    if (n == 0) return Dual(1.0f);
+    if (n == 2) return a * a;
+    return {powf(a.v, (float)n), (float)n * powf(a.v, (float)(n - 1)) * a.d};
+}
+
 // sum_i (-1)^i x^(2i) / d_i,  d_i = prod_{j<=i} (2j+first)(2j+first+1)   (spline.py:46-62)
 template <class T>
 __device__ T taylor_series(T x, int first) {
@@ -177,6 +200,33 @@ __global__ void spline_kernel(const float* __restrict__ knots, const float* __re
     interpolate_pose<float>(k, ts[p], traj, out);
 #pragma unroll
     for (int i = 0; i < 12; ++i) poses[p * 12 + i] = out[i];
+}
+
+// d L / d knots [4,6] (+= ) and d L / d transform [6] (+=) from d L / d poses [P,3,4]: thread (p, j) differentiates
+// pose p along knot element j.  The RGB knots are knots + transform (optimize.py:86-89), so the transform's
+// gradient is the sum of the four knots' gradients element-wise.
+__global__ void spline_backward_kernel(const float* __restrict__ knots, const float* __restrict__ transform,
+                                       const float* __restrict__ ts, int P, int traj, const float* __restrict__ d_poses,
+                                       float* __restrict__ d_knots, float* __restrict__ d_transform) {
+    const int p = blockIdx.x, j = threadIdx.x;
+    if (p >= P || j >= 24) return;
+    Dual k[24];
+    for (int i = 0; i < 24; ++i) k[i] = Dual(knots[i] + (transform ? transform[i % 6] : 0.0f), i == j ? 1.0f : 0.0f);
+    Dual out[12];
+    interpolate_pose<Dual>(k, ts[p], traj, out);
+    float g = 0.f;
+    for (int i = 0; i < 12; ++i) g += out[i].d * d_poses[p * 12 + i];
+    if (g != g) g = 0.f;                       // 0/0 of a derivative at an exactly-zero rotation (the reference yields NaN there)
+    atomicAdd(d_knots + j, g);
+    if (transform && d_transform) atomicAdd(d_transform + (j % 6), g);
+}
+
+int launch_spline_backward(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts, int P, int traj,
+                           const float* d_poses, float* d_knots, float* d_transform, cudaStream_t st) {
+    if (!knots || !ts || !d_poses || !d_knots || P <= 0 || (traj != 0 && traj != 1)) return fail(ctx, BNRF_ERR_ARG, "spline_backward: bad argument");
+    spline_backward_kernel<<<P, 32, 0, st>>>(knots, transform, ts, P, traj, d_poses, d_knots, d_transform);
+    BNRF_LAUNCH_CHECK(ctx);
+    return BNRF_OK;
 }
 
 int launch_spline(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts, int P, int traj,

@@ -118,8 +118,10 @@ class Engine:
         flat = [float(v) for v in torch.as_tensor(K, dtype=torch.float32).reshape(-1).tolist()]
         return (C.c_float * 9)(*flat)
 
-    def render(self, poses, ray_idx, H, W, K, remap=None, rng=None, seed=0, offset=0, want_sigma=True, want_depth=False, want_z=False):
-        """Graph.render (model/nerf.py:236-343).  rng: dict of the four draws (parity mode) or None (Philox)."""
+    def render(self, poses, ray_idx, H, W, K, remap=None, rng=None, seed=0, offset=0, want_sigma=True, want_depth=False, want_z=False,
+               saved=None):
+        """Graph.render (model/nerf.py:236-343).  rng: dict of the four draws (parity mode) or None (Philox).
+        saved: uint8 device tensor of saved_bytes(N) bytes -> training mode (bnrf_render_forward_train)."""
         P, R = poses.shape[0], ray_idx.numel()
         n = P * R
         Sf = self.n_samples + self.n_importance
@@ -143,15 +145,61 @@ class Engine:
         need = self.lib.bnrf_workspace_bytes(self._ctx, n)
         if self._workspace is None or self._workspace.numel() < need:
             self._workspace = torch.empty(need, device=self.device, dtype=torch.uint8)
-        self._check(self.lib.bnrf_render_forward(
-            self._ctx, _ptr(poses, name="poses"), _ptr(ray_idx, torch.int64, name="ray_idx"), P, R, int(H), int(W),
-            self._K(K), _ptr(remap, name="remap"), C.byref(r), C.byref(outs), C.c_void_p(self._workspace.data_ptr()),
-            self._workspace.numel(), _stream()), "bnrf_render_forward")
+        common = (self._ctx, _ptr(poses, name="poses"), _ptr(ray_idx, torch.int64, name="ray_idx"), P, R, int(H), int(W),
+                  self._K(K), _ptr(remap, name="remap"), C.byref(r), C.byref(outs), C.c_void_p(self._workspace.data_ptr()),
+                  self._workspace.numel())
+        if saved is None:
+            self._check(self.lib.bnrf_render_forward(*common, _stream()), "bnrf_render_forward")
+        else:
+            self._check(self.lib.bnrf_render_forward_train(*common, _ptr(saved, torch.uint8, name="saved"), saved.numel(), _stream()),
+                        "bnrf_render_forward_train")
         if want_depth:
             ret["depth_map"] = depth
         if want_z:
             ret["z_vals"] = z_vals
         return ret
+
+    # -- a16: backward ------------------------------------------------------------------------
+    def saved_bytes(self, n_rays):
+        return int(self.lib.bnrf_saved_bytes(self._ctx, int(n_rays)))
+
+    def _grad_table(self, grads):
+        """grads: {'pts_linears.0.weight': tensor, ...} fp32 device tensors in the parameters' own shapes."""
+        t, keep = _lib.ParamGrads(), []
+        for i, name in enumerate(_lib.LINEAR_NAMES):
+            t.weights[i] = _ptr(grads[name + ".weight"], device=self.device, name="grad " + name + ".weight").value
+            t.biases[i] = _ptr(grads[name + ".bias"], device=self.device, name="grad " + name + ".bias").value
+        return t
+
+    def render_backward(self, poses, ray_idx, H, W, K, saved, d_rgb_map, d_rgb0, grads_coarse, grads_fine, d_poses, remap=None):
+        """Adds d loss / d parameters into grads_* and d loss / d poses into d_poses (bnrf_render_backward)."""
+        P, R = poses.shape[0], ray_idx.numel()
+        need = self.lib.bnrf_backward_workspace_bytes(self._ctx, P * R)
+        if getattr(self, "_bwd_workspace", None) is None or self._bwd_workspace.numel() < need:
+            self._bwd_workspace = torch.empty(need, device=self.device, dtype=torch.uint8)
+        gc = self._grad_table(grads_coarse) if grads_coarse is not None else None
+        gf = self._grad_table(grads_fine) if grads_fine is not None else None
+        self._check(self.lib.bnrf_render_backward(
+            self._ctx, _ptr(poses, name="poses"), _ptr(ray_idx, torch.int64, name="ray_idx"), P, R, int(H), int(W), self._K(K),
+            _ptr(remap, name="remap"), _ptr(d_rgb_map, name="d_rgb_map"), _ptr(d_rgb0, name="d_rgb0"),
+            _ptr(saved, torch.uint8, name="saved"), saved.numel(), C.byref(gc) if gc is not None else None,
+            C.byref(gf) if gf is not None else None, _ptr(d_poses, name="d_poses"),
+            C.c_void_p(self._bwd_workspace.data_ptr()), self._bwd_workspace.numel(), _stream()), "bnrf_render_backward")
+
+    def spline_poses_backward(self, knots, transform, ts, d_poses, traj="spline"):
+        d_knots = torch.zeros(4, 6, device=self.device, dtype=torch.float32)
+        d_transform = torch.zeros(6, device=self.device, dtype=torch.float32) if transform is not None else None
+        self._check(self.lib.bnrf_spline_poses_backward(
+            self._ctx, _ptr(knots, name="knots"), _ptr(transform, name="transform"), _ptr(ts, name="ts"), ts.numel(), TRAJ[traj],
+            _ptr(d_poses, name="d_poses"), _ptr(d_knots), _ptr(d_transform), _stream()), "bnrf_spline_poses_backward")
+        return d_knots, d_transform
+
+    def debug_sgemm(self, A, B, ta, tb, M, N, K, epi=0, C_out=None, mask=None, r_row=None, r_col=None):
+        out = C_out if C_out is not None else torch.zeros(M, N, device=self.device, dtype=torch.float32)
+        self._check(self.lib.bnrf_debug_sgemm(
+            self._ctx, int(ta), int(tb), M, N, K, _ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(out), out.stride(0), int(epi),
+            _ptr(mask), mask.stride(0) if mask is not None else 0, _ptr(r_row), 1, _ptr(r_col), _stream()), "bnrf_debug_sgemm")
+        return out
 
     # -- stage operators ------------------------------------------------------------------
     def op_rays(self, poses, ray_idx, H, W, K, remap=None):
@@ -196,8 +244,58 @@ def _rc(rc, what):
         raise BnrfError(f"{what} failed ({rc})")
 
 
+class _BlurMeanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb, n_poses):
+        ctx.n_poses, ctx.shape = n_poses, rgb.shape
+        return _blur_mean_raw(rgb.contiguous(), n_poses)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        d = torch.empty(ctx.shape, device=g.device, dtype=torch.float32)
+        C_ = ctx.shape[-1]
+        _rc(lib.bnrf_blur_mean_backward(_ptr(g.contiguous(), name="g"), int(ctx.n_poses), g.numel() // C_, C_, _ptr(d), _stream()),
+            "bnrf_blur_mean_backward")
+        return d, None
+
+
+class _EventLogDiffFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb, n_bins, mode):
+        rgb = rgb.contiguous()
+        ctx.save_for_backward(rgb)
+        ctx.n_bins, ctx.mode = n_bins, mode
+        return _event_logdiff_raw(rgb, n_bins, mode)
+
+    @staticmethod
+    def backward(ctx, g):
+        (rgb,) = ctx.saved_tensors
+        lib = _lib.load()
+        C_ = rgb.shape[-1]
+        R = rgb.numel() // ((ctx.n_bins + 1) * C_)
+        d = torch.empty_like(rgb)
+        _rc(lib.bnrf_event_logdiff_backward(_ptr(rgb, name="rgb"), _ptr(g.contiguous(), name="g"), int(ctx.n_bins), R, C_,
+                                            LOG_MODE[ctx.mode], _ptr(d), _stream()), "bnrf_event_logdiff_backward")
+        return d, None, None
+
+
 def blur_mean(rgb, n_poses):
-    """[P*R, C] pose-major (or [P,R,C]) -> [R, C]   (train.py:299-318)."""
+    """[P*R, C] pose-major (or [P,R,C]) -> [R, C]   (train.py:299-318).  Differentiable (bnrf_blur_mean_backward)."""
+    if torch.is_grad_enabled() and rgb.requires_grad:
+        return _BlurMeanFn.apply(rgb, n_poses)
+    return _blur_mean_raw(rgb, n_poses)
+
+
+def event_logdiff(rgb, n_bins, dataset_or_mode):
+    """[(B+1)*R, C] pose-major -> [B, R] log-brightness differences of consecutive poses (train.py:205-292).
+    Differentiable (bnrf_event_logdiff_backward)."""
+    if torch.is_grad_enabled() and rgb.requires_grad:
+        return _EventLogDiffFn.apply(rgb, n_bins, dataset_or_mode)
+    return _event_logdiff_raw(rgb, n_bins, dataset_or_mode)
+
+
+def _blur_mean_raw(rgb, n_poses):
     lib = _lib.load()
     C_ = rgb.shape[-1]
     R = rgb.numel() // (n_poses * C_)
@@ -206,8 +304,7 @@ def blur_mean(rgb, n_poses):
     return out
 
 
-def event_logdiff(rgb, n_bins, dataset_or_mode):
-    """[(B+1)*R, C] pose-major -> [B, R] log-brightness differences of consecutive poses (train.py:205-292)."""
+def _event_logdiff_raw(rgb, n_bins, dataset_or_mode):
     lib = _lib.load()
     C_ = rgb.shape[-1]
     R = rgb.numel() // ((n_bins + 1) * C_)

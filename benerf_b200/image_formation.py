@@ -23,6 +23,23 @@ def event_loss(diff, target, event_threshold, event_coeff_syn=0.1, event_coeff_r
     return mse(dn, tn) * event_coeff_real
 
 
+def training_loss(ret_event, ret_rgb, events_accu, ray_idx_event, blur_target, args):
+    """The loss block of train.py:163-337 (CRFs off, as in every shipped config) on the fused image-formation kernels.
+
+    ret_event: Graph.render of the event pose pair ([2*R_e, C] pose-major), ret_rgb: of the N blur poses;
+    events_accu [H_ev, W_ev] float64; blur_target [R_b, C].  Returns (loss, parts); differentiable end to end.
+    """
+    target = events_accu.reshape(-1, 1)[ray_idx_event]
+    parts = {}
+    for level in ("rgb_map", "rgb0"):
+        diff = event_logdiff(ret_event[level], 1, args.dataset).reshape(-1, 1)
+        parts["event_" + level] = event_loss(diff, target, args.event_threshold, getattr(args, "event_coeff_syn", 0.1),
+                                             getattr(args, "event_coeff_real", 2.0))
+        parts["blur_" + level] = mse(blur_mean(ret_rgb[level], args.num_interpolated_pose), blur_target) * getattr(args, "rgb_coeff", 1.0)
+    loss = (parts["event_rgb0"] + parts["event_rgb_map"]) + (parts["blur_rgb_map"] + parts["blur_rgb0"])
+    return loss, parts
+
+
 def accumulate_events_on_gpu(out, xs, ys, ps, device="cuda"):
     """Signature of utils/event_utils.py:247-259: numpy x/y/polarity of the window -> float64 [H,W]."""
     import numpy as np

@@ -15,6 +15,49 @@ from .engine import Engine
 from . import image_formation
 
 
+from ._lib import LINEAR_NAMES
+
+_OUT_KEYS = ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0", "sigma")
+
+
+class _RenderFn(torch.autograd.Function):
+    """Graph.render under autograd: forward = bnrf_render_forward_train, backward = bnrf_render_backward.
+
+    Differentiable inputs: poses [P,3,4] and the 24 (+24) NeRF parameters; differentiable outputs: rgb_map and rgb0
+    (the only outputs train.py:205-331 puts into a loss).  Everything else is marked non-differentiable.
+    """
+
+    @staticmethod
+    def forward(ctx, call, poses, *params):
+        eng, ray_idx, H, W, K, remap, rng, seed, offset, n_fine = call
+        n = poses.shape[0] * ray_idx.numel()
+        saved = torch.empty(eng.saved_bytes(n), device=eng.device, dtype=torch.uint8)
+        ret = eng.render(poses, ray_idx, H, W, K, remap=remap, rng=rng, seed=seed, offset=offset, saved=saved)
+        keys = [k for k in _OUT_KEYS if k in ret]
+        ctx.call, ctx.keys, ctx.saved_buf, ctx.poses = call, keys, saved, poses
+        ctx.param_shapes = [p.shape for p in params]
+        outs = tuple(ret[k] for k in keys)
+        ctx.mark_non_differentiable(*[o for k, o in zip(keys, outs) if k not in ("rgb_map", "rgb0")])
+        return outs
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        eng, ray_idx, H, W, K, remap, rng, seed, offset, n_fine = ctx.call
+        g = {k: (go.contiguous() if go is not None else None) for k, go in zip(ctx.keys, gouts)}
+        flat = torch.zeros(sum(s.numel() for s in ctx.param_shapes), device=eng.device, dtype=torch.float32)
+        grads, off = [], 0
+        for s in ctx.param_shapes:
+            grads.append(flat[off:off + s.numel()].view(s))
+            off += s.numel()
+        names = [n + sfx for n in LINEAR_NAMES for sfx in (".weight", ".bias")]
+        gc = dict(zip(names, grads[:24]))
+        gf = dict(zip(names, grads[24:48])) if n_fine else None
+        d_poses = torch.zeros_like(ctx.poses)
+        eng.render_backward(ctx.poses, ray_idx, H, W, K, ctx.saved_buf, g.get("rgb_map"), g.get("rgb0"), gc, gf, d_poses, remap=remap)
+        ctx.saved_buf = None
+        return (None, d_poses) + tuple(grads)
+
+
 class Model:
     @abc.abstractmethod
     def build_network(self, args, poses=None, event_poses=None):
@@ -148,8 +191,14 @@ class Graph(nn.Module):
         use_remap = args.dataset == "TUM_VIE" and remap is not None
         remap_t = torch.as_tensor(remap, dtype=torch.float32, device=dev).contiguous() if use_remap else None
         self._render_calls += 1
-        return eng.render(poses, ray_idx, H, W, np.asarray(K.cpu() if isinstance(K, torch.Tensor) else K, dtype=np.float32),
-                          remap=remap_t, rng=rng, seed=self._seed, offset=self._render_calls)
+        K_np = np.asarray(K.cpu() if isinstance(K, torch.Tensor) else K, dtype=np.float32)
+        nets = [self.nerf] + ([self.nerf_fine] if hasattr(self, "nerf_fine") else [])
+        params = [dict(m.named_parameters())[n + sfx] for m in nets for n in LINEAR_NAMES for sfx in (".weight", ".bias")]
+        if torch.is_grad_enabled() and (poses.requires_grad or any(p.requires_grad for p in params)):
+            call = (eng, ray_idx, H, W, K_np, remap_t, rng, self._seed, self._render_calls, len(nets) > 1)
+            outs = _RenderFn.apply(call, poses, *params)
+            return dict(zip([k for k in _OUT_KEYS if len(nets) > 1 or k in ("rgb_map", "disp_map", "acc_map")], outs))
+        return eng.render(poses.detach(), ray_idx, H, W, K_np, remap=remap_t, rng=rng, seed=self._seed, offset=self._render_calls)
 
     @torch.no_grad()
     def render_video(self, iter_step, poses, H, W, K, args, remap, type):

@@ -142,6 +142,40 @@ int bnrf_render_forward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_id
                         int H, int W, const float* K, const float* remap, const bnrf_rng* rng,
                         const bnrf_outputs* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* -------------------------------------------------------------------------------------- */
+/* a16: training -- the part of loss.backward() (train.py:340) that runs through Graph.render */
+
+/* Gradient tables of one network: 12 weight and 12 bias tensors in PyTorch (out,in) layout, order as
+ * bnrf_set_weights.  The backward pass ADDS into them (autograd .grad accumulation semantics). */
+typedef struct {
+    float* weights[BNRF_NUM_LINEARS];
+    float* biases[BNRF_NUM_LINEARS];
+} bnrf_param_grads;
+
+/* Bytes of the caller-owned buffer in which bnrf_render_forward_train keeps what the backward pass needs
+ * (rays, depths, raw outputs, densities and the activations of both networks: ~10 KB per sample). */
+size_t bnrf_saved_bytes(const bnrf_ctx* ctx, int64_t n_rays);
+/* bnrf_render_forward that additionally fills `saved`.  Needs cfg.mlp_mode == BNRF_MLP_TC_FP16X2. */
+int bnrf_render_forward_train(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R,
+                              int H, int W, const float* K, const float* remap, const bnrf_rng* rng,
+                              const bnrf_outputs* out, void* workspace, size_t workspace_bytes,
+                              void* saved, size_t saved_bytes, void* stream);
+size_t bnrf_backward_workspace_bytes(const bnrf_ctx* ctx, int64_t n_rays);
+/* d_rgb_map / d_rgb0: device [N,C] gradients of the loss w.r.t. the two colour outputs (either may be NULL;
+ * the other outputs of Graph.render do not enter any loss of train.py:205-331).  Adds the parameter
+ * gradients into grads_coarse / grads_fine and d L / d poses into d_poses (device [P,3,4]).  Same poses,
+ * ray_idx, H, W, K, remap as the forward call.  z_vals carry no gradient (model/nerf.py:324 detaches them). */
+int bnrf_render_backward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W,
+                         const float* K, const float* remap, const float* d_rgb_map, const float* d_rgb0,
+                         const void* saved, size_t saved_bytes, const bnrf_param_grads* grads_coarse,
+                         const bnrf_param_grads* grads_fine, float* d_poses, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* Backward of bnrf_spline_poses: adds d L / d knots (device [4,6]) and, when transform != NULL,
+ * d L / d transform (device [6]) given d L / d poses (device [P,3,4]).  spline.py:247-331 under autograd. */
+int bnrf_spline_poses_backward(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts,
+                               int P, int traj, const float* d_poses, float* d_knots, float* d_transform,
+                               void* stream);
+
 /* Stage-level operators (the same kernels bnrf_render_forward chains; exported so each can be
  * checked 1:1 against the reference function it replaces). */
 
@@ -173,6 +207,10 @@ int bnrf_blur_mean(const float* rgb /*device [P,R,C]*/, int P, int64_t R, int C,
  * pair of train.py:166-173; B > 1 serves get_pose_evt(..., seg_num=B+1) renders. */
 int bnrf_event_logdiff(const float* rgb /*device [B+1,R,C]*/, int B, int64_t R, int C, int log_mode,
                        float* out /*device [B,R]*/, void* stream);
+/* Backward of the two operators above (train.py:340): g = d loss / d out; d_rgb has the shape of rgb and is OVERWRITTEN. */
+int bnrf_blur_mean_backward(const float* g /*device [R,C]*/, int P, int64_t R, int C, float* d_rgb /*device [P,R,C]*/, void* stream);
+int bnrf_event_logdiff_backward(const float* rgb /*device [B+1,R,C]*/, const float* g /*device [B,R]*/, int B, int64_t R, int C,
+                                int log_mode, float* d_rgb /*device [B+1,R,C]*/, void* stream);
 /* Scatter-add polarities into a float64 image (utils/event_utils.py:247-259; float64 per Q10).
  * x, y device int32 [E]; pol device float [E]; out device double [H,W], NOT cleared here. */
 int bnrf_accumulate_events(const int32_t* x, const int32_t* y, const float* pol, int64_t E,
@@ -195,6 +233,12 @@ int bnrf_profile_read(bnrf_ctx* ctx, double* mlp_ms, int64_t* mlp_timed, double*
  * swizzle, UMMA descriptors, tcgen05.mma and tcgen05.ld helpers as the MLP kernel.  A, B device
  * fp16 row-major; D device fp32 [128,N]; lbo_field = raw 14-bit leading-byte-offset field. */
 int bnrf_debug_umma_probe(const void* A_half, const void* B_half, int N, int lbo_field, float* D, void* stream);
+
+/* Test hook: C[M,N] (op)= A_op * B_op through the backward pass's fp32 GEMM (sgemm.cu).  ta/tb: operand stored
+ * transposed; epi 0 store, 1 accumulate, 2 atomic add (split contraction), 3 masked store with optional rank-1 term. */
+int bnrf_debug_sgemm(bnrf_ctx* ctx, int ta, int tb, int64_t M, int N, int64_t K, const float* A, int64_t lda,
+                     const float* B, int64_t ldb, float* C, int64_t ldc, int epi, const float* mask, int64_t ldm,
+                     const float* r_row, int64_t r_stride, const float* r_col, void* stream);
 
 /* Debug: when counters != NULL (device, [148][16] uint64) every tensor-core MLP launch records per-CTA clock64
  * stall accounting of its warp roles there (see mlp_tc.cu); NULL switches it off. */
