@@ -155,6 +155,71 @@ def workload_config(n_pixels, n_gpus, note=None):
 
 
 # ----------------------------------------------------------------------------------------------
+def bench_train_step(opts, dev, world, rank, steps=5, warmup=3):
+    """BASELINE.json configs[2] shape per GPU (weak scaling): e2nerf_synthetic 800x800, 1024 event pixels x 2 poses +
+    2048 // 19 = 107 blur pixels x 19 poses = 4081 rays, 64 + 128 samples, forward + backward + the reference's Adam
+    steps + ONE gradient all-reduce (benerf_b200.train.Trainer.step).  Device-timed, max over ranks."""
+    import torch.distributed as dist
+    from benerf_b200 import optimize, run_nerf_helpers
+    from benerf_b200.train import Trainer
+    Ht = Wt = 800
+    f = 1111.111
+    Kt = [[f, 0.0, 400.0], [0.0, f, 400.0], [0.0, 0.0, 1.0]]
+    args = ref_args()
+    args.dataset, args.event_threshold, args.seed = "E2NeRF_Synthetic", 0.2, 1
+    args.lrate, args.pose_lrate, args.transform_lrate, args.rgb_crf_lrate, args.event_crf_lrate = 5e-4, 1e-3, 1e-6, 5e-4, 5e-4
+    args.optimize_nerf, args.optimize_pose, args.optimize_trans = True, True, False
+    torch.manual_seed(0)
+    model = optimize.Model(args)
+    graph = model.build_network(args)
+    run_nerf_helpers.init_nerf(graph.nerf)
+    run_nerf_helpers.init_nerf(graph.nerf_fine)
+    graph.to(dev)
+    trainer = Trainer(model, args)
+    g = torch.Generator().manual_seed(99 + rank)
+    r_evt, r_rgb = 1024, 2048 // N_POSES
+    idx_evt = torch.randint(0, Ht * Wt, (r_evt,), generator=g).to(dev)
+    idx_rgb = torch.randint(0, Ht * Wt, (r_rgb,), generator=g).to(dev)
+    blur_t = torch.rand(r_rgb, CH, generator=g).to(dev)
+    accu = torch.randint(-3, 4, (Ht, Wt), generator=g).double().to(dev)
+    ts_evt, ts_rgb = torch.tensor(WINDOW), torch.tensor(EXPOSURE)
+
+    def one():
+        return trainer.step(accu, idx_evt, idx_rgb, blur_t, ts_evt, ts_rgb, Ht, Wt, Kt, Kt)
+
+    for _ in range(warmup):
+        loss, _ = one()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    eng = graph.engine(args)
+    eng.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss, _ = one()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = eng.profile_read()["launches"]
+    eng.profile(False)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    rays = (2 * r_evt + N_POSES * r_rgb) * world
+    return {"metric": "rays_per_sec (training step: forward + backward + Adam + gradient all-reduce)", "value": rays / (ms / 1e3),
+            "unit": "rays/s", "ms_per_step": ms, "steps": steps, "warmup": warmup, "rays_per_step_per_gpu": rays // world,
+            "workload": "e2nerf_synthetic 800x800, 1024 event px x 2 poses + 107 blur px x 19 poses, 64+128 samples, C=3 "
+                        "(BASELINE.json configs[2], weak scaling)",
+            "algorithmic_tflops": 3 * rays / world * FLOP_PER_RAY / (ms / 1e3) / 1e12,
+            "gpu_launches_per_step": launches / steps, "final_loss": float(loss),
+            "backward": "fp32 SIMT GEMMs (sgemm.cu); tensor-core backward is the next step"}
+
+
+# ----------------------------------------------------------------------------------------------
 def bench_ours(opts):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -187,6 +252,7 @@ def bench_ours(opts):
     ts_rgb = torch.tensor(EXPOSURE, dtype=torch.float32)
     launches_py = 0
 
+    @torch.no_grad()        # render + image-formation throughput; the training step is measured by bench_train_step
     def step(idx_evt, idx_rgb, target_blur, target_evt, it):
         """The hot path through the reference-facing API (model/nerf.py:208-232 + train.py:163-331)."""
         nonlocal launches_py
@@ -259,6 +325,7 @@ def bench_ours(opts):
     peak_tf, _, peak_src = peaks()
     mlp_ms_per_launch = prof["mlp_ms"] / max(prof["mlp_timed"], 1)
     achieved = prof["mlp_flops"] / max(prof["mlp_ms"], 1e-9) / 1e9          # algorithmic TFLOP/s of the MLP kernel
+    train = None if opts.no_train_step else bench_train_step(opts, dev, world, rank)
     cpu = None
     if rank == 0 and world == 1 and not opts.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
@@ -285,6 +352,7 @@ def bench_ours(opts):
                          "note": "achieved counts the reference's 593,408 MAC/sample once; the 1e-4 parity bound needs 3 fp16 "
                                  "MMAs per product, so the tensor pipe issues 3x that (issued_*)"},
             "cpu_baseline": cpu,
+            "train_step": train,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * wall_e2e / opts.steps},
             "gpu_launches": int(launches_dev_region),
@@ -306,6 +374,7 @@ def main():
     ap.add_argument("--cpu-pixels", type=int, default=128, help="pixels of the bounded CPU sample")
     ap.add_argument("--mlp-mode", default="tc", choices=["tc", "tc1", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the extra training-step measurement")
     opts = ap.parse_args()
     if opts.impl == "reference":
         bench_reference(opts)

@@ -18,8 +18,13 @@ def event_loss(diff, target, event_threshold, event_coeff_syn=0.1, event_coeff_r
     """One level of train.py:207-292.  diff [R,1] fp32, target [R,1] float64 (Q10)."""
     if event_threshold > 0:
         return mse(diff, target * event_threshold) * event_coeff_syn
-    dn = diff / (torch.linalg.norm(diff, dim=0, keepdim=True) + 1e-9)
-    tn = target / (torch.linalg.norm(target, dim=0, keepdim=True) + 1e-9)
+    # the norms run over the whole ray batch (dim 0): with pixel-sharded ranks the squared sums are all-reduced
+    # (differentiably), so every rank normalises by the global norm exactly as a single process would
+    from .parallel import global_sum
+    dnorm = torch.sqrt(global_sum((diff * diff).sum(dim=0, keepdim=True)))
+    tnorm = torch.sqrt(global_sum((target * target).sum(dim=0, keepdim=True)))
+    dn = diff / (dnorm + 1e-9)
+    tn = target / (tnorm + 1e-9)
     return mse(dn, tn) * event_coeff_real
 
 
