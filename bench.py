@@ -155,6 +155,53 @@ def workload_config(n_pixels, n_gpus, note=None):
 
 
 # ----------------------------------------------------------------------------------------------
+def bench_image_formation_stress(dev, steps=5, warmup=3):
+    """BASELINE.json configs[4]: the image-formation stage standalone at 1920x1080 on pre-rendered frames:
+    blur mean over 51 poses, log-intensity differences of 257 frames (256 event bins), scatter of 1e7 events.  HBM-bound;
+    inputs (1.3 GB / 6.4 GB) are far larger than the 126 MB L2, so no flush is needed between iterations."""
+    from benerf_b200 import image_formation as IF
+    R, P, B = 1920 * 1080, 51, 256
+    _, hbm_peak, src = peaks()
+    frames = torch.rand(B + 1, R, 3, device=dev)
+    out = {}
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    with torch.no_grad():
+        blur_in = frames[:P].reshape(P * R, 3)
+        ms = timed(lambda: IF.blur_mean(blur_in, P))
+        nbytes = 4 * R * 3 * (P + 1)
+        out["blur_mean"] = {"ms": ms, "bytes": nbytes, "achieved_gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / hbm_peak}
+        ev_in = frames.reshape((B + 1) * R, 3)
+        ms = timed(lambda: IF.event_logdiff(ev_in, B, "BeNeRF_Unreal"))
+        nbytes = 4 * R * (3 * (B + 1) + B)
+        out["event_logdiff"] = {"ms": ms, "bytes": nbytes, "achieved_gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / hbm_peak}
+        E = 10_000_000
+        g = torch.Generator(device=dev).manual_seed(0)
+        x = torch.randint(0, 1920, (E,), device=dev, generator=g, dtype=torch.int32)
+        y = torch.randint(0, 1080, (E,), device=dev, generator=g, dtype=torch.int32)
+        pol = (torch.randint(0, 2, (E,), device=dev, generator=g) * 2 - 1).float()
+        img = torch.zeros(1080, 1920, device=dev, dtype=torch.float64)
+        ms = timed(lambda: IF.accumulate_events(x, y, pol, 1080, 1920, out=img))
+        out["event_scatter"] = {"ms": ms, "events": E, "events_per_s": E / ms * 1e3, "read_gbs": 12 * E / ms / 1e6}
+    out["peak_gbs"], out["peak_source"] = hbm_peak, src
+    out["workload"] = "1920x1080, 51 blur poses, 257 frames -> 256 event bins, 1e7 events (BASELINE.json configs[4], per GPU)"
+    del frames
+    torch.cuda.empty_cache()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 def bench_train_step(opts, dev, world, rank, steps=5, warmup=3):
     """BASELINE.json configs[2] shape per GPU (weak scaling): e2nerf_synthetic 800x800, 1024 event pixels x 2 poses +
     2048 // 19 = 107 blur pixels x 19 poses = 4081 rays, 64 + 128 samples, forward + backward + the reference's Adam
@@ -176,6 +223,8 @@ def bench_train_step(opts, dev, world, rank, steps=5, warmup=3):
     run_nerf_helpers.init_nerf(graph.nerf_fine)
     graph.to(dev)
     trainer = Trainer(model, args)
+    if os.environ.get("BNRF_STEP_TRACE"):
+        trainer.phase_ms = []
     g = torch.Generator().manual_seed(99 + rank)
     r_evt, r_rgb = 1024, 2048 // N_POSES
     idx_evt = torch.randint(0, Ht * Wt, (r_evt,), generator=g).to(dev)
@@ -194,28 +243,32 @@ def bench_train_step(opts, dev, world, rank, steps=5, warmup=3):
     torch.cuda.synchronize()
     eng = graph.engine(args)
     eng.profile(True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record()
+    for i in range(steps):
         loss, _ = one()
-    e1.record()
+        evs[i + 1].record()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    ms = evs[0].elapsed_time(evs[-1]) / steps
+    per_step = [round(evs[i].elapsed_time(evs[i + 1]), 2) for i in range(steps)]
     launches = eng.profile_read()["launches"]
     eng.profile(False)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
+    if trainer.phase_ms:
+        print("phase trace:", trainer.phase_ms, file=sys.stderr)
     rays = (2 * r_evt + N_POSES * r_rgb) * world
     return {"metric": "rays_per_sec (training step: forward + backward + Adam + gradient all-reduce)", "value": rays / (ms / 1e3),
             "unit": "rays/s", "ms_per_step": ms, "steps": steps, "warmup": warmup, "rays_per_step_per_gpu": rays // world,
             "workload": "e2nerf_synthetic 800x800, 1024 event px x 2 poses + 107 blur px x 19 poses, 64+128 samples, C=3 "
                         "(BASELINE.json configs[2], weak scaling)",
             "algorithmic_tflops": 3 * rays / world * FLOP_PER_RAY / (ms / 1e3) / 1e12,
-            "gpu_launches_per_step": launches / steps, "final_loss": float(loss),
+            "ms_each_step": per_step, "gpu_launches_per_step": launches / steps, "final_loss": float(loss),
+            "mem_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 1),
             "backward": "fp32 SIMT GEMMs (sgemm.cu); tensor-core backward is the next step"}
 
 
@@ -241,6 +294,17 @@ def bench_ours(opts):
     run_nerf_helpers.init_nerf(graph.nerf_fine)
     graph.to(dev)
     eng = graph.engine(args)
+    if opts.mode == "train":                 # development aid: only the training-step measurement
+        t = bench_train_step(opts, dev, world, rank, steps=opts.steps, warmup=opts.warmup)
+        if rank == 0:
+            print(json.dumps(t))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # the two secondary measurements run first, on a quiet device (the headline render phase holds ~12 GB and the power cap)
+    train = None if opts.no_train_step else bench_train_step(opts, dev, world, rank)
+    stress = None if opts.no_train_step else bench_image_formation_stress(dev)
+    torch.cuda.empty_cache()
     R = opts.pixels
     g = torch.Generator().manual_seed(1234 + rank)
     host_idx_evt = torch.randint(0, H * W, (R,), generator=g).pin_memory()
@@ -325,7 +389,6 @@ def bench_ours(opts):
     peak_tf, _, peak_src = peaks()
     mlp_ms_per_launch = prof["mlp_ms"] / max(prof["mlp_timed"], 1)
     achieved = prof["mlp_flops"] / max(prof["mlp_ms"], 1e-9) / 1e9          # algorithmic TFLOP/s of the MLP kernel
-    train = None if opts.no_train_step else bench_train_step(opts, dev, world, rank)
     cpu = None
     if rank == 0 and world == 1 and not opts.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
@@ -353,6 +416,7 @@ def bench_ours(opts):
                                  "MMAs per product, so the tensor pipe issues 3x that (issued_*)"},
             "cpu_baseline": cpu,
             "train_step": train,
+            "image_formation_stress": stress,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * wall_e2e / opts.steps},
             "gpu_launches": int(launches_dev_region),
@@ -373,6 +437,7 @@ def main():
     ap.add_argument("--pixels", type=int, default=65536, help="pixels per GPU per step (R)")
     ap.add_argument("--cpu-pixels", type=int, default=128, help="pixels of the bounded CPU sample")
     ap.add_argument("--mlp-mode", default="tc", choices=["tc", "tc1", "simt"])
+    ap.add_argument("--mode", default="render", choices=["render", "train"], help="train: print only the training-step line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-step", action="store_true", help="skip the extra training-step measurement")
     opts = ap.parse_args()

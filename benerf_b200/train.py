@@ -21,19 +21,26 @@ class Trainer:
         self.flat = FlatGrads(params)
         self.base_lr = [[grp["lr"] for grp in o.param_groups] for o in self.optims]
         self.global_step = 0
+        self.phase_ms = None           # set to a list to get synchronised per-phase wall times (debug aid; serialises the step)
 
     def step(self, events_accu, idx_evt, idx_rgb, blur_target, ts_evt, ts_rgb, H, W, K, K_event, H_ev=None, W_ev=None):
         """idx_* are THIS rank's pixels; events_accu [H_ev, W_ev] float64; blur_target [R_rgb, C].  Returns (loss, parts)."""
         g, a = self.graph, self.args
+        mark = self._mark
+        mark(None)
         poses_evt = g.get_pose_evt(a, ts_evt)
         poses_rgb = g.get_pose_rgb(a, ts_rgb)
         ret_evt = g.render(self.global_step, poses_evt, idx_evt, H_ev or H, W_ev or W, K_event, a, enable_crf=True, sensor_type="event",
                            remap=None, training=True)
         ret_rgb = g.render(self.global_step, poses_rgb, idx_rgb, H, W, K, a, enable_crf=True, sensor_type="rgb", remap=None, training=True)
+        mark("forward")
         loss, parts = IF.training_loss(ret_evt, ret_rgb, events_accu, idx_evt, blur_target, a)
         self.flat.zero()
+        mark("loss")
         loss.backward()
+        mark("backward")
         self.flat.all_reduce_mean()                                      # the single exchange of the step
+        mark("all_reduce")
         opt_nerf, opt_pose, opt_trans = self.optims[0], self.optims[1], self.optims[2]
         if getattr(a, "optimize_nerf", True):
             opt_nerf.step()
@@ -48,5 +55,16 @@ class Trainer:
         for o, base, rate in zip(self.optims, self.base_lr, rates):
             for grp, lr0 in zip(o.param_groups, base):
                 grp["lr"] = lr0 * rate ** (self.global_step / decay_steps)
+        mark("optimizer")
         self.global_step += 1
         return loss.detach(), parts
+
+    def _mark(self, name):
+        if self.phase_ms is None:
+            return
+        import time
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        if name is not None:
+            self.phase_ms.append((self.global_step, name, round((now - self._t_prev) * 1e3, 2)))
+        self._t_prev = now

@@ -167,3 +167,32 @@ def test_image_formation_streaming_shapes():
         frames = rgb.reshape(B + 1, R, C)
         want = torch.stack([oif.event_log_diff(torch.cat([frames[b], frames[b + 1]]), ds, C).reshape(-1) for b in range(B)])
         assert max_abs(got, want) < 5e-6
+
+
+def test_full_image_eval_render_and_drivers(tmp_path):
+    """Graph.render_video / render_image_test / render_video_test (model/nerf.py:353-390, run_nerf_helpers.py:117-171):
+    whole 48x64 frames in one launch sequence, maps shaped [H,W,...], PNGs written, PSNR of two stochastic renders of the
+    same pose bounded (the reference's own eval renders are stochastic too, Q1/Q2/Q4)."""
+    from tests.test_gpu_backward import case_args
+    from benerf_b200 import optimize, run_nerf_helpers as rh
+    case = CASES["unreal_rgb"]
+    inp = make_inputs(case)
+    args = case_args(case)
+    graph = optimize.Model(args).build_network(args)
+    graph.nerf.load_state_dict(inp["coarse"]); graph.nerf_fine.load_state_dict(inp["fine"])
+    graph.to(DEV)
+    H, W = 48, 64
+    K = [[60.0, 0, 32.0], [0, 60.0, 24.0], [0, 0, 1]]
+    poses = graph.get_pose_rgb(args, torch.tensor(case.exposure), seg_num=3)
+    ret = graph.render_video(0, poses[:1], H, W, K, args, None, type="rgb")
+    assert ret["rgb_map"].shape == (H, W, 3) and ret["disp_map"].shape == (H, W) and ret["sigma"].shape == (H, W, 128)
+    assert not torch.isnan(ret["rgb_map"]).any()
+    rgbs, disps = rh.render_video_test(0, graph, poses, H, W, K, args, None)
+    assert rgbs.shape == (3, H, W, 3) and disps.shape == (3, H, W)
+    imgs, depth = rh.render_image_test(7, graph, poses, H, W, K, args, str(tmp_path), None, dir="images_test_x", need_depth=True)
+    assert len(imgs) == 3 and len(depth) == 3 and imgs[0].dtype.name == "uint8"
+    files = sorted(p.name for p in (tmp_path / "images_test_x" / "img_test_000007").iterdir())
+    assert files == ["_x000.png", "_x001.png", "_x002.png", "depth_000.png", "depth_001.png", "depth_002.png"]   # dir[11:] prefix, as upstream
+    again = graph.render_video(0, poses[:1], H, W, K, args, None, type="rgb")["rgb_map"]
+    mse = float(((again - ret["rgb_map"]) ** 2).mean())
+    assert mse < 0.05      # different noise/jitter draws, same scene
