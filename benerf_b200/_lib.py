@@ -18,7 +18,7 @@ LINEAR_NAMES = [f"pts_linears.{i}" for i in range(8)] + ["views_linears.0", "fea
 
 class Cfg(C.Structure):
     _fields_ = [("n_samples", C.c_int32), ("n_importance", C.c_int32), ("channels", C.c_int32), ("ndc", C.c_int32),
-                ("near_", C.c_float), ("far_", C.c_float), ("mlp_mode", C.c_int32), ("reserved", C.c_int32)]
+                ("near_", C.c_float), ("far_", C.c_float), ("mlp_mode", C.c_int32), ("gemm_mode", C.c_int32)]
 
 
 class Rng(C.Structure):

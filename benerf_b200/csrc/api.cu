@@ -147,6 +147,7 @@ int bnrf_create(bnrf_ctx** out, int device, const bnrf_cfg* cfg) {
     *out = nullptr;
     if (cfg->n_samples < 3 || cfg->n_importance < 0 || cfg->n_samples + cfg->n_importance > kMaxSamples)
         return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: need 3 <= n_samples and n_samples + n_importance <= %d", kMaxSamples);
+    if (cfg->gemm_mode != BNRF_GEMM_TC && cfg->gemm_mode != BNRF_GEMM_SIMT_FP32) return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: unknown gemm_mode %d", cfg->gemm_mode);
     if (cfg->channels != 1 && cfg->channels != 3) return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: channels must be 1 or 3");
     if (cfg->mlp_mode != BNRF_MLP_TC_FP16X2 && cfg->mlp_mode != BNRF_MLP_SIMT_FP32 && cfg->mlp_mode != BNRF_MLP_TC_1CTA)
         return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: unknown mlp_mode %d", cfg->mlp_mode);

@@ -18,6 +18,10 @@ struct GemmArgs {
     int vec_a, vec_b;                 // set by the launcher (16-byte aligned, ld % 4 == 0)
 };
 
+// Dispatches to the tensor-core kernel (gemm_tc.cu) when cfg.gemm_mode == BNRF_GEMM_TC and the shape qualifies,
+// else to the fp32 FFMA kernel.
 int launch_sgemm(bnrf_ctx* ctx, bool ta, bool tb, GemmArgs g, cudaStream_t st);
+bool gemm_tc_eligible(const GemmArgs& g);
+int launch_gemm_tc(bnrf_ctx* ctx, bool ta, bool tb, GemmArgs g, cudaStream_t st);
 
 }  // namespace bnrf

@@ -34,13 +34,14 @@ def _ptr(t, dtype=torch.float32, device=None, name="tensor"):
 class Engine:
     """One context per (process, device) -- SURVEY 8-b conventions."""
 
-    def __init__(self, n_samples=64, n_importance=64, channels=3, ndc=True, near=0.0, far=1.0, mlp_mode="tc", device=None):
+    def __init__(self, n_samples=64, n_importance=64, channels=3, ndc=True, near=0.0, far=1.0, mlp_mode="tc", device=None, gemm_mode="tc"):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise BnrfError("benerf_b200 needs a CUDA (sm_100a) device; there is no CPU path")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else torch.device(device).index or 0)
-        self.cfg = _lib.Cfg(n_samples, n_importance, channels, int(bool(ndc)), near, far, MLP_MODES[mlp_mode], 0)
+        self.cfg = _lib.Cfg(n_samples, n_importance, channels, int(bool(ndc)), near, far, MLP_MODES[mlp_mode], {"tc": 0, "simt": 1}[gemm_mode])
         self.n_samples, self.n_importance, self.channels = n_samples, n_importance, channels
+        self.mlp_mode, self.gemm_mode = mlp_mode, gemm_mode
         self._ctx = C.c_void_p()
         rc = self.lib.bnrf_create(C.byref(self._ctx), self.device.index, C.byref(self.cfg))
         if rc != _lib.OK:

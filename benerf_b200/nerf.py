@@ -112,7 +112,7 @@ class Graph(nn.Module):
                 raise ValueError("benerf_b200 covers the configuration every shipped config uses: ndc=True, "
                                  "use_viewdirs=True, use_barf_c2f=False")
             self._engine = Engine(n_samples=args.N_samples, n_importance=args.N_importance, channels=args.channels,
-                                  mlp_mode=getattr(args, "mlp_mode", "tc"))
+                                  mlp_mode=getattr(args, "mlp_mode", "tc"), gemm_mode=getattr(args, "gemm_mode", "tc"))
         return self._engine
 
     def _sync(self, eng):

@@ -47,6 +47,10 @@ typedef enum {
 #define BNRF_MLP_SIMT_FP32 1  /* plain fp32 FFMA; on-device cross-check of the tensor-core path */
 #define BNRF_MLP_TC_1CTA 2    /* same arithmetic as mode 0 on single CTAs (cta_group::1); mode 0 runs CTA pairs (cta_group::2) */
 
+/* Backward-pass GEMMs (cfg.gemm_mode). */
+#define BNRF_GEMM_TC 0         /* tcgen05.mma kind::f16 on bf16 hi/lo split operands (3 MMAs per product), fp32 accumulate */
+#define BNRF_GEMM_SIMT_FP32 1  /* plain fp32 FFMA (on-device cross-check; also used for shapes too small for a 128-row tile) */
+
 /* Order of the 12 linears in bnrf_set_weights (the reference's state-dict order). */
 enum {
     BNRF_L_PTS0 = 0, /* .. BNRF_L_PTS0 + 7 : pts_linears.0-7  (256,63) (256,256)x4 (256,319) (256,256)x2 */
@@ -67,7 +71,7 @@ typedef struct {
     int32_t ndc;           /* args.ndc (always 1 in the reference, Q3)    model/nerf.py:278 */
     float near_, far_;     /* sampling range, Graph.render defaults 0, 1  model/nerf.py:239 */
     int32_t mlp_mode;      /* BNRF_MLP_*                                                    */
-    int32_t reserved;
+    int32_t gemm_mode;     /* BNRF_GEMM_*: arithmetic of the backward pass's dgrad / wgrad GEMMs                */
 } bnrf_cfg;
 
 /* The four random draws of one Graph.render.  Parity mode: device pointers to

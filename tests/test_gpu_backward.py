@@ -33,29 +33,33 @@ def rel_err(got, want):
     return float((got - want).norm() / want.norm().clamp_min(1e-30))
 
 
-@pytest.fixture(scope="module")
-def eng():
+@pytest.fixture(scope="module", params=["tc", "simt"])
+def eng(request):
     from benerf_b200.engine import Engine
-    return Engine()
+    return Engine(gemm_mode=request.param)
 
 
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 63, 1000), (3, 128, 5000), (1, 256, 777), (257, 320, 129)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 63, 1000), (3, 128, 5000), (1, 256, 777), (257, 320, 129), (1000, 256, 256),
+                                   (256, 256, 20000), (128, 96, 333), (4097, 64, 256)])
 def test_sgemm_matches_torch(eng, ta, tb, M, N, K):
     g = torch.Generator().manual_seed(M * 1000 + N + K)
     A = torch.randn((K, M) if ta else (M, K), generator=g).to(DEV)
     B = torch.randn((N, K) if tb else (K, N), generator=g).to(DEV)
     want = (A.t() if ta else A).double() @ (B.t() if tb else B).double()
+    # tensor-core path: bf16 hi/lo split (~2^-16 per product) + the TMEM accumulator truncates (not rounds) each of the
+    # 3*K/16 accumulation steps, a measured systematic shrink of ~0.5 ulp per step (7e-5 at K = 20000)
+    tol = 2e-6 + 1e-9 * K if eng.gemm_mode == "simt" else 3e-5 + 5e-9 * K
     got = eng.debug_sgemm(A, B, ta, tb, M, N, K, epi=0)
-    assert rel_err(got, want) < 2e-6
+    assert rel_err(got, want) < tol
     got = eng.debug_sgemm(A, B, ta, tb, M, N, K, epi=2, C_out=torch.ones(M, N, device=DEV))      # split contraction, atomics
-    assert rel_err(got, want + 1.0) < 2e-6
+    assert rel_err(got, want + 1.0) < tol
     got = eng.debug_sgemm(A, B, ta, tb, M, N, K, epi=1, C_out=torch.full((M, N), 2.0, device=DEV))
-    assert rel_err(got, want + 2.0) < 2e-6
+    assert rel_err(got, want + 2.0) < tol
     mask = torch.randn(M, N, generator=g).to(DEV)
     r_row, r_col = torch.randn(M, generator=g).to(DEV), torch.randn(N, generator=g).to(DEV)
     got = eng.debug_sgemm(A, B, ta, tb, M, N, K, epi=3, mask=mask, r_row=r_row, r_col=r_col)
-    assert rel_err(got, (want + torch.outer(r_row, r_col).double()) * (mask > 0)) < 2e-6
+    assert rel_err(got, (want + torch.outer(r_row, r_col).double()) * (mask > 0)) < tol
 
 
 @pytest.mark.parametrize("traj", ["spline", "linear"])
