@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <math.h>
 #include "common.cuh"
+#include "bwd_tiles.cuh"
 
 namespace bnrf {
 
@@ -46,6 +47,7 @@ int alloc_net(bnrf_ctx* ctx, int n) {
     BNRF_CUDA(ctx, cudaMalloc(&np.tc_stream, tc_stream_halfs() * sizeof(__half)));
     BNRF_CUDA(ctx, cudaMalloc(&np.tc2_stream, tc2_stream_halfs() * sizeof(__half)));
     BNRF_CUDA(ctx, cudaMalloc(&np.tc_scale, 16 * sizeof(float)));
+    BNRF_CUDA(ctx, cudaMalloc(&np.dg_img, dgrad_images_bytes()));
     return BNRF_OK;
 }
 
@@ -53,7 +55,7 @@ void free_net(bnrf_ctx* ctx, int n) {
     NetParams& np = ctx->net[n];
     for (int s = 0; s < 10; ++s) { cudaFree(np.wt[s]); cudaFree(np.bias[s]); }
     cudaFree(np.w_alpha); cudaFree(np.b_alpha); cudaFree(np.w_rgb); cudaFree(np.b_rgb); cudaFree(np.w_dir);
-    cudaFree(np.tc_stream); cudaFree(np.tc2_stream); cudaFree(np.tc_scale);
+    cudaFree(np.tc_stream); cudaFree(np.tc2_stream); cudaFree(np.tc_scale); cudaFree(np.dg_img);
     memset(&np, 0, sizeof(np));
 }
 
@@ -93,6 +95,7 @@ int pack_weights(bnrf_ctx* ctx, int n, const float* const* w, const float* const
     int rc = pack_tc_stream(ctx, n, st);
     if (rc != BNRF_OK) return rc;
     np.ready = true;
+    np.dg_dirty = true;
     return BNRF_OK;
 }
 
@@ -121,7 +124,7 @@ static Workspace carve(const bnrf_cfg& c, int64_t n, void* base) {
 }
 
 static int run_mlp(bnrf_ctx* ctx, int net, const float* o, const float* d, const float* vb, const float* z, int64_t n,
-                   int S, float* raw, float* acts, cudaStream_t st) {
+                   int S, float* raw, const ActPtrs* acts, cudaStream_t st) {
     if (!ctx->net[net].ready) return fail(ctx, BNRF_ERR_STATE, "weights of network %d not set (bnrf_set_weights)", net);
     const double macs = 63.0 * 256 + 4 * 65536.0 + 319.0 * 256 + 2 * 65536.0 + 256 + 65536.0 + 283.0 * 128 + 128.0 * ctx->cfg.channels;
     MlpTimer timer(ctx, st, 2.0 * macs * (double)n * (double)S);
@@ -285,7 +288,7 @@ static int render_impl(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx
     if ((rc = launch_rays(ctx, poses, ray_idx, P, R, H, W, K, remap, w.o, w.d, w.view, st))) return rc;
     if ((rc = launch_stratified(ctx, r.t_rand, &r, n, Sc, w.z_c, st))) return rc;
     if ((rc = launch_viewbias(ctx, 0, w.view, n, w.vb, st))) return rc;
-    if ((rc = run_mlp(ctx, 0, w.o, w.d, w.vb, w.z_c, n, Sc, raw_c, s.acts_c, st))) return rc;
+    if ((rc = run_mlp(ctx, 0, w.o, w.d, w.vb, w.z_c, n, Sc, raw_c, saved ? &s.acts_c : nullptr, st))) return rc;
     // coarse composite: outputs go to rgb0/disp0/acc0 when a fine pass follows (model/nerf.py:319-343)
     float* sigma_c_out = saved ? sig_c : (fine ? nullptr : out->sigma);
     if ((rc = launch_composite(ctx, raw_c, w.z_c, w.d, r.noise_c, &r, kStreamNoiseC, n, Sc,
@@ -303,7 +306,7 @@ static int render_impl(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx
     }
     if (out->z_vals) BNRF_CUDA(ctx, cudaMemcpyAsync(out->z_vals, w.z_f, (size_t)n * Sf * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if ((rc = launch_viewbias(ctx, 1, w.view, n, w.vb, st))) return rc;
-    if ((rc = run_mlp(ctx, 1, w.o, w.d, w.vb, w.z_f, n, Sf, raw_f, s.acts_f, st))) return rc;
+    if ((rc = run_mlp(ctx, 1, w.o, w.d, w.vb, w.z_f, n, Sf, raw_f, saved ? &s.acts_f : nullptr, st))) return rc;
     if ((rc = launch_composite(ctx, raw_f, w.z_f, w.d, r.noise_f, &r, kStreamNoiseF, n, Sf, out->rgb_map, out->disp_map,
                                out->acc_map, nullptr, out->depth_map, saved ? sig_f : out->sigma, st))) return rc;
     if (saved && out->sigma) BNRF_CUDA(ctx, cudaMemcpyAsync(out->sigma, sig_f, (size_t)n * Sf * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -2,11 +2,14 @@
 // model/nerf.py:236-343): d(rgb_map, rgb0) -> d(NeRF parameters of both networks), d(poses).
 //
 // The forward pass in training mode (bnrf_render_forward_train) keeps, per network, the encoded
-// points and the nine hidden activations of every sample (written by the tensor-core kernel's
-// epilogue, mlp_tc2.cu) plus raw / z / sigma.  The backward pass is layer-by-layer:
+// points and the nine hidden activations of every sample as bf16 hi/lo tile matrices (written by
+// the tensor-core kernel's epilogue, mlp_tc2.cu; format in bwd_tiles.cuh) plus raw / z / sigma.
+// The backward pass is layer-by-layer:
 //   composite_backward   raw2output (model/nerf.py:118-148): sigmoid, relu(sigma+noise), alpha,
 //                        exclusive cumprod, sum(w*rgb) -- one warp per ray, suffix scan
-//   heads / dgrad / wgrad the 12 linears of NeRF.forward (model/nerf.py:93-112) through sgemm.cu
+//   heads / dgrad / wgrad the 12 linears of NeRF.forward (model/nerf.py:93-112): the 256-wide ones
+//                        through the tile kernels of bwd_tiles.cu (gradients stay bf16 hi/lo tile
+//                        matrices between layers), the narrow heads through sgemm.cu
 //   pe_ray_backward      sin/cos encoding (model/embedder.py:9-34) and pts = o + d*z
 //   viewdir_backward     direction encoding + the per-ray view bias
 //   rays_backward        ndc_rays + get_specific_rays + viewdirs (run_nerf_helpers.py:35-71) -> d poses
@@ -14,6 +17,8 @@
 // model/nerf.py:324), exactly as in the reference.  d poses -> d knots is pose.cu (dual numbers).
 #include "common.cuh"
 #include "sgemm.cuh"
+#include "bwd_tiles.cuh"
+#include "tc_ptx.cuh"
 
 namespace bnrf {
 
@@ -125,18 +130,44 @@ __global__ void composite_backward_kernel(const float* __restrict__ raw, const f
 }
 
 // ------------------------------------------------------------------ rgb head backward + ReLU of the view layer
-// dZ9[row][j] = (H9[row][j] > 0) * sum_c d_raw[row][c] * W_rgb[c][j]
+// dZ9[row][j] = (H9[row][j] > 0) * sum_c d_raw[row][c] * W_rgb[c][j]; a thread owns 8 columns of one row and writes them
+// as fp32 (per-ray view-bias sum) and as bf16 hi/lo into the width-128 tile matrix the dgrad / wgrad kernels read.
+// Rows of the last tile beyond `rows` are written as zeros (they take part in the wgrad contraction).
 template <int C>
 __global__ void heads_backward_kernel(const float* __restrict__ d_raw, const float* __restrict__ h9,
-                                      const float* __restrict__ w_rgb, int64_t rows, float* __restrict__ dz9) {
+                                      const float* __restrict__ w_rgb, int64_t rows, int64_t rows_pad,
+                                      float* __restrict__ dz9, unsigned char* __restrict__ dz9_tiles) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= rows * kHalf) return;
-    const int64_t row = e / kHalf;
-    const int j = (int)(e % kHalf);
-    float v = 0.f;
+    if (e >= rows_pad * (kHalf / 8)) return;
+    const int64_t row = e / (kHalf / 8);
+    const int c8 = (int)(e % (kHalf / 8));
+    float v[8];
 #pragma unroll
-    for (int c = 0; c < C; ++c) v = fmaf(d_raw[row * (C + 1) + c], w_rgb[c * kHalf + j], v);
-    dz9[e] = (h9[e] > 0.0f) ? v : 0.0f;
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (row < rows) {
+        float g[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) g[c] = d_raw[row * (C + 1) + c];
+        const float4 a = *reinterpret_cast<const float4*>(h9 + row * kHalf + c8 * 8), b = *reinterpret_cast<const float4*>(h9 + row * kHalf + c8 * 8 + 4);
+        const float h[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float x = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) x = fmaf(g[c], w_rgb[c * kHalf + c8 * 8 + j], x);
+            v[j] = (h[j] > 0.0f) ? x : 0.0f;
+        }
+        float4* dst = reinterpret_cast<float4*>(dz9 + row * kHalf + c8 * 8);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    uint4 hi, lo;
+    bwt::split8_bf16_pub(v, hi, lo);
+    const int64_t tile = row / bwt::kTileRows;
+    const int r = (int)(row % bwt::kTileRows);
+    unsigned char* t = dz9_tiles + (size_t)tile * bwt::tile_bytes(kHalf) + (size_t)(c8 / 8) * bwt::kKbBytes + (size_t)r * 128 + ((uint32_t)((c8 & 7) ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(t) = hi;
+    *reinterpret_cast<uint4*>(t + bwt::tile_part_bytes(kHalf)) = lo;
 }
 
 // dvb[ray][j] = sum_s dZ9[ray*S + s][j]  (the view bias is shared by the S samples of a ray)
@@ -348,95 +379,147 @@ __global__ void rays_backward_kernel(const float* __restrict__ poses, const int6
 // ------------------------------------------------------------------ per-network MLP backward
 // d_raw [rows, C+1] -> parameter gradients (PyTorch layouts, accumulated) and d_pe [rows,64], dvb [n,128].
 struct BwdBuffers {
-    float *d_raw, *buf_a, *buf_b, *d_pe, *dz9, *dvb, *pe_dir;
+    float *d_raw, *d_pe, *dz9, *dvb, *pe_dir;
+    unsigned char* dz_tiles;     // 9 bf16 tile matrices of width 256: dZ0..dZ7, d feature
+    unsigned char* dz9_tiles;    // bf16 tile matrix of width 128
+    int64_t tiles;
 };
 
-static int mlp_backward(bnrf_ctx* ctx, int net, int64_t n, int S, const float* acts, const BwdBuffers& w,
+// dgrad B operands of one network, in the order the backward pass uses them
+struct DgImage { int step, k0, N, K; };
+static const DgImage kDgImages[11] = {
+    {9, 0, 256, 128},                                  // views_linears.0 (feature block): dZ9 -> d feature
+    {8, 0, 256, 256},                                  // feature_linear: d feature -> d h7
+    {7, 0, 256, 256}, {6, 0, 256, 256},
+    {5, kPtsChPad, 256, 256}, {5, 0, 64, 256},         // pts_linears.5: h4 block, encoded-points block
+    {4, 0, 256, 256}, {3, 0, 256, 256}, {2, 0, 256, 256}, {1, 0, 256, 256},
+    {0, 0, 64, 256},                                   // pts_linears.0: encoded points
+};
+static size_t dg_image_offset(int i) {
+    size_t off = 0;
+    for (int j = 0; j < i; ++j) off += bwt::dgrad_image_bytes(kDgImages[j].N, kDgImages[j].K);
+    return off;
+}
+size_t dgrad_images_bytes() { return dg_image_offset(11); }
+
+static int pack_dgrad_images(bnrf_ctx* ctx, int net, cudaStream_t st) {
+    NetParams& np = ctx->net[net];
+    for (int i = 0; i < 11; ++i) {
+        const DgImage& d = kDgImages[i];
+        int rc = bwt::pack_dgrad_image(ctx, np.wt[d.step] + (size_t)d.k0 * d.K, d.N, d.K, np.dg_img + dg_image_offset(i), st);
+        if (rc) return rc;
+    }
+    np.dg_dirty = false;
+    return BNRF_OK;
+}
+
+static int mlp_backward(bnrf_ctx* ctx, int net, int64_t n, int S, const ActPtrs& acts, const BwdBuffers& w,
                         float* const* dW, float* const* dB, cudaStream_t st) {
-    const NetParams& np = ctx->net[net];
+    NetParams& np = ctx->net[net];
     const int C = ctx->cfg.channels;
     const int64_t rows = n * S;
-    const float* pe = acts;
-    auto H = [&](int l) { return acts + rows * kPtsChPad + (int64_t)l * rows * kWidth; };   // l = 0..7, 8 = feature
-    const float* h9 = acts + rows * (kPtsChPad + 9 * kWidth);
+    const int tiles = (int)bwt::tile_count(rows);
+    const size_t mat = (size_t)w.tiles * bwt::tile_bytes(kWidth);                       // one gradient tile matrix
+    const size_t hmat = (size_t)acts.t_alloc * bwt::tile_bytes(kWidth);                 // one activation tile matrix
+    auto DZ = [&](int l) { return w.dz_tiles + (size_t)l * mat; };                      // l = 0..7, 8 = d feature
+    auto H = [&](int l) { return acts.h_tiles + (size_t)l * hmat; };                    // l = 0..7, 8 = feature
     int rc;
+    if (np.dg_dirty && (rc = pack_dgrad_images(ctx, net, st))) return rc;
     auto colsum = [&](const float* X, int N, int64_t ld, int64_t cnt, float* out) {
         const int64_t rpb = 512;
         colsum_kernel<<<dim3((unsigned)ceil_div(cnt, rpb), (unsigned)ceil_div(N, 128)), 128, 0, st>>>(X, cnt, N, ld, rpb, out);
         ctx->launches++;
     };
-    // wgrad: dW[n_out][col0 + k] += sum_rows dZ[row][n_out] * A[row][k]
-    auto wgrad = [&](const float* dZ, int n_out, int64_t ldz, const float* A, int k_in, int64_t lda, float* dWl, int64_t ldw, int col0) {
-        GemmArgs g{};
-        g.M = n_out; g.N = k_in; g.K = rows; g.A = dZ; g.lda = ldz; g.B = A; g.ldb = lda;
-        g.C = dWl + col0; g.ldc = ldw; g.epi = GEMM_ATOMIC;
-        return launch_sgemm(ctx, true, false, g, st);
-    };
-    // dgrad: out[row][k] = sum_n dZ[row][n] * Wt[k][n]   (Wt = k-major copy, [K_pad][N])
-    auto dgrad = [&](const float* dZ, int n_out, const float* Wt, int k_in, float* out, int64_t ldo, int epi,
-                     const float* mask, const float* r_row, int64_t r_stride, const float* r_col) {
-        GemmArgs g{};
-        g.M = rows; g.N = k_in; g.K = n_out; g.A = dZ; g.lda = n_out; g.B = Wt; g.ldb = n_out;
-        g.C = out; g.ldc = ldo; g.epi = epi; g.mask = mask; g.ldm = ldo; g.r_row = r_row; g.r_stride = r_stride; g.r_col = r_col;
-        return launch_sgemm(ctx, false, true, g, st);
+    auto dgrad = [&](const unsigned char* A, int K, int img, int epi, const unsigned char* mask, unsigned char* out_tiles, float* out_f32,
+                     const float* r_row, int64_t r_stride, const float* r_col) {
+        bwt::DgradArgs a{};
+        a.a_tiles = A; a.K = K; a.b_img = np.dg_img + dg_image_offset(img); a.N = kDgImages[img].N; a.epi = epi;
+        a.mask_tiles = mask; a.r_row = r_row; a.r_stride = r_stride; a.r_col = r_col;
+        a.out_tiles = out_tiles; a.out_f32 = out_f32; a.ld_out = kPtsChPad; a.rows = rows; a.tiles = tiles;
+        return bwt::launch_tile_dgrad(ctx, a, st);
     };
 
     // ---- heads: rgb_linear (128 -> C) and the ReLU of the view layer ----
-    if (C == 3) heads_backward_kernel<3><<<(unsigned)ceil_div(rows * kHalf, 256), 256, 0, st>>>(w.d_raw, h9, np.w_rgb, rows, w.dz9);
-    else heads_backward_kernel<1><<<(unsigned)ceil_div(rows * kHalf, 256), 256, 0, st>>>(w.d_raw, h9, np.w_rgb, rows, w.dz9);
-    BNRF_LAUNCH_CHECK(ctx);
-    if ((rc = wgrad(w.d_raw, C, C + 1, h9, kHalf, kHalf, dW[BNRF_L_RGB], kHalf, 0))) return rc;
+    const float* h9 = acts.h9_f32;
+    {
+        const int64_t rows_pad = (int64_t)tiles * bwt::kTileRows;
+        const unsigned grid = (unsigned)ceil_div(rows_pad * (kHalf / 8), 256);
+        if (C == 3) heads_backward_kernel<3><<<grid, 256, 0, st>>>(w.d_raw, h9, np.w_rgb, rows, rows_pad, w.dz9, w.dz9_tiles);
+        else heads_backward_kernel<1><<<grid, 256, 0, st>>>(w.d_raw, h9, np.w_rgb, rows, rows_pad, w.dz9, w.dz9_tiles);
+        BNRF_LAUNCH_CHECK(ctx);
+    }
+    {   // rgb_linear weight gradient: [C, rows] x [rows, 128] (too narrow for a tensor-core tile)
+        GemmArgs g{};
+        g.M = C; g.N = kHalf; g.K = rows; g.A = w.d_raw; g.lda = C + 1; g.B = h9; g.ldb = kHalf;
+        g.C = dW[BNRF_L_RGB]; g.ldc = kHalf; g.epi = GEMM_ATOMIC;
+        if ((rc = launch_sgemm(ctx, true, false, g, st))) return rc;
+    }
     colsum(w.d_raw, C, C + 1, rows, dB[BNRF_L_RGB]);
-    // ---- views_linears.0: feature block by GEMM, direction block + bias per ray ----
+    // ---- views_linears.0: direction block + bias per ray (the view bias is shared by the S samples of a ray) ----
     sum_samples_kernel<<<(unsigned)n, kHalf, 0, st>>>(w.dz9, S, w.dvb);
     BNRF_LAUNCH_CHECK(ctx);
     colsum(w.dvb, kHalf, kHalf, n, dB[BNRF_L_VIEWS]);
-    if ((rc = wgrad(w.dz9, kHalf, kHalf, H(8), kWidth, kWidth, dW[BNRF_L_VIEWS], kWidth + kDirCh, 0))) return rc;
-    if ((rc = dgrad(w.dz9, kHalf, np.wt[9], kWidth, w.buf_a, kWidth, GEMM_STORE, nullptr, nullptr, 0, nullptr))) return rc;   // dF
-    // ---- feature_linear (no activation) + alpha_linear; ReLU of layer 7 ----
-    if ((rc = wgrad(w.buf_a, kWidth, kWidth, H(7), kWidth, kWidth, dW[BNRF_L_FEATURE], kWidth, 0))) return rc;
-    colsum(w.buf_a, kWidth, kWidth, rows, dB[BNRF_L_FEATURE]);
-    if ((rc = wgrad(w.d_raw + C, 1, C + 1, H(7), kWidth, kWidth, dW[BNRF_L_ALPHA], kWidth, 0))) return rc;
-    colsum(w.d_raw + C, 1, C + 1, rows, dB[BNRF_L_ALPHA]);
-    if ((rc = dgrad(w.buf_a, kWidth, np.wt[8], kWidth, w.buf_b, kWidth, GEMM_MASKED, H(7), w.d_raw + C, C + 1, np.w_alpha))) return rc;   // dZ7
-    // ---- pts_linears 7 .. 0 ----
-    float* cur = w.buf_b;
-    float* nxt = w.buf_a;
-    for (int l = 7; l >= 0; --l) {
-        colsum(cur, kWidth, kWidth, rows, dB[l]);
-        if (l == 0) {
-            if ((rc = wgrad(cur, kWidth, kWidth, pe, kPtsCh, kPtsChPad, dW[0], kPtsCh, 0))) return rc;
-            if ((rc = dgrad(cur, kWidth, np.wt[0], kPtsChPad, w.d_pe, kPtsChPad, GEMM_ACCUM, nullptr, nullptr, 0, nullptr))) return rc;
-        } else if (l == 5) {                      // input = cat([encoded pts (63), h4 (256)])  (model/nerf.py:98)
-            if ((rc = wgrad(cur, kWidth, kWidth, pe, kPtsCh, kPtsChPad, dW[5], kPtsCh + kWidth, 0))) return rc;
-            if ((rc = wgrad(cur, kWidth, kWidth, H(4), kWidth, kWidth, dW[5], kPtsCh + kWidth, kPtsCh))) return rc;
-            if ((rc = dgrad(cur, kWidth, np.wt[5], kPtsChPad, w.d_pe, kPtsChPad, GEMM_STORE, nullptr, nullptr, 0, nullptr))) return rc;
-            if ((rc = dgrad(cur, kWidth, np.wt[5] + (size_t)kPtsChPad * kWidth, kWidth, nxt, kWidth, GEMM_MASKED, H(4), nullptr, 0, nullptr))) return rc;
+    // ---- dgrad chain: dZ9 -> d feature -> dZ7 -> ... -> dZ0 -> d encoding ----
+    if ((rc = dgrad(w.dz9_tiles, kHalf, 0, bwt::DG_TILE, nullptr, DZ(8), nullptr, nullptr, 0, nullptr))) return rc;
+    if ((rc = dgrad(DZ(8), kWidth, 1, bwt::DG_TILE_MASKED, H(7), DZ(7), nullptr, w.d_raw + C, C + 1, np.w_alpha))) return rc;   // + alpha_linear
+    if ((rc = dgrad(DZ(7), kWidth, 2, bwt::DG_TILE_MASKED, H(6), DZ(6), nullptr, nullptr, 0, nullptr))) return rc;
+    if ((rc = dgrad(DZ(6), kWidth, 3, bwt::DG_TILE_MASKED, H(5), DZ(5), nullptr, nullptr, 0, nullptr))) return rc;
+    if ((rc = dgrad(DZ(5), kWidth, 4, bwt::DG_TILE_MASKED, H(4), DZ(4), nullptr, nullptr, 0, nullptr))) return rc;              // cat([pe, h4]) (model/nerf.py:98)
+    if ((rc = dgrad(DZ(5), kWidth, 5, bwt::DG_F32_STORE, nullptr, nullptr, w.d_pe, nullptr, 0, nullptr))) return rc;
+    for (int l = 4; l >= 1; --l)
+        if ((rc = dgrad(DZ(l), kWidth, 10 - l, bwt::DG_TILE_MASKED, H(l - 1), DZ(l - 1), nullptr, nullptr, 0, nullptr))) return rc;
+    if ((rc = dgrad(DZ(0), kWidth, 10, bwt::DG_F32_ACCUM, nullptr, nullptr, w.d_pe, nullptr, 0, nullptr))) return rc;
+    // ---- every 256-wide weight / bias gradient in one launch ----
+    bwt::WgradParams p{};
+    p.tiles = tiles; p.rows = rows;
+    auto job = [&](const unsigned char* dz, int M, const unsigned char* h, int N, float* dWl, int ldw, int col0, int n_valid, float* dBl) {
+        bwt::WgradJob& j = p.job[p.n_jobs++];
+        j.dz_tiles = dz; j.M = M; j.h_tiles = h; j.N = N; j.dW = dWl; j.ldw = ldw; j.col0 = col0; j.n_valid = n_valid; j.dB = dBl;
+        return &j;
+    };
+    job(DZ(0), kWidth, acts.pe_tiles, kPtsChPad, dW[0], kPtsCh, 0, kPtsCh, dB[0]);
+    for (int l = 1; l < 8; ++l) {
+        if (l == 5) {
+            job(DZ(5), kWidth, acts.pe_tiles, kPtsChPad, dW[5], kPtsCh + kWidth, 0, kPtsCh, dB[5]);
+            job(DZ(5), kWidth, H(4), kWidth, dW[5], kPtsCh + kWidth, kPtsCh, kWidth, nullptr);
         } else {
-            if ((rc = wgrad(cur, kWidth, kWidth, H(l - 1), kWidth, kWidth, dW[l], kWidth, 0))) return rc;
-            if ((rc = dgrad(cur, kWidth, np.wt[l], kWidth, nxt, kWidth, GEMM_MASKED, H(l - 1), nullptr, 0, nullptr))) return rc;
+            job(DZ(l), kWidth, H(l - 1), kWidth, dW[l], kWidth, 0, kWidth, dB[l]);
         }
-        float* t = cur; cur = nxt; nxt = t;
     }
-    return BNRF_OK;
+    {
+        bwt::WgradJob* j = job(DZ(8), kWidth, H(7), kWidth, dW[BNRF_L_FEATURE], kWidth, 0, kWidth, dB[BNRF_L_FEATURE]);
+        j->wrow = w.d_raw + C; j->wrow_stride = C + 1; j->dWv = dW[BNRF_L_ALPHA]; j->dBv = dB[BNRF_L_ALPHA];   // alpha_linear reads the same h7 slices
+    }
+    job(w.dz9_tiles, kHalf, H(8), kWidth, dW[BNRF_L_VIEWS], kWidth + kDirCh, 0, kWidth, nullptr);
+    return bwt::launch_tile_wgrad(ctx, p, st);
 }
 
 // ------------------------------------------------------------------ saved-tensor and workspace carve-ups
 SavedLayout carve_saved(const bnrf_cfg& c, int64_t n, void* base) {
     SavedLayout s;
     size_t off = 0;
-    auto take = [&](size_t floats) {
-        float* p = base ? reinterpret_cast<float*>(static_cast<char*>(base) + off) : nullptr;
-        off += (floats * sizeof(float) + 255) / 256 * 256;
+    auto take_bytes = [&](size_t bytes) {
+        char* p = base ? static_cast<char*>(base) + off : nullptr;
+        off += (bytes + 1023) / 1024 * 1024;            // tile matrices are read by cp.async.bulk: keep everything 1 KB aligned
         return p;
     };
+    auto take = [&](size_t floats) { return reinterpret_cast<float*>(take_bytes(floats * sizeof(float))); };
     const int Sc = c.n_samples, Sf = c.n_samples + c.n_importance;
     const bool fine = c.n_importance > 0;
+    auto acts = [&](int64_t rows) {
+        ActPtrs a{};
+        a.t_alloc = rows > 0 ? bwt::tile_alloc(rows) : 0;
+        a.pe_f32 = take(rows * kPtsChPad);
+        a.h9_f32 = take(rows * kHalf);
+        a.pe_tiles = reinterpret_cast<unsigned char*>(take_bytes((size_t)a.t_alloc * bwt::tile_bytes(kPtsChPad)));
+        a.h_tiles = reinterpret_cast<unsigned char*>(take_bytes(9 * (size_t)a.t_alloc * bwt::tile_bytes(kWidth)));
+        return a;
+    };
     s.o = take(n * 3); s.d = take(n * 3); s.view = take(n * 3);
     s.z_c = take(n * Sc); s.raw_c = take(n * Sc * (c.channels + 1)); s.sig_c = take(n * Sc);
-    s.acts_c = take((size_t)n * Sc * kActFloatsPerRow);
+    s.acts_c = acts(n * Sc);
     s.z_f = take(fine ? n * Sf : 0); s.raw_f = take(fine ? n * Sf * (c.channels + 1) : 0); s.sig_f = take(fine ? n * Sf : 0);
-    s.acts_f = take(fine ? (size_t)n * Sf * kActFloatsPerRow : 0);
+    s.acts_f = acts(fine ? n * Sf : 0);
     s.bytes = off;
     return s;
 }
@@ -445,14 +528,17 @@ struct BwdWorkspace { BwdBuffers b; float *g_o, *g_d, *g_v, *g_dn; size_t bytes;
 static BwdWorkspace carve_bwd(const bnrf_cfg& c, int64_t n, void* base) {
     BwdWorkspace w;
     size_t off = 0;
-    auto take = [&](size_t floats) {
-        float* p = base ? reinterpret_cast<float*>(static_cast<char*>(base) + off) : nullptr;
-        off += (floats * sizeof(float) + 255) / 256 * 256;
+    auto take_bytes = [&](size_t bytes) {
+        char* p = base ? static_cast<char*>(base) + off : nullptr;
+        off += (bytes + 1023) / 1024 * 1024;
         return p;
     };
+    auto take = [&](size_t floats) { return reinterpret_cast<float*>(take_bytes(floats * sizeof(float))); };
     const int64_t rows = n * (c.n_samples + c.n_importance);
+    w.b.tiles = bwt::tile_count(rows);
     w.b.d_raw = take(rows * (c.channels + 1));
-    w.b.buf_a = take(rows * kWidth); w.b.buf_b = take(rows * kWidth);
+    w.b.dz_tiles = reinterpret_cast<unsigned char*>(take_bytes(9 * (size_t)w.b.tiles * bwt::tile_bytes(kWidth)));
+    w.b.dz9_tiles = reinterpret_cast<unsigned char*>(take_bytes((size_t)w.b.tiles * bwt::tile_bytes(kHalf)));
     w.b.d_pe = take(rows * kPtsChPad); w.b.dz9 = take(rows * kHalf);
     w.b.dvb = take(n * kHalf); w.b.pe_dir = take(n * 32);
     w.g_o = take(n * 3); w.g_d = take(n * 3); w.g_v = take(n * 3); w.g_dn = take(n);
@@ -507,7 +593,7 @@ int bnrf_render_backward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_i
         if (!g) continue;
         const int S = net ? Sf : Sc;
         const float *raw = net ? s.raw_f : s.raw_c, *z = net ? s.z_f : s.z_c, *sig = net ? s.sig_f : s.sig_c;
-        const float* acts = net ? s.acts_f : s.acts_c;
+        const ActPtrs& acts = net ? s.acts_f : s.acts_c;
         const bnrf_param_grads* pg = net ? grads_fine : grads_coarse;
         const unsigned grid = (unsigned)ceil_div(n, kWarps);
         if (c.channels == 3) composite_backward_kernel<3><<<grid, 32 * kWarps, 0, st>>>(raw, z, sig, s.d, g, n, S, w.b.d_raw, w.g_dn);
@@ -523,7 +609,7 @@ int bnrf_render_backward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_i
             g2.C = pg->weights[BNRF_L_VIEWS] + kWidth; g2.ldc = kWidth + kDirCh; g2.epi = GEMM_ATOMIC;
             if ((rc = launch_sgemm(ctx, true, false, g2, st))) return rc;
         }
-        pe_ray_backward_kernel<<<grid, 32 * kWarps, 0, st>>>(acts, w.b.d_pe, z, n, S, w.g_o, w.g_d);
+        pe_ray_backward_kernel<<<grid, 32 * kWarps, 0, st>>>(acts.pe_f32, w.b.d_pe, z, n, S, w.g_o, w.g_d);
         BNRF_LAUNCH_CHECK(ctx);
     }
     rays_backward_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(poses, ray_idx, P, R, H, W, K[0], K[4], K[2], K[5], remap,

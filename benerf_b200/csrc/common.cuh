@@ -34,7 +34,20 @@ struct NetParams {
     __half* tc_stream;    // single-CTA kernel (mlp_tc.cu)
     __half* tc2_stream;   // CTA-pair kernel (mlp_tc2.cu): [rank][stage], each CTA's half of the output columns
     float* tc_scale;      // [10] 2^-s per GEMM step undoing the fp16 weight pre-scale
+    // backward pass (bwd_tiles.cu): the 11 dgrad B operands as bf16 hi/lo K-major blocks, packed lazily by the first
+    // backward call after bnrf_set_weights
+    unsigned char* dg_img;
+    bool dg_dirty;
     bool ready;
+};
+
+// Activations the training-mode forward pass keeps for one network (written by mlp_tc2.cu, read by backward.cu).
+struct ActPtrs {
+    float* pe_f32;             // [rows, 64] encoded points, fp32 (encoding backward)
+    float* h9_f32;             // [rows, 128] view-layer activations, fp32 (rgb head)
+    unsigned char* pe_tiles;   // bf16 hi/lo tile matrix of width 64 (bwd_tiles.cuh)
+    unsigned char* h_tiles;    // 9 bf16 hi/lo tile matrices of width 256: h0..h7, feature; t_alloc tiles each
+    int64_t t_alloc;
 };
 
 inline int gemm_k(int step) { return step == 0 ? 64 : (step == 5 ? 320 : 256); }
@@ -144,17 +157,17 @@ size_t tc_stream_halfs();
 size_t tc2_stream_halfs();
 int pack_tc2_stream(bnrf_ctx*, int net, const float* const* table_dev, const float* scale_dev, cudaStream_t);
 int launch_mlp_tc2(bnrf_ctx*, int net, const float* o, const float* d, const float* vb, const float* z,
-                   int64_t n, int S, float* raw, float* acts /*NULL unless training*/, cudaStream_t);
+                   int64_t n, int S, float* raw, const ActPtrs* acts /*NULL unless training*/, cudaStream_t);
 
 // Tensors the forward pass keeps for the backward pass (bnrf_render_forward_train), carved from the caller's buffer.
-constexpr int kActFloatsPerRow = kPtsChPad + 9 * kWidth + kHalf;   // encoding | h0..h7 | feature | view layer
 struct SavedLayout {
     float *o, *d, *view;            // [N,3] NDC origin / direction, pre-NDC unit view direction
     float *z_c, *raw_c, *sig_c;     // [N,S_c], [N,S_c,C+1], [N,S_c] relu(raw_sigma + noise)
     float *z_f, *raw_f, *sig_f;     // fine network
-    float *acts_c, *acts_f;         // [rows * kActFloatsPerRow]
+    ActPtrs acts_c, acts_f;
     size_t bytes;
 };
 SavedLayout carve_saved(const bnrf_cfg& c, int64_t n, void* base);
+size_t dgrad_images_bytes();   // backward.cu: the 11 dgrad weight images of one network
 
 }  // namespace bnrf

@@ -50,13 +50,14 @@ __host__ __device__ inline size_t stage_offset_bytes(int i) {
 }
 __host__ __device__ inline size_t rank_stream_bytes() { return stage_offset_bytes(STAGES_PER_TILE); }
 
-// TRAIN: the epilogue / front end also write the encoded points and every hidden activation (fp32, as computed) to
-// `acts` for the backward pass: [rows,64] encoding | 8 x [rows,256] h0..h7 | [rows,256] feature | [rows,128] view layer.
+// TRAIN: the epilogue / front end also write what the backward pass reads (ActPtrs, common.cuh): every A operand
+// they build (encoded points, h0..h7, feature) also goes to a bf16 hi/lo tile matrix in global memory (bwd_tiles.cuh: the backward GEMMs consume them without conversion), plus fp32 copies of the encoding and of
+// the view layer for the two SIMT backward kernels.
 template <int C, bool TRAIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                const float* __restrict__ viewbias, const float* __restrict__ z, int64_t rows, int S, int num_pairs,
-               float* __restrict__ raw, float* __restrict__ acts, unsigned int* err_flag, unsigned long long* __restrict__ trace) {
+               float* __restrict__ raw, const ActPtrs acts, unsigned int* err_flag, unsigned long long* __restrict__ trace) {
     // trace (debug, normally NULL): per-CTA stall accounting, 16 counters of clock64 cycles --
     //   0 kernel total   1 mma: wait PE_FULL   2 mma: wait A_READY   3 mma: wait W_FULL   4 mma: loop total
     //   5 tma: wait W_EMPTY   6 epilogue(warp 8): wait ACC_FULL   7 epilogue: loop total
@@ -221,7 +222,8 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
         unsigned long long w_acc = 0;
         const long long e_t0 = clock64();
         for (int it = 0; it < my_iters; ++it) {
-            const int64_t row = tile_of(it) * TILE_M + r;
+            const int64_t tile = tile_of(it);
+            const int64_t row = tile * TILE_M + r;
             float sigma_acc = 0.0f;
             for (int t = 0; t < 10; ++t) {
                 const int b = t & 1;
@@ -277,15 +279,15 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
                                 sigma_acc = fmaf(v[j + 2], wa.z, sigma_acc); sigma_acc = fmaf(v[j + 3], wa.w, sigma_acc);
                             }
                         }
-                        if (TRAIN && row < rows) {                             // h_t (t < 8) or the feature vector (t == 8)
-                            float4* dst = reinterpret_cast<float4*>(acts + rows * kPtsChPad + (int64_t)t * rows * kWidth + row * kWidth + col0 + ch * 16);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        }
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             const uint32_t off = (kh >> 1) * KBLOCK_BYTES + sw128_offset(r, (kh & 1) * 32 + ch * 16 + j * 8);
-                            split_store8(v + 8 * j, sm + OFF_A_HI + off, sm + OFF_A_LO + off);
+                            if (TRAIN) {                                       // h_t (t < 8) or the feature vector (t == 8)
+                                unsigned char* gt = acts.h_tiles + ((size_t)t * (size_t)acts.t_alloc + (size_t)tile) * (8 * KBLOCK_BYTES) + off;
+                                split_store8_dual(v + 8 * j, sm + OFF_A_HI + off, sm + OFF_A_LO + off, gt, gt + 4 * KBLOCK_BYTES);
+                            } else {
+                                split_store8(v + 8 * j, sm + OFF_A_HI + off, sm + OFF_A_LO + off);
+                            }
                         }
                         if (tl && kh == 0) trace[148 * 16 + 128 + t * 8 + 6] = (unsigned long long)clock64();
                         tc_fence_before();
@@ -320,7 +322,7 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
                             const float x2 = fmaxf(fmaf(__uint_as_float(cur[j + 2]), inv_scale, bv.z), 0.0f);
                             const float x3 = fmaxf(fmaf(__uint_as_float(cur[j + 3]), inv_scale, bv.w), 0.0f);
                             if (TRAIN && row < rows)
-                                *reinterpret_cast<float4*>(acts + rows * (kPtsChPad + 9 * kWidth) + row * kHalf + ch * 32 + col) = make_float4(x0, x1, x2, x3);
+                                *reinterpret_cast<float4*>(acts.h9_f32 + row * kHalf + ch * 32 + col) = make_float4(x0, x1, x2, x3);
 #pragma unroll
                             for (int c = 0; c < C; ++c) {
                                 const float4 wr = __ldg(reinterpret_cast<const float4*>(p.w_rgb + c * kHalf + ch * 32 + col));
@@ -362,7 +364,8 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
         unsigned long long w_pee = 0;
         const long long f_t0 = clock64();
         for (int it = 0; it < my_iters; ++it) {
-            const int64_t row = tile_of(it) * TILE_M + r;
+            const int64_t tile = tile_of(it);
+            const int64_t row = tile * TILE_M + r;
             float enc[64];
             float x[3] = {0.f, 0.f, 0.f};
             const bool live = row < rows;
@@ -385,7 +388,7 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
                 }
             enc[63] = 0.0f;
             if (TRAIN && live) {
-                float4* dst = reinterpret_cast<float4*>(acts + row * kPtsChPad);
+                float4* dst = reinterpret_cast<float4*>(acts.pe_f32 + row * kPtsChPad);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) dst[j] = make_float4(enc[4 * j], enc[4 * j + 1], enc[4 * j + 2], enc[4 * j + 3]);
             }
@@ -393,7 +396,12 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
 #pragma unroll
             for (int c8 = 0; c8 < 8; ++c8) {
                 const uint32_t off = sw128_offset(r, c8 * 8);
-                split_store8(enc + 8 * c8, sm + OFF_PE_HI + off, sm + OFF_PE_LO + off);
+                if (TRAIN) {
+                    unsigned char* gt = acts.pe_tiles + (size_t)tile * (2 * KBLOCK_BYTES) + off;
+                    split_store8_dual(enc + 8 * c8, sm + OFF_PE_HI + off, sm + OFF_PE_LO + off, gt, gt + KBLOCK_BYTES);
+                } else {
+                    split_store8(enc + 8 * c8, sm + OFF_PE_HI + off, sm + OFF_PE_LO + off);
+                }
             }
             fence_proxy_async();
             __syncwarp();
@@ -455,7 +463,7 @@ int pack_tc2_stream(bnrf_ctx* ctx, int net, const float* const* table_dev, const
 
 template <int C, bool TRAIN>
 static int launch_one(bnrf_ctx* ctx, const tcp::TcParams& p, int clusters, const float* o, const float* d, const float* vb,
-                      const float* z, int64_t rows, int S, int pairs, float* raw, float* acts, cudaStream_t st) {
+                      const float* z, int64_t rows, int S, int pairs, float* raw, const ActPtrs& acts, cudaStream_t st) {
     using namespace tc2;
     BNRF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<C, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     mlp_tc2_kernel<C, TRAIN><<<2 * clusters, NUM_THREADS, SMEM_BYTES, st>>>(p, o, d, vb, z, rows, S, pairs, raw, acts, ctx->err_flag, ctx->trace);
@@ -464,7 +472,7 @@ static int launch_one(bnrf_ctx* ctx, const tcp::TcParams& p, int clusters, const
 }
 
 int launch_mlp_tc2(bnrf_ctx* ctx, int net, const float* o, const float* d, const float* vb, const float* z,
-                   int64_t n, int S, float* raw, float* acts, cudaStream_t st) {
+                   int64_t n, int S, float* raw, const ActPtrs* acts, cudaStream_t st) {
     using namespace tc2;
     const NetParams& np = ctx->net[net];
     TcParams p;
@@ -478,10 +486,14 @@ int launch_mlp_tc2(bnrf_ctx* ctx, int net, const float* o, const float* d, const
     const int max_clusters = ctx->sm_count / 2;
     const int clusters = pairs < max_clusters ? pairs : max_clusters;
     const bool c3 = ctx->cfg.channels == 3;
-    if (acts) return c3 ? launch_one<3, true>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, acts, st)
-                        : launch_one<1, true>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, acts, st);
-    return c3 ? launch_one<3, false>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, acts, st)
-              : launch_one<1, false>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, acts, st);
+    if (acts) {
+        if (acts->t_alloc < 2 * (int64_t)pairs) return fail(ctx, BNRF_ERR_STATE, "mlp: activation tile matrices too small");
+        return c3 ? launch_one<3, true>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, *acts, st)
+                  : launch_one<1, true>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, *acts, st);
+    }
+    const ActPtrs none{};
+    return c3 ? launch_one<3, false>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, none, st)
+              : launch_one<1, false>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, none, st);
 }
 
 }  // namespace bnrf

@@ -145,6 +145,22 @@ __device__ __forceinline__ void split_store8(const float* v, unsigned char* hi_d
     *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// same, and the values also go to a tile matrix in global memory as bf16 hi/lo (training mode, bwd_tiles.cuh: the
+// backward GEMMs multiply them with bf16 gradients, and kind::f16 wants one format for both operands)
+__device__ __forceinline__ void split_store8_dual(const float* v, unsigned char* hi_dst, unsigned char* lo_dst,
+                                                  unsigned char* ghi, unsigned char* glo) {
+    split_store8(v, hi_dst, lo_dst);
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+        const float b0 = __uint_as_float(h[i] << 16), b1 = __uint_as_float(h[i] & 0xffff0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l[i]) : "f"(v[2 * i + 1] - b1), "f"(v[2 * i] - b0));
+    }
+    *reinterpret_cast<uint4*>(ghi) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(glo) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // ---------------------------------------------------------------------------- CTA-pair (cta_group::2) helpers
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 // shared::cluster address of the same shared-memory offset in CTA `rank` of this cluster

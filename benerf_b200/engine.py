@@ -202,6 +202,26 @@ class Engine:
             _ptr(mask), mask.stride(0) if mask is not None else 0, _ptr(r_row), 1, _ptr(r_col), _stream()), "bnrf_debug_sgemm")
         return out
 
+    def debug_tile_dgrad(self, A, B, mask=None, r_row=None, r_col=None, out=None):
+        """out[rows,N] = A[rows,K] @ B[N,K].T (+ outer(r_row, r_col)) (* (mask > 0)) through bwd_tiles.cu (tests)."""
+        rows, K = A.shape
+        N = B.shape[0]
+        acc = out is not None
+        if out is None:
+            out = torch.zeros(rows, N, device=self.device, dtype=torch.float32)
+        self._check(self.lib.bnrf_debug_tile_dgrad(self._ctx, rows, K, N, _ptr(A), _ptr(B), _ptr(mask), _ptr(r_row), _ptr(r_col),
+                                                   int(acc), _ptr(out), _stream()), "bnrf_debug_tile_dgrad")
+        return out
+
+    def debug_tile_wgrad(self, dz, h, dW, col0=0, n_valid=None, dB=None, wrow=None, dWv=None, dBv=None):
+        """dW[:, col0:col0+n_valid] += dz.T @ h[:, :n_valid]; dB += dz.sum(0); dWv += wrow @ h; dBv += wrow.sum() (tests)."""
+        rows, M = dz.shape
+        N = h.shape[1]
+        self._check(self.lib.bnrf_debug_tile_wgrad(self._ctx, rows, M, N, _ptr(dz), _ptr(h), _ptr(wrow), _ptr(dW), dW.stride(0), int(col0),
+                                                   int(N if n_valid is None else n_valid), _ptr(dB), _ptr(dWv), _ptr(dBv), _stream()),
+                    "bnrf_debug_tile_wgrad")
+        return dW
+
     # -- stage operators ------------------------------------------------------------------
     def op_rays(self, poses, ray_idx, H, W, K, remap=None):
         n = poses.shape[0] * ray_idx.numel()

@@ -248,6 +248,17 @@ int bnrf_debug_sgemm(bnrf_ctx* ctx, int ta, int tb, int64_t M, int N, int64_t K,
  * stall accounting of its warp roles there (see mlp_tc.cu); NULL switches it off. */
 int bnrf_debug_mlp_trace(bnrf_ctx* ctx, unsigned long long* counters);
 
+/* Debug / tests: the two tensor-core kernels of the backward pass (csrc/bwd_tiles.cu) on caller-provided fp32 device
+ * matrices; the conversion to the library's 16-bit tile matrices happens inside the call.
+ *   dgrad: out[rows, N] = A[rows, K] . B[N, K]^T (+ r_row (x) r_col) (* (mask[rows, 256] > 0));  K in {128, 256};
+ *          N = 256 (mask / rank-1 term optional) or N = 64 (fp32 store, or += when accumulate != 0)
+ *   wgrad: dW[m, col0 + n] += sum_rows dz[rows, M]^T . h[rows, N] for n < n_valid; dB[M] += column sums of dz;
+ *          with wrow: dWv[N] += sum_rows wrow[row] * h[row, :], dBv[0] += sum wrow.  M in {128, 256}, N in {64, 256}. */
+int bnrf_debug_tile_dgrad(bnrf_ctx* ctx, int64_t rows, int K, int N, const float* A, const float* B, const float* mask,
+                          const float* r_row, const float* r_col, int accumulate, float* out, void* stream);
+int bnrf_debug_tile_wgrad(bnrf_ctx* ctx, int64_t rows, int M, int N, const float* dz, const float* h, const float* wrow,
+                          float* dW, int ldw, int col0, int n_valid, float* dB, float* dWv, float* dBv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

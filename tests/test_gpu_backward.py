@@ -62,6 +62,53 @@ def test_sgemm_matches_torch(eng, ta, tb, M, N, K):
     assert rel_err(got, (want + torch.outer(r_row, r_col).double()) * (mask > 0)) < tol
 
 
+@pytest.mark.parametrize("rows", [128, 1000, 4096 + 64, 150 * 128])
+@pytest.mark.parametrize("K,N", [(256, 256), (128, 256), (256, 64)])
+def test_tile_dgrad_matches_torch(rows, K, N):
+    """bwd_tiles.cu dgrad on tile matrices: bf16 hi/lo operands, mask from activation tiles, rank-1 term."""
+    from benerf_b200.engine import Engine
+    e = Engine()
+    g = torch.Generator().manual_seed(rows + K + N)
+    A = (torch.randn(rows, K, generator=g) * torch.logspace(-6, 0, rows).unsqueeze(1)).to(DEV)     # gradients span many decades
+    B = (torch.randn(N, K, generator=g) * 0.1).to(DEV)
+    want = A.double() @ B.double().t()
+    if N == 256:
+        assert rel_err(e.debug_tile_dgrad(A, B), want) < 3e-5
+        mask = torch.relu(torch.randn(rows, 256, generator=g)).to(DEV)
+        r_row, r_col = (torch.randn(rows, generator=g) * 1e-3).to(DEV), torch.randn(256, generator=g).to(DEV)
+        got = e.debug_tile_dgrad(A, B, mask=mask, r_row=r_row, r_col=r_col)
+        assert rel_err(got, (want + torch.outer(r_row, r_col).double()) * (mask > 0)) < 3e-5
+    else:
+        got = e.debug_tile_dgrad(A, B)
+        assert rel_err(got, want) < 3e-5
+        got = e.debug_tile_dgrad(A, B, out=torch.ones(rows, N, device=DEV))
+        assert rel_err(got, want + 1.0) < 3e-5
+
+
+@pytest.mark.parametrize("rows", [128, 1000, 5000, 40000])
+@pytest.mark.parametrize("M,N", [(256, 256), (128, 256), (256, 64)])
+def test_tile_wgrad_matches_torch(rows, M, N):
+    """bwd_tiles.cu wgrad: contraction over the rows of two tile matrices (MN-major bf16 operands), split over
+    CTAs with red.global; bias gradient and the weighted column sum of alpha_linear ride along."""
+    from benerf_b200.engine import Engine
+    e = Engine()
+    g = torch.Generator().manual_seed(rows + M + N)
+    dz = (torch.randn(rows, M, generator=g) * torch.logspace(-5, 0, rows).unsqueeze(1)).to(DEV)
+    h = torch.relu(torch.randn(rows, N, generator=g)).to(DEV)
+    wrow = (torch.randn(rows, generator=g) * 1e-2).to(DEV)
+    ldw, col0, n_valid = (N + 63, 63, N) if N == 256 else (63, 0, 63)
+    dW = torch.ones(M, ldw, device=DEV)
+    dB, dWv, dBv = torch.ones(M, device=DEV), torch.ones(N, device=DEV), torch.ones(1, device=DEV)
+    e.debug_tile_wgrad(dz, h, dW, col0=col0, n_valid=n_valid, dB=dB, wrow=wrow, dWv=dWv, dBv=dBv)
+    want = torch.ones(M, ldw, dtype=torch.float64)
+    want[:, col0:col0 + n_valid] += (dz.double().t() @ h.double()[:, :n_valid]).cpu()
+    assert rel_err(dW.cpu() - 1.0, want - 1.0) < 3e-5
+    assert float((dW.cpu() - want).abs().max()) < 1e-4 * float(want.abs().max())
+    assert rel_err(dB - 1.0, dz.double().sum(0)) < 1e-5
+    assert rel_err(dWv - 1.0, wrow.double() @ h.double()) < 1e-5
+    assert abs(float(dBv) - 1.0 - float(wrow.double().sum())) < 1e-4
+
+
 @pytest.mark.parametrize("traj", ["spline", "linear"])
 @pytest.mark.parametrize("with_transform", [False, True])
 def test_spline_backward_matches_autograd(eng, traj, with_transform):
