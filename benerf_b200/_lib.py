@@ -30,6 +30,10 @@ class Outputs(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0", "sigma", "depth_map", "z_vals")]
 
 
+class AdamGroup(C.Structure):
+    _fields_ = [("begin", C.c_int64), ("end", C.c_int64), ("lr", C.c_float), ("active", C.c_int32)]
+
+
 class ParamGrads(C.Structure):
     """bnrf_param_grads: 12 weight + 12 bias gradient pointers (PyTorch layouts, accumulated into)."""
     _fields_ = [("weights", C.c_void_p * 12), ("biases", C.c_void_p * 12)]
@@ -63,6 +67,7 @@ PROTOTYPES = {
     "bnrf_blur_mean_backward": (_I, [_P, _I, _L, _I, _P, _P]),
     "bnrf_event_logdiff_backward": (_I, [_P, _P, _I, _L, _I, _I, _P, _P]),
     "bnrf_accumulate_events": (_I, [_P, _P, _P, _L, _I, _I, _P, _P]),
+    "bnrf_adam_step": (_I, [_P, _P, _P, _P, _L, C.POINTER(AdamGroup), _I, _L, C.c_float, C.c_float, C.c_float, C.c_float, _I, _P]),
     "bnrf_profile": (_I, [_P, _I]),
     "bnrf_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "bnrf_debug_mlp_trace": (_I, [_P, _P]),

@@ -282,12 +282,7 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             const uint32_t off = (kh >> 1) * KBLOCK_BYTES + sw128_offset(r, (kh & 1) * 32 + ch * 16 + j * 8);
-                            if (TRAIN) {                                       // h_t (t < 8) or the feature vector (t == 8)
-                                unsigned char* gt = acts.h_tiles + ((size_t)t * (size_t)acts.t_alloc + (size_t)tile) * (8 * KBLOCK_BYTES) + off;
-                                split_store8_dual(v + 8 * j, sm + OFF_A_HI + off, sm + OFF_A_LO + off, gt, gt + 4 * KBLOCK_BYTES);
-                            } else {
-                                split_store8(v + 8 * j, sm + OFF_A_HI + off, sm + OFF_A_LO + off);
-                            }
+                            split_store8(v + 8 * j, sm + OFF_A_HI + off, sm + OFF_A_LO + off);
                         }
                         if (tl && kh == 0) trace[148 * 16 + 128 + t * 8 + 6] = (unsigned long long)clock64();
                         tc_fence_before();
@@ -295,6 +290,14 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(lbar(BAR_A_READY + kh));   // one arrival per warp, on the leader's barrier
                         if (tl && (kh & 1) == 0) trace[148 * 16 + 128 + t * 8 + 1 + (kh >> 1)] = (unsigned long long)clock64();
+                        if (TRAIN) {                                           // h_t (t < 8) or the feature vector (t == 8), after the
+#pragma unroll                                                                 // hand-off: the spill is off the layer-to-layer critical path
+                            for (int j = 0; j < 2; ++j) {
+                                const uint32_t off = (kh >> 1) * KBLOCK_BYTES + sw128_offset(r, (kh & 1) * 32 + ch * 16 + j * 8);
+                                unsigned char* gt = acts.h_tiles + ((size_t)t * (size_t)acts.t_alloc + (size_t)tile) * (8 * KBLOCK_BYTES) + off;
+                                split_store8_bf16_global(v + 8 * j, gt, gt + 4 * KBLOCK_BYTES);
+                            }
+                        }
                         if (kh < 7) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) bq[j] = bn[j];
@@ -396,16 +399,18 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
 #pragma unroll
             for (int c8 = 0; c8 < 8; ++c8) {
                 const uint32_t off = sw128_offset(r, c8 * 8);
-                if (TRAIN) {
-                    unsigned char* gt = acts.pe_tiles + (size_t)tile * (2 * KBLOCK_BYTES) + off;
-                    split_store8_dual(enc + 8 * c8, sm + OFF_PE_HI + off, sm + OFF_PE_LO + off, gt, gt + KBLOCK_BYTES);
-                } else {
-                    split_store8(enc + 8 * c8, sm + OFF_PE_HI + off, sm + OFF_PE_LO + off);
-                }
+                split_store8(enc + 8 * c8, sm + OFF_PE_HI + off, sm + OFF_PE_LO + off);
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(lbar(BAR_PE_FULL));
+            if (TRAIN) {
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    unsigned char* gt = acts.pe_tiles + (size_t)tile * (2 * KBLOCK_BYTES) + sw128_offset(r, c8 * 8);
+                    split_store8_bf16_global(enc + 8 * c8, gt, gt + KBLOCK_BYTES);
+                }
+            }
         }
         if (trace && threadIdx.x == 128) {
             trace[blockIdx.x * 16 + 8] = w_pee; trace[blockIdx.x * 16 + 9] = (unsigned long long)(clock64() - f_t0);

@@ -145,11 +145,9 @@ __device__ __forceinline__ void split_store8(const float* v, unsigned char* hi_d
     *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// same, and the values also go to a tile matrix in global memory as bf16 hi/lo (training mode, bwd_tiles.cuh: the
-// backward GEMMs multiply them with bf16 gradients, and kind::f16 wants one format for both operands)
-__device__ __forceinline__ void split_store8_dual(const float* v, unsigned char* hi_dst, unsigned char* lo_dst,
-                                                  unsigned char* ghi, unsigned char* glo) {
-    split_store8(v, hi_dst, lo_dst);
+// 8 values -> bf16 hi/lo words of a tile matrix in global memory (training mode, bwd_tiles.cuh: the backward GEMMs
+// multiply them with bf16 gradients, and kind::f16 wants one format for both operands)
+__device__ __forceinline__ void split_store8_bf16_global(const float* v, unsigned char* ghi, unsigned char* glo) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

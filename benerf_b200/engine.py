@@ -86,6 +86,10 @@ class Engine:
             self.set_weights(net, module)
             self._weights_version[net] = version
 
+    def invalidate_weights(self):
+        """Force a repack at the next render: for parameter updates torch cannot see (bnrf_adam_step writes in place)."""
+        self._weights_version = [None, None]
+
     def set_sample_grid(self, t_vals):
         t = torch.as_tensor(t_vals, dtype=torch.float32).cpu().contiguous()
         arr = (C.c_float * t.numel())(*t.tolist())
@@ -260,6 +264,16 @@ class Engine:
 
 
 # -- image formation: context-free entry points ---------------------------------------------
+def adam_step(params, grads, exp_avg, exp_avg_sq, groups, step, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, zero_grads=True):
+    """bnrf_adam_step over flat fp32 device buffers; groups: [(begin, end, lr, active), ...] (see benerf_b200.h)."""
+    lib = _lib.load()
+    n = params.numel()
+    arr = (_lib.AdamGroup * len(groups))(*[_lib.AdamGroup(int(b), int(e), float(lr), int(bool(a))) for b, e, lr, a in groups])
+    _rc(lib.bnrf_adam_step(_ptr(params, name="params"), _ptr(grads, name="grads"), _ptr(exp_avg, name="exp_avg"),
+                           _ptr(exp_avg_sq, name="exp_avg_sq"), n, arr, len(groups), int(step), float(betas[0]), float(betas[1]),
+                           float(eps), float(grad_scale), int(bool(zero_grads)), _stream()), "bnrf_adam_step")
+
+
 def _rc(rc, what):
     if rc != _lib.OK:
         raise BnrfError(f"{what} failed ({rc})")

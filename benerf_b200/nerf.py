@@ -35,7 +35,7 @@ class _RenderFn(torch.autograd.Function):
         ret = eng.render(poses, ray_idx, H, W, K, remap=remap, rng=rng, seed=seed, offset=offset, saved=saved)
         keys = [k for k in _OUT_KEYS if k in ret]
         ctx.call, ctx.keys, ctx.saved_buf, ctx.poses = call, keys, saved, poses
-        ctx.param_shapes = [p.shape for p in params]
+        ctx.params = params
         outs = tuple(ret[k] for k in keys)
         ctx.mark_non_differentiable(*[o for k, o in zip(keys, outs) if k not in ("rgb_map", "rgb0")])
         return outs
@@ -44,18 +44,26 @@ class _RenderFn(torch.autograd.Function):
     def backward(ctx, *gouts):
         eng, ray_idx, H, W, K, remap, rng, seed, offset, n_fine = ctx.call
         g = {k: (go.contiguous() if go is not None else None) for k, go in zip(ctx.keys, gouts)}
-        flat = torch.zeros(sum(s.numel() for s in ctx.param_shapes), device=eng.device, dtype=torch.float32)
-        grads, off = [], 0
-        for s in ctx.param_shapes:
-            grads.append(flat[off:off + s.numel()].view(s))
-            off += s.numel()
+        # bnrf_render_backward ACCUMULATES into the gradient tables.  When every parameter already owns a gradient buffer
+        # (benerf_b200.parallel.FlatGrads: p.grad are views of one flat fp32 buffer) the kernels add straight into p.grad
+        # and autograd is told there is nothing left to accumulate: no temporaries, no 48 add kernels per render.
+        direct = all(p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 and p.grad.device == eng.device
+                     for p in ctx.params)
+        if direct:
+            grads = [p.grad for p in ctx.params]
+        else:
+            flat = torch.zeros(sum(p.numel() for p in ctx.params), device=eng.device, dtype=torch.float32)
+            grads, off = [], 0
+            for p in ctx.params:
+                grads.append(flat[off:off + p.numel()].view(p.shape))
+                off += p.numel()
         names = [n + sfx for n in LINEAR_NAMES for sfx in (".weight", ".bias")]
         gc = dict(zip(names, grads[:24]))
         gf = dict(zip(names, grads[24:48])) if n_fine else None
         d_poses = torch.zeros_like(ctx.poses)
         eng.render_backward(ctx.poses, ray_idx, H, W, K, ctx.saved_buf, g.get("rgb_map"), g.get("rgb0"), gc, gf, d_poses, remap=remap)
         ctx.saved_buf = None
-        return (None, d_poses) + tuple(grads)
+        return (None, d_poses) + (tuple(None for _ in grads) if direct else tuple(grads))
 
 
 class Model:

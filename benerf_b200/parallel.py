@@ -68,6 +68,12 @@ class FlatGrads:
     def zero(self):
         self.flat.zero_()
 
+    def all_reduce_sum(self):
+        """Sum over ranks on the current stream (the fused optimiser tail applies the 1 / world factor itself)."""
+        if world() > 1:
+            dist.all_reduce(self.flat)
+        return self.flat
+
     def all_reduce_mean(self):
         """Sum over ranks on the current stream, divided by the world size; returns the async work handle's result."""
         if world() > 1:

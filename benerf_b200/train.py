@@ -7,7 +7,8 @@ ONE gradient all-reduce -> the reference's Adam steps and exponential learning-r
 import torch
 
 from . import image_formation as IF
-from .parallel import FlatGrads
+from .engine import adam_step
+from .parallel import FlatGrads, world
 
 
 class Trainer:
@@ -18,6 +19,17 @@ class Trainer:
         g = self.graph
         params = list(g.nerf.parameters()) + (list(g.nerf_fine.parameters()) if hasattr(g, "nerf_fine") else [])
         params += [g.evt_knot_pose_se3.params.weight, g.transform.params.weight]
+        self.fused = bool(getattr(args, "fused_optimizer", True))
+        if self.fused:
+            # parameters, like their gradients, become views of ONE flat buffer (same order), so that the optimiser tail is a
+            # single launch (bnrf_adam_step); state_dict / load_state_dict / init_nerf keep working on the views
+            self.flat_params = torch.cat([p.data.reshape(-1) for p in params])
+            off, n_nerf = 0, sum(p.numel() for p in params[:-2])
+            for p in params:
+                p.data = self.flat_params[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.flat_params), torch.zeros_like(self.flat_params)
+            self.group_ranges = [(0, n_nerf), (n_nerf, n_nerf + 24), (n_nerf + 24, n_nerf + 30)]      # nerf(s), knots [4,6], transform [1,6]
         self.flat = FlatGrads(params)
         self.base_lr = [[grp["lr"] for grp in o.param_groups] for o in self.optims]
         self.global_step = 0
@@ -35,19 +47,29 @@ class Trainer:
         ret_rgb = g.render(self.global_step, poses_rgb, idx_rgb, H, W, K, a, enable_crf=True, sensor_type="rgb", remap=None, training=True)
         mark("forward")
         loss, parts = IF.training_loss(ret_evt, ret_rgb, events_accu, idx_evt, blur_target, a)
-        self.flat.zero()
+        if not self.fused:
+            self.flat.zero()
         mark("loss")
         loss.backward()
         mark("backward")
-        self.flat.all_reduce_mean()                                      # the single exchange of the step
-        mark("all_reduce")
         opt_nerf, opt_pose, opt_trans = self.optims[0], self.optims[1], self.optims[2]
-        if getattr(a, "optimize_nerf", True):
-            opt_nerf.step()
-        if getattr(a, "optimize_pose", True):
-            opt_pose.step()
-        if getattr(a, "optimize_trans", False):
-            opt_trans.step()
+        flags = [getattr(a, "optimize_nerf", True), getattr(a, "optimize_pose", True), getattr(a, "optimize_trans", False)]
+        if self.fused:
+            self.flat.all_reduce_sum()                                   # the single exchange of the step
+            mark("all_reduce")
+            groups = [(b, e, o.param_groups[0]["lr"], f) for (b, e), o, f in zip(self.group_ranges, self.optims[:3], flags)]
+            adam_step(self.flat_params, self.flat.flat, self.exp_avg, self.exp_avg_sq, groups, self.global_step + 1,
+                      grad_scale=1.0 / world(), zero_grads=True)         # averages, steps all three optimisers, clears the gradients
+            g.engine(a).invalidate_weights()                             # in-place update torch's version counters do not see
+        else:
+            self.flat.all_reduce_mean()
+            mark("all_reduce")
+            if flags[0]:
+                opt_nerf.step()
+            if flags[1]:
+                opt_pose.step()
+            if flags[2]:
+                opt_trans.step()
         # lr = lr0 * rate ** (step / (lrate_decay * 1000)) with one rate per optimiser, applied after the step (train.py:355-394)
         decay_steps = getattr(a, "lrate_decay", 200) * 1000
         rates = [getattr(a, k, d) for k, d in (("decay_rate", 0.1), ("decay_rate_pose", 0.01), ("decay_rate_transform", 0.01),

@@ -221,6 +221,24 @@ int bnrf_accumulate_events(const int32_t* x, const int32_t* y, const float* pol,
                            int H, int W, double* out, void* stream);
 
 /* -------------------------------------------------------------------------------------- */
+/* f3: fused optimiser tail -- train.py:343-394 (optimizer.step() x3, learning-rate decay, zero_grad),
+ * model/optimize.py:36-55 (torch.optim.Adam, default betas / eps, no weight decay) */
+
+typedef struct {
+    int64_t begin, end;   /* element range [begin, end) of the flat buffers that forms one optimiser (param group) */
+    float lr;             /* this step's learning rate of the group (the caller applies the exponential decay) */
+    int32_t active;       /* 0: the reference would not call this optimiser's step() (e.g. optimize_trans = False): skipped */
+} bnrf_adam_group;
+
+/* One Adam step over flat fp32 device buffers of n elements: grads are first multiplied by grad_scale (1 / world size
+ * after the gradient all-reduce), moments and parameters are updated in place with torch.optim.Adam's arithmetic
+ * (step = 1-based count of this call, bias corrections from it), and grads are cleared when zero_grads != 0.
+ * Elements outside every group are left untouched (their gradients are still cleared). */
+int bnrf_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   const bnrf_adam_group* groups, int n_groups, int64_t step, float beta1, float beta2, float eps,
+                   float grad_scale, int zero_grads, void* stream);
+
+/* -------------------------------------------------------------------------------------- */
 /* measurement hooks (bench.py): CUDA-event timing of the dominant kernel on its own stream */
 
 /* enable != 0: every MLP kernel launched through this context is bracketed by a cudaEvent pair

@@ -220,3 +220,42 @@ def test_training_iteration_gradients_match_reference(name):
         report[f"samples_{lvl}"] = rel_err(samples, gold[f"grad_samples_{lvl}"])
     print(f"{name}: loss {float(loss):.6f} (ref {float(gold['loss']):.6f}) gradient errors vs reference {report}")
     assert max(report.values()) < 1e-2, report
+
+
+def test_trainer_fused_tail_matches_torch_adam_tail():
+    """benerf_b200.train.Trainer: three optimisation steps with the fused tail (flat parameters, bnrf_adam_step, gradients
+    accumulated straight into the flat buffer) against the reference's tail (three torch.optim.Adam, train.py:343-394) from
+    the same initial state and the same Philox draws; the loss of the fixed batch must also go down."""
+    from benerf_b200 import optimize, run_nerf_helpers
+    from benerf_b200.train import Trainer
+    case = CASES["e2nerf_syn"]
+    runs = {}
+    for fused in (True, False):
+        args = case_args(case)
+        args.fused_optimizer = fused
+        args.lrate, args.pose_lrate, args.transform_lrate, args.rgb_crf_lrate, args.event_crf_lrate = 5e-4, 1e-3, 1e-6, 5e-4, 5e-4
+        args.optimize_nerf, args.optimize_pose, args.optimize_trans = True, True, True
+        args.event_coeff_syn, args.rgb_coeff = 0.1, 1.0
+        torch.manual_seed(0)
+        model = optimize.Model(args)
+        graph = model.build_network(args)
+        run_nerf_helpers.init_nerf(graph.nerf)
+        run_nerf_helpers.init_nerf(graph.nerf_fine)
+        graph.to(DEV)
+        tr = Trainer(model, args)
+        g = torch.Generator().manual_seed(5)
+        idx_evt = torch.randint(0, case.H * case.W, (96,), generator=g).to(DEV)
+        idx_rgb = torch.randint(0, case.H * case.W, (16,), generator=g).to(DEV)
+        blur_t = torch.rand(16, case.channels, generator=g).to(DEV)
+        accu = torch.randint(-3, 4, (case.H, case.W), generator=g).double().to(DEV)
+        losses = []
+        for _ in range(3):
+            loss, _ = tr.step(accu, idx_evt, idx_rgb, blur_t, torch.tensor(case.window), torch.tensor(case.exposure), case.H, case.W, case.K, case.K)
+            losses.append(float(loss))
+        runs[fused] = (losses, torch.cat([p.detach().reshape(-1) for p in graph.parameters()]).cpu())
+    (lf, pf), (lt, pt) = runs[True], runs[False]
+    print("losses fused", lf, "torch", lt)
+    assert lf[-1] < lf[0]
+    for a, b in zip(lf, lt):
+        assert abs(a - b) <= 2e-3 * abs(b)           # split atomics order + ReLU-mask flips (see the module docstring)
+    assert float((pf - pt).abs().max()) < 2e-3       # three Adam steps of lr <= 1e-3 each move a parameter by <= 3e-3

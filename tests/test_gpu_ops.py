@@ -151,3 +151,32 @@ def test_mlp_tail_tile_and_odd_sample_count():
         eng.set_weights(0, to_dev(inp["coarse"]))
         raw = eng.op_mlp(0, o.to(DEV), d.to(DEV), v.to(DEV), z.to(DEV))
         assert max_abs(raw, want) < tol, mode
+
+
+def test_fused_adam_matches_torch_adam():
+    """bnrf_adam_step (one launch over flat buffers, three groups, gradient averaging + zeroing) against torch.optim.Adam
+    stepping the same three parameter sets with the reference's per-optimiser learning rates (model/optimize.py:36-55)."""
+    from benerf_b200.engine import adam_step
+    g = torch.Generator().manual_seed(11)
+    sizes, lrs, active = [100_003, 24, 6], [5e-4, 1e-3, 1e-6], [True, True, False]
+    ref = [torch.nn.Parameter(torch.randn(n, generator=g).to(DEV)) for n in sizes]
+    opts = [torch.optim.Adam([p], lr=lr) for p, lr in zip(ref, lrs)]
+    flat = torch.cat([p.detach().clone() for p in ref])
+    m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+    bounds = [0, sizes[0], sizes[0] + sizes[1], sum(sizes)]
+    world = 4
+    for step in range(1, 6):
+        grads = torch.randn(sum(sizes), generator=g).to(DEV) * 10.0 ** torch.randint(-6, 1, (1,), generator=g).item()
+        lr_now = [lr * 0.1 ** (step / 1000) for lr in lrs]
+        off = 0
+        for p, o, lr, a in zip(ref, opts, lr_now, active):
+            p.grad = (grads[off:off + p.numel()] / world).clone()
+            off += p.numel()
+            o.param_groups[0]["lr"] = lr
+            if a:
+                o.step()
+        gbuf = grads.clone()
+        adam_step(flat, gbuf, m, v, [(bounds[i], bounds[i + 1], lr_now[i], active[i]) for i in range(3)], step, grad_scale=1.0 / world)
+        assert float(gbuf.abs().max()) == 0.0
+        want = torch.cat([p.detach() for p in ref])
+        assert float((flat - want).abs().max()) <= 2e-7 * float(want.abs().max()) + 1e-9, step
