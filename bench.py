@@ -216,6 +216,7 @@ def bench_train_step(opts, dev, world, rank, steps=5, warmup=3):
     args.dataset, args.event_threshold, args.seed = "E2NeRF_Synthetic", 0.2, 1
     args.lrate, args.pose_lrate, args.transform_lrate, args.rgb_crf_lrate, args.event_crf_lrate = 5e-4, 1e-3, 1e-6, 5e-4, 5e-4
     args.optimize_nerf, args.optimize_pose, args.optimize_trans = True, True, False
+    args.fused_optimizer = os.environ.get("BNRF_FUSED_TAIL", "1") != "0"
     torch.manual_seed(0)
     model = optimize.Model(args)
     graph = model.build_network(args)

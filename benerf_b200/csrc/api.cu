@@ -17,17 +17,22 @@ int fail(bnrf_ctx* ctx, int code, const char* fmt, ...) {
     return code;
 }
 
-// dst[(k_dst + k) * N + n] = W[n * in_f + k_src + k]   (PyTorch (out,in) -> k-major)
-__global__ void pack_transpose_kernel(const float* __restrict__ W, int out_f, int in_f, int k_src, int k_dst, int k_count,
-                                      int N, float* __restrict__ dst) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= k_count * out_f) return;
-    const int k = idx / out_f, n = idx % out_f;
-    dst[(size_t)(k_dst + k) * N + n] = W[(size_t)n * in_f + k_src + k];
-}
-__global__ void copy_kernel(const float* __restrict__ src, int n, float* __restrict__ dst) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = src[i];
+// One launch repacks every tensor of a network (bnrf_set_weights runs after every optimiser step): a table of segments,
+// blockIdx.y = segment.  Transposes (in_f > 0): dst[(k_dst + k) * N + n] = src[n * in_f + k_src + k] for k < k_count,
+// n < out_f (PyTorch (out,in) -> k-major); plain copies (in_f == 0): dst[i] = src[i] for i < k_count.
+struct PackSeg { const float* src; float* dst; int out_f, in_f, k_src, k_dst, k_count, N; };
+struct PackTable { PackSeg seg[28]; int n; };
+__global__ void pack_all_kernel(const __grid_constant__ PackTable t) {
+    const PackSeg& s = t.seg[blockIdx.y];
+    const int total = s.in_f ? s.k_count * s.out_f : s.k_count;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        if (s.in_f) {
+            const int k = idx / s.out_f, n = idx % s.out_f;
+            s.dst[(size_t)(s.k_dst + k) * s.N + n] = s.src[(size_t)n * s.in_f + s.k_src + k];
+        } else {
+            s.dst[idx] = s.src[idx];
+        }
+    }
 }
 
 int pack_tc_stream(bnrf_ctx*, int net, cudaStream_t);   // mlp_tc.cu
@@ -37,12 +42,20 @@ int alloc_net(bnrf_ctx* ctx, int n) {
     memset(&np, 0, sizeof(np));
     for (int s = 0; s < 10; ++s) {
         BNRF_CUDA(ctx, cudaMalloc(&np.wt[s], (size_t)gemm_k(s) * gemm_n(s) * sizeof(float)));
+        BNRF_CUDA(ctx, cudaMemset(np.wt[s], 0, (size_t)gemm_k(s) * gemm_n(s) * sizeof(float)));   // padding rows stay zero for good
         BNRF_CUDA(ctx, cudaMalloc(&np.bias[s], gemm_n(s) * sizeof(float)));
     }
+    BNRF_CUDA(ctx, cudaMalloc(&np.wt_table, 10 * sizeof(float*)));
+    BNRF_CUDA(ctx, cudaMemcpy(np.wt_table, np.wt, 10 * sizeof(float*), cudaMemcpyHostToDevice));
+    BNRF_CUDA(ctx, cudaMalloc(&np.absmax, 16 * sizeof(unsigned int)));
+    BNRF_CUDA(ctx, cudaMemset(np.absmax, 0, 16 * sizeof(unsigned int)));
+    BNRF_CUDA(ctx, cudaMalloc(&np.scale, 16 * sizeof(float)));
     BNRF_CUDA(ctx, cudaMalloc(&np.w_alpha, kWidth * sizeof(float)));
     BNRF_CUDA(ctx, cudaMalloc(&np.b_alpha, sizeof(float)));
     BNRF_CUDA(ctx, cudaMalloc(&np.w_rgb, 3 * kHalf * sizeof(float)));
     BNRF_CUDA(ctx, cudaMalloc(&np.b_rgb, 3 * sizeof(float)));
+    BNRF_CUDA(ctx, cudaMemset(np.w_rgb, 0, 3 * kHalf * sizeof(float)));                               // rows >= C stay zero
+    BNRF_CUDA(ctx, cudaMemset(np.b_rgb, 0, 3 * sizeof(float)));
     BNRF_CUDA(ctx, cudaMalloc(&np.w_dir, kDirCh * kHalf * sizeof(float)));
     BNRF_CUDA(ctx, cudaMalloc(&np.tc_stream, tc_stream_halfs() * sizeof(__half)));
     BNRF_CUDA(ctx, cudaMalloc(&np.tc2_stream, tc2_stream_halfs() * sizeof(__half)));
@@ -56,20 +69,19 @@ void free_net(bnrf_ctx* ctx, int n) {
     for (int s = 0; s < 10; ++s) { cudaFree(np.wt[s]); cudaFree(np.bias[s]); }
     cudaFree(np.w_alpha); cudaFree(np.b_alpha); cudaFree(np.w_rgb); cudaFree(np.b_rgb); cudaFree(np.w_dir);
     cudaFree(np.tc_stream); cudaFree(np.tc2_stream); cudaFree(np.tc_scale); cudaFree(np.dg_img);
+    cudaFree(np.wt_table); cudaFree(np.absmax); cudaFree(np.scale);
     memset(&np, 0, sizeof(np));
 }
 
 int pack_weights(bnrf_ctx* ctx, int n, const float* const* w, const float* const* b, cudaStream_t st) {
     NetParams& np = ctx->net[n];
     const int C = ctx->cfg.channels;
+    PackTable t{};
     auto tr = [&](const float* W, int out_f, int in_f, int k_src, int k_dst, int k_count, int N, float* dst) {
-        const int total = k_count * out_f;
-        pack_transpose_kernel<<<(total + 255) / 256, 256, 0, st>>>(W, out_f, in_f, k_src, k_dst, k_count, N, dst);
+        t.seg[t.n++] = PackSeg{W, dst, out_f, in_f, k_src, k_dst, k_count, N};
     };
-    auto cp = [&](const float* src, int cnt, float* dst) { copy_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(src, cnt, dst); };
+    auto cp = [&](const float* src, int cnt, float* dst) { t.seg[t.n++] = PackSeg{src, dst, 0, 0, 0, 0, cnt, 0}; };
     // GEMM step s <- reference linear: 0-7 pts_linears, 8 feature_linear, 9 views_linears.0 (feature block)
-    for (int s = 0; s < 10; ++s)
-        BNRF_CUDA(ctx, cudaMemsetAsync(np.wt[s], 0, (size_t)gemm_k(s) * gemm_n(s) * sizeof(float), st));
     tr(w[BNRF_L_PTS0], kWidth, kPtsCh, 0, 0, kPtsCh, kWidth, np.wt[0]);
     for (int l = 1; l < 8; ++l) {
         if (l == 5) {   // cat([input_pts, h]) -> [pe64 | h256]  (model/nerf.py:98)
@@ -87,10 +99,9 @@ int pack_weights(bnrf_ctx* ctx, int n, const float* const* w, const float* const
     cp(b[BNRF_L_VIEWS], kHalf, np.bias[9]);
     cp(w[BNRF_L_ALPHA], kWidth, np.w_alpha);
     cp(b[BNRF_L_ALPHA], 1, np.b_alpha);
-    BNRF_CUDA(ctx, cudaMemsetAsync(np.w_rgb, 0, 3 * kHalf * sizeof(float), st));
-    BNRF_CUDA(ctx, cudaMemsetAsync(np.b_rgb, 0, 3 * sizeof(float), st));
     cp(w[BNRF_L_RGB], C * kHalf, np.w_rgb);
     cp(b[BNRF_L_RGB], C, np.b_rgb);
+    pack_all_kernel<<<dim3(16, t.n), 256, 0, st>>>(t);
     BNRF_LAUNCH_CHECK(ctx);
     int rc = pack_tc_stream(ctx, n, st);
     if (rc != BNRF_OK) return rc;

@@ -404,11 +404,13 @@ size_t dgrad_images_bytes() { return dg_image_offset(11); }
 
 static int pack_dgrad_images(bnrf_ctx* ctx, int net, cudaStream_t st) {
     NetParams& np = ctx->net[net];
+    bwt::DgImageTable t{};
     for (int i = 0; i < 11; ++i) {
         const DgImage& d = kDgImages[i];
-        int rc = bwt::pack_dgrad_image(ctx, np.wt[d.step] + (size_t)d.k0 * d.K, d.N, d.K, np.dg_img + dg_image_offset(i), st);
-        if (rc) return rc;
+        t.seg[t.n++] = bwt::DgImageSeg{np.wt[d.step] + (size_t)d.k0 * d.K, np.dg_img + dg_image_offset(i), d.N, d.K};
     }
+    int rc = bwt::pack_dgrad_images(ctx, t, st);
+    if (rc) return rc;
     np.dg_dirty = false;
     return BNRF_OK;
 }

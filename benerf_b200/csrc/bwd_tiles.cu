@@ -506,23 +506,25 @@ int launch_from_tiles(bnrf_ctx* ctx, const unsigned char* tiles, int64_t rows, i
     return BNRF_OK;
 }
 
-// img: per 64-wide K-block [hi: N x 128 B][lo: N x 128 B], element (n, k) <- src[n * K + k]
-__global__ void pack_dgrad_image_kernel(const float* __restrict__ src, int N, int K, unsigned char* __restrict__ img) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= N * K / 8) return;
-    const int cpr = K / 8, n = e / cpr, c8 = e % cpr;
-    float v[8];
+// img: per 64-wide K-block [hi: N x 128 B][lo: N x 128 B], element (n, k) <- src[n * K + k]; blockIdx.y = image
+__global__ void pack_dgrad_images_kernel(const __grid_constant__ DgImageTable t) {
+    const DgImageSeg& s = t.seg[blockIdx.y];
+    const int cpr = s.K / 8, total = s.N * cpr;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int n = e / cpr, c8 = e % cpr;
+        float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = src[(size_t)n * K + c8 * 8 + j];
-    uint4 hi, lo;
-    split8_bf16(v, hi, lo);
-    unsigned char* dst = img + (size_t)(c8 / 8) * 2 * N * 128 + (size_t)n * 128 + ((uint32_t)((c8 & 7) ^ (n & 7)) << 4);
-    *reinterpret_cast<uint4*>(dst) = hi;
-    *reinterpret_cast<uint4*>(dst + (size_t)N * 128) = lo;
+        for (int j = 0; j < 8; ++j) v[j] = s.src[(size_t)n * s.K + c8 * 8 + j];
+        uint4 hi, lo;
+        split8_bf16(v, hi, lo);
+        unsigned char* dst = s.img + (size_t)(c8 / 8) * 2 * s.N * 128 + (size_t)n * 128 + ((uint32_t)((c8 & 7) ^ (n & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = hi;
+        *reinterpret_cast<uint4*>(dst + (size_t)s.N * 128) = lo;
+    }
 }
 
-int pack_dgrad_image(bnrf_ctx* ctx, const float* wt_rows, int N, int K, unsigned char* img, cudaStream_t st) {
-    pack_dgrad_image_kernel<<<(N * K / 8 + 255) / 256, 256, 0, st>>>(wt_rows, N, K, img);
+int pack_dgrad_images(bnrf_ctx* ctx, const DgImageTable& t, cudaStream_t st) {
+    pack_dgrad_images_kernel<<<dim3(8, t.n), 256, 0, st>>>(t);
     BNRF_LAUNCH_CHECK(ctx);
     return BNRF_OK;
 }
@@ -544,7 +546,7 @@ int bnrf_debug_tile_dgrad(bnrf_ctx* ctx, int64_t rows, int K, int N, const float
     BNRF_CUDA(ctx, cudaMallocAsync(&a_t, tiles * bwt::tile_bytes(K), st));
     BNRF_CUDA(ctx, cudaMallocAsync(&img, bwt::dgrad_image_bytes(N, K), st));
     int rc = bwt::launch_to_tiles(ctx, A, rows, K, K, 1, a_t, st);
-    if (!rc) rc = bwt::pack_dgrad_image(ctx, B, N, K, img, st);
+    if (!rc) { bwt::DgImageTable t{}; t.n = 1; t.seg[0] = bwt::DgImageSeg{B, img, N, K}; rc = bwt::pack_dgrad_images(ctx, t, st); }
     if (!rc && mask) {
         BNRF_CUDA(ctx, cudaMallocAsync(&m_t, tiles * bwt::tile_bytes(256), st));
         rc = bwt::launch_to_tiles(ctx, mask, rows, 256, 256, 1, m_t, st);

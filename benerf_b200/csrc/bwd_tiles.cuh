@@ -71,8 +71,11 @@ int launch_tile_wgrad(bnrf_ctx* ctx, WgradParams& p, cudaStream_t st);   // assi
 // fp32 [rows, W] (row stride ld) -> tile matrix (fmt 0 = fp16 hi/lo, 1 = bf16 hi/lo); rows beyond `rows` are zero
 int launch_to_tiles(bnrf_ctx* ctx, const float* src, int64_t rows, int W, int64_t ld, int fmt, unsigned char* tiles, cudaStream_t st);
 int launch_from_tiles(bnrf_ctx* ctx, const unsigned char* tiles, int64_t rows, int W, int fmt, float* dst, cudaStream_t st);
-// weights of GEMM step s as the dgrad B operand (rows k0 .. k0 + N of wt[s], i.e. B[n][k] = wt[s][k0 + n][k])
-int pack_dgrad_image(bnrf_ctx* ctx, const float* wt_rows, int N, int K, unsigned char* img, cudaStream_t st);
+// weights as dgrad B operands: image i <- fp32 [N, K] row-major (rows k0 .. k0 + N of the k-major copy wt[s], i.e.
+// B[n][k] = wt[s][k0 + n][k]); all images of a network in one launch
+struct DgImageSeg { const float* src; unsigned char* img; int N, K; };
+struct DgImageTable { DgImageSeg seg[12]; int n; };
+int pack_dgrad_images(bnrf_ctx* ctx, const DgImageTable& t, cudaStream_t st);
 __host__ __device__ inline size_t dgrad_image_bytes(int N, int K) { return (size_t)(K / 64) * 2 * N * 128; }
 
 }  // namespace bwt

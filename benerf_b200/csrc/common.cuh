@@ -34,6 +34,9 @@ struct NetParams {
     __half* tc_stream;    // single-CTA kernel (mlp_tc.cu)
     __half* tc2_stream;   // CTA-pair kernel (mlp_tc2.cu): [rank][stage], each CTA's half of the output columns
     float* tc_scale;      // [10] 2^-s per GEMM step undoing the fp16 weight pre-scale
+    const float** wt_table;   // device copy of wt[10] (the packing kernels index it by GEMM step)
+    unsigned int* absmax;     // device [16] scratch of the per-step max |W| (self-clearing)
+    float* scale;             // device [16] 2^s per GEMM step
     // backward pass (bwd_tiles.cu): the 11 dgrad B operands as bf16 hi/lo K-major blocks, packed lazily by the first
     // backward call after bnrf_set_weights
     unsigned char* dg_img;

@@ -393,17 +393,22 @@ __host__ __device__ inline StageInfo stage_info(int i) {
     return {t, kbi * 64 + hk * 32, t == 9 ? 128 : 256, lo}; // wt[t] rows are already ordered [pe64 | h256]
 }
 
-__global__ void absmax_kernel(const float* __restrict__ w, int n, unsigned int* out) {
+// absmax[t] = max |wt[t]| (as uint bits; non-negative floats order like their bit patterns); blockIdx.y = GEMM step
+__global__ void absmax_kernel(const float* const* __restrict__ wt, unsigned int* out) {
+    const int t = blockIdx.y;
+    const int n = (t == 0 ? 64 : (t == 5 ? 320 : 256)) * (t == 9 ? 128 : 256);
+    const float* w = wt[t];
     float m = 0.0f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (threadIdx.x % 32 == 0) atomicMax(out, __float_as_uint(m));
+    if (threadIdx.x % 32 == 0) atomicMax(out + t, __float_as_uint(m));
 }
-// scale[t] = 2^s with max|W| * 2^s in [1024, 2048); inv_scale[t] = 2^-s
-__global__ void scale_kernel(const unsigned int* __restrict__ absmax, float* __restrict__ scale, float* __restrict__ inv_scale) {
+// scale[t] = 2^s with max|W| * 2^s in [1024, 2048); inv_scale[t] = 2^-s.  Clears absmax for the next repack.
+__global__ void scale_kernel(unsigned int* __restrict__ absmax, float* __restrict__ scale, float* __restrict__ inv_scale) {
     const int t = threadIdx.x;
     if (t >= 10) return;
     const float m = __uint_as_float(absmax[t]);
+    absmax[t] = 0u;
     int s = 0;
     if (m > 0.0f && isfinite(m)) s = 10 - ilogbf(m);
     s = max(-24, min(24, s));
@@ -432,29 +437,16 @@ size_t tc_stream_halfs() { return tc::stage_offset_bytes(tc::STAGES_PER_TILE) / 
 int pack_tc_stream(bnrf_ctx* ctx, int net, cudaStream_t st) {
     using namespace tc;
     NetParams& np = ctx->net[net];
-    // scratch inside tc_scale: [0,10) inv_scale (read by the kernel), then absmax bits / scale / pointer table live in
-    // a small side allocation made once per context.
-    static_assert(sizeof(unsigned int) == sizeof(float), "");
-    float* inv_scale = np.tc_scale;
-    unsigned int* absmax = nullptr;
-    float* scale = nullptr;
-    const float** table = nullptr;
-    BNRF_CUDA(ctx, cudaMallocAsync(&absmax, 16 * sizeof(unsigned int), st));
-    BNRF_CUDA(ctx, cudaMallocAsync(&scale, 16 * sizeof(float), st));
-    BNRF_CUDA(ctx, cudaMallocAsync(&table, 10 * sizeof(float*), st));
-    BNRF_CUDA(ctx, cudaMemsetAsync(absmax, 0, 16 * sizeof(unsigned int), st));
-    for (int t = 0; t < 10; ++t) absmax_kernel<<<32, 256, 0, st>>>(np.wt[t], gemm_k(t) * gemm_n(t), absmax + t);
-    scale_kernel<<<1, 32, 0, st>>>(absmax, scale, inv_scale);
-    BNRF_CUDA(ctx, cudaMemcpyAsync(table, np.wt, 10 * sizeof(float*), cudaMemcpyHostToDevice, st));
-    pack_stream_kernel<<<STAGES_PER_TILE, 256, 0, st>>>(table, scale, np.tc_stream);
+    absmax_kernel<<<dim3(8, 10), 256, 0, st>>>(np.wt_table, np.absmax);
+    scale_kernel<<<1, 32, 0, st>>>(np.absmax, np.scale, np.tc_scale);
     BNRF_LAUNCH_CHECK(ctx);
-    {
-        const int rc2 = pack_tc2_stream(ctx, net, table, scale, st);
-        if (rc2 != BNRF_OK) return rc2;
+    // only the stream of the configured kernel is rebuilt (this runs after every optimiser step)
+    if (ctx->cfg.mlp_mode == BNRF_MLP_TC_1CTA) {
+        pack_stream_kernel<<<STAGES_PER_TILE, 256, 0, st>>>(np.wt_table, np.scale, np.tc_stream);
+        BNRF_LAUNCH_CHECK(ctx);
+    } else if (ctx->cfg.mlp_mode == BNRF_MLP_TC_FP16X2) {
+        return pack_tc2_stream(ctx, net, np.wt_table, np.scale, st);
     }
-    BNRF_CUDA(ctx, cudaFreeAsync(absmax, st));
-    BNRF_CUDA(ctx, cudaFreeAsync(scale, st));
-    BNRF_CUDA(ctx, cudaFreeAsync(table, st));
     return BNRF_OK;
 }
 

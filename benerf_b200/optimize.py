@@ -57,7 +57,8 @@ class Model(nerf.Model):
 class Graph(nerf.Graph):
     def _poses(self, args, ts2, num, with_transform):
         eng = self.engine(args)
-        ts = torch.linspace(float(ts2[0]), float(ts2[1]), num).to(eng.device)
+        # built on the device: a host linspace + .to(device) is a pageable copy, i.e. a stream synchronisation every iteration
+        ts = torch.linspace(float(ts2[0]), float(ts2[1]), num, device=eng.device)
         if args.traj not in ("linear", "spline"):
             raise ValueError(args.traj)
         return _SplineFn.apply(eng, args.traj, ts, self.evt_knot_pose_se3.params.weight,
