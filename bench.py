@@ -55,6 +55,19 @@ def peaks():
         return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(flop_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r01_mlp_tc2_ncu_bench.json, written by tools/ncu_key_metrics.py), scaled by algorithmic work to this run's
+    average launch (the kernel's traffic is proportional to its rows); None when no capture is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_mlp_tc2_ncu_bench.json")) as f:
+            cap = json.load(f)
+        return {"bytes_per_launch": cap["dram_bytes"] * flop_per_launch / cap["algorithmic_flop"],
+                "source": "ncu --set full, %s, scaled from a launch of %.3g algorithmic FLOP" % (cap["kernel"], cap["algorithmic_flop"])}
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
@@ -270,7 +283,8 @@ def bench_train_step(opts, dev, world, rank, steps=5, warmup=3):
             "algorithmic_tflops": 3 * rays / world * FLOP_PER_RAY / (ms / 1e3) / 1e12,
             "ms_each_step": per_step, "gpu_launches_per_step": launches / steps, "final_loss": float(loss),
             "mem_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 1),
-            "backward": "fp32 SIMT GEMMs (sgemm.cu); tensor-core backward is the next step"}
+            "optimizer_tail": "fused (bnrf_adam_step)" if args.fused_optimizer else "torch.optim.Adam x3",
+            "backward": "tcgen05 dgrad / wgrad on bf16 hi/lo tile matrices (bwd_tiles.cu), 3 MMAs per product, fp32 accumulate"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -407,7 +421,7 @@ def bench_ours(opts):
             "data": "synthetic", "config": workload_config(R, world),
             "roofline": {"bound": "tensor", "kernel": {"tc": "bnrf::tc2::mlp_tc2_kernel<3> (CTA pairs, cta_group::2)", "tc1": "bnrf::tc::mlp_tc_kernel<3>", "simt": "bnrf::mlp_simt_kernel<3>"}[opts.mlp_mode],
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": ncu_traffic(prof["mlp_flops"] / max(prof["mlp_timed"], 1)), "peak_source": peak_src,
                          "algorithmic_flop_per_launch": prof["mlp_flops"] / max(prof["mlp_timed"], 1),
                          "ms_per_launch": mlp_ms_per_launch, "launches_timed": prof["mlp_timed"],
                          "issued_tflops": achieved * 3 if opts.mlp_mode != "simt" else achieved,
