@@ -50,7 +50,7 @@ def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained bf16)"
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json: sustained bf16 TFLOP/s, copy GB/s)"
     except Exception:
         return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 

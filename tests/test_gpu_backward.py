@@ -151,11 +151,24 @@ def _oracle_leaves(case, inp):
     return knots, transform, coarse, fine
 
 
-@pytest.mark.parametrize("name", ["unreal_rgb", "gray_linear", "blender_gray_coarse"])
-def test_render_backward_matches_oracle_autograd(name):
-    """One Graph.render under autograd with random cotangents on rgb_map / rgb0, identical samples injected."""
+def _first_pixels(case, inp, n_px):
+    """Restrict the blur batch of a case to its first n_px pixels (pose-major draws are sliced per pose)."""
+    inp = dict(inp)
+    inp["idx_rgb"] = inp["idx_rgb"][:n_px]
+    inp["rng_rgb"] = {k: v.reshape(case.n_poses, case.r_rgb, -1)[:, :n_px].reshape(case.n_poses * n_px, -1).contiguous()
+                      for k, v in inp["rng_rgb"].items()}
+    return inp
+
+
+@pytest.mark.parametrize("name,n_px", [("unreal_rgb", None), ("gray_linear", None), ("blender_gray_coarse", None),
+                                       ("unreal_rgb", 3), ("blender_gray_coarse", 5)])
+def test_render_backward_matches_oracle_autograd(name, n_px):
+    """One Graph.render under autograd with random cotangents on rgb_map / rgb0, identical samples injected.
+    The n_px variants leave a partial last tile and an odd tile count (57 rays x 64 / 128 samples, 35 rays x 64)."""
     case, gold = CASES[name], load_golden(name)
     inp = make_inputs(case)
+    if n_px is not None:
+        inp = _first_pixels(case, inp, n_px)
     graph, args = _build_graph(case, inp)
     fine = case.n_importance > 0
     knots, transform, coarse, fine_p = _oracle_leaves(case, inp)
