@@ -411,6 +411,7 @@ static int pack_dgrad_images(bnrf_ctx* ctx, int net, cudaStream_t st) {
     }
     int rc = bwt::pack_dgrad_images(ctx, t, st);
     if (rc) return rc;
+    if ((rc = pack_dgrad_chain_stream(ctx, net, st))) return rc;
     np.dg_dirty = false;
     return BNRF_OK;
 }
@@ -462,15 +463,21 @@ static int mlp_backward(bnrf_ctx* ctx, int net, int64_t n, int S, const ActPtrs&
     BNRF_LAUNCH_CHECK(ctx);
     colsum(w.dvb, kHalf, kHalf, n, dB[BNRF_L_VIEWS]);
     // ---- dgrad chain: dZ9 -> d feature -> dZ7 -> ... -> dZ0 -> d encoding ----
-    if ((rc = dgrad(w.dz9_tiles, kHalf, 0, bwt::DG_TILE, nullptr, DZ(8), nullptr, nullptr, 0, nullptr))) return rc;
-    if ((rc = dgrad(DZ(8), kWidth, 1, bwt::DG_TILE_MASKED, H(7), DZ(7), nullptr, w.d_raw + C, C + 1, np.w_alpha))) return rc;   // + alpha_linear
-    if ((rc = dgrad(DZ(7), kWidth, 2, bwt::DG_TILE_MASKED, H(6), DZ(6), nullptr, nullptr, 0, nullptr))) return rc;
-    if ((rc = dgrad(DZ(6), kWidth, 3, bwt::DG_TILE_MASKED, H(5), DZ(5), nullptr, nullptr, 0, nullptr))) return rc;
-    if ((rc = dgrad(DZ(5), kWidth, 4, bwt::DG_TILE_MASKED, H(4), DZ(4), nullptr, nullptr, 0, nullptr))) return rc;              // cat([pe, h4]) (model/nerf.py:98)
-    if ((rc = dgrad(DZ(5), kWidth, 5, bwt::DG_F32_STORE, nullptr, nullptr, w.d_pe, nullptr, 0, nullptr))) return rc;
-    for (int l = 4; l >= 1; --l)
-        if ((rc = dgrad(DZ(l), kWidth, 10 - l, bwt::DG_TILE_MASKED, H(l - 1), DZ(l - 1), nullptr, nullptr, 0, nullptr))) return rc;
-    if ((rc = dgrad(DZ(0), kWidth, 10, bwt::DG_F32_ACCUM, nullptr, nullptr, w.d_pe, nullptr, 0, nullptr))) return rc;
+    if (ctx->cfg.gemm_mode != BNRF_GEMM_TC_PER_LINEAR) {
+        // one launch, the gradient of a tile stays on the SM across all ten linears (dgrad_chain.cu)
+        if ((rc = launch_dgrad_chain(ctx, net, w.dz9_tiles, acts.mask_bits, acts.t_alloc, w.d_raw + C, C + 1, rows, w.tiles, w.dz_tiles,
+                                     w.d_pe, st))) return rc;
+    } else {
+        if ((rc = dgrad(w.dz9_tiles, kHalf, 0, bwt::DG_TILE, nullptr, DZ(8), nullptr, nullptr, 0, nullptr))) return rc;
+        if ((rc = dgrad(DZ(8), kWidth, 1, bwt::DG_TILE_MASKED, H(7), DZ(7), nullptr, w.d_raw + C, C + 1, np.w_alpha))) return rc;   // + alpha_linear
+        if ((rc = dgrad(DZ(7), kWidth, 2, bwt::DG_TILE_MASKED, H(6), DZ(6), nullptr, nullptr, 0, nullptr))) return rc;
+        if ((rc = dgrad(DZ(6), kWidth, 3, bwt::DG_TILE_MASKED, H(5), DZ(5), nullptr, nullptr, 0, nullptr))) return rc;
+        if ((rc = dgrad(DZ(5), kWidth, 4, bwt::DG_TILE_MASKED, H(4), DZ(4), nullptr, nullptr, 0, nullptr))) return rc;              // cat([pe, h4]) (model/nerf.py:98)
+        if ((rc = dgrad(DZ(5), kWidth, 5, bwt::DG_F32_STORE, nullptr, nullptr, w.d_pe, nullptr, 0, nullptr))) return rc;
+        for (int l = 4; l >= 1; --l)
+            if ((rc = dgrad(DZ(l), kWidth, 10 - l, bwt::DG_TILE_MASKED, H(l - 1), DZ(l - 1), nullptr, nullptr, 0, nullptr))) return rc;
+        if ((rc = dgrad(DZ(0), kWidth, 10, bwt::DG_F32_ACCUM, nullptr, nullptr, w.d_pe, nullptr, 0, nullptr))) return rc;
+    }
     // ---- every 256-wide weight / bias gradient in one launch ----
     bwt::WgradParams p{};
     p.tiles = tiles; p.rows = rows;
@@ -515,6 +522,7 @@ SavedLayout carve_saved(const bnrf_cfg& c, int64_t n, void* base) {
         a.h9_f32 = take(rows * kHalf);
         a.pe_tiles = reinterpret_cast<unsigned char*>(take_bytes((size_t)a.t_alloc * bwt::tile_bytes(kPtsChPad)));
         a.h_tiles = reinterpret_cast<unsigned char*>(take_bytes(9 * (size_t)a.t_alloc * bwt::tile_bytes(kWidth)));
+        a.mask_bits = reinterpret_cast<uint4*>(take_bytes(8 * (size_t)a.t_alloc * bwt::kTileRows * 2 * sizeof(uint4)));
         return a;
     };
     s.o = take(n * 3); s.d = take(n * 3); s.view = take(n * 3);

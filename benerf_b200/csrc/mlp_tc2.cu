@@ -244,6 +244,7 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
                     // hand-off granularity = one K-half (32 columns): every warp converts 16 columns of each K-half, so the
                     // MMA of the next layer can start after 1/8 of the epilogue.
                     uint32_t va[16], vb[16];
+                    uint32_t mw[4] = {0u, 0u, 0u, 0u};          // TRAIN: ReLU mask of this thread's 128 columns, 1 bit each
                     tc_ld16_issue(acc_addr, va);
 #pragma unroll
                     for (int kh = 0; kh < 8; ++kh) {
@@ -296,6 +297,14 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
                                 const uint32_t off = (kh >> 1) * KBLOCK_BYTES + sw128_offset(r, (kh & 1) * 32 + ch * 16 + j * 8);
                                 unsigned char* gt = acts.h_tiles + ((size_t)t * (size_t)acts.t_alloc + (size_t)tile) * (8 * KBLOCK_BYTES) + off;
                                 split_store8_bf16_global(v + 8 * j, gt, gt + 4 * KBLOCK_BYTES);
+                            }
+                            if (t < 8) {
+                                uint32_t bits = 0;
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) bits |= (v[j] > 0.0f ? 1u : 0u) << j;
+                                mw[kh >> 1] |= bits << (16 * (kh & 1));
+                                if (kh == 7)
+                                    acts.mask_bits[(((size_t)t * (size_t)acts.t_alloc + (size_t)tile) * TILE_M + r) * 2 + ch] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
                             }
                         }
                         if (kh < 7) {

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(NT, 2) sgemm_kernel(GemmArgs g) {
 
 int launch_sgemm(bnrf_ctx* ctx, bool ta, bool tb, GemmArgs g, cudaStream_t st) {
     if (g.M <= 0 || g.N <= 0 || g.K < 0) return fail(ctx, BNRF_ERR_ARG, "sgemm: bad shape");
-    if (ctx->cfg.gemm_mode == BNRF_GEMM_TC && gemm_tc_eligible(g)) return launch_gemm_tc(ctx, ta, tb, g, st);
+    if (ctx->cfg.gemm_mode != BNRF_GEMM_SIMT_FP32 && gemm_tc_eligible(g)) return launch_gemm_tc(ctx, ta, tb, g, st);
     g.vec_a = ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && g.lda % 4 == 0) ? 1 : 0;
     g.vec_b = ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0 && g.ldb % 4 == 0) ? 1 : 0;
     int splits = 1;
