@@ -14,8 +14,9 @@
 // [N x 32] SWIZZLE_64B tiles filled by cp.async.bulk from an L2-resident image, layer hand-off per 32-column K-half.
 // Differences: the first A operand (dZ9, written by heads_backward_kernel as a tile matrix) arrives by cp.async.bulk; the
 // epilogue applies the ReLU mask from 1 bit per activation emitted by the training-mode forward pass (16 B per row and
-// layer instead of re-reading activations) and writes every dZ_l ALSO to its tile matrix in global memory, which is what
-// the weight-gradient kernel (bwd_tiles.cu) contracts with the saved activations.  HBM traffic per sample: 9 x 1 KB of
+// layer instead of re-reading activations); and every dZ_l, which in shared memory already IS a tile of its tile matrix,
+// is copied to global memory by the bulk-copy engine (one thread, cp.async.bulk.global.shared) for the weight-gradient
+// kernel (bwd_tiles.cu) -- the epilogue warps issue no global stores, whose completion their release-arrive would await.  HBM traffic per sample: 9 x 1 KB of
 // dZ out + 0.4 KB in, against 10 x 2.5 KB for the per-linear kernels it replaces (tile_dgrad_kernel, kept as a fallback).
 #include "tc_ptx.cuh"
 #include "bwd_tiles.cuh"
@@ -36,8 +37,12 @@ constexpr uint32_t OFF_BAR = OFF_W + NS * STAGE_BYTES;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr uint32_t TMEM_COLS = 512;
 
-enum { BAR_W_FULL = 0, BAR_W_EMPTY = BAR_W_FULL + NS, BAR_A0_FULL = BAR_W_EMPTY + NS, BAR_A_FREE, BAR_A_READY,
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = BAR_W_FULL + NS, BAR_A0_FULL = BAR_W_EMPTY + NS, BAR_A_FREE, BAR_SPILLED, BAR_A_READY,
        BAR_ACC_FULL = BAR_A_READY + 8, BAR_COUNT = BAR_ACC_FULL + 2 };
+
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
 
 // ---- weight stream: stage i = (pass, K-block, K-half, hi/lo) in MMA consumption order ----
 // pass p: 0 = s0, 1..4 = s1..s4, 5 = s4' (encoded-points block of layer 5), 6..9 = s5..s8, 10 = s9
@@ -84,6 +89,7 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
         for (int i = 0; i < NS; ++i) { mbar_init(bar(BAR_W_FULL + i), 1); mbar_init(bar(BAR_W_EMPTY + i), 1); }
         mbar_init(bar(BAR_A0_FULL), 1);
         mbar_init(bar(BAR_A_FREE), 1);
+        mbar_init(bar(BAR_SPILLED), 1);
         for (int i = 0; i < 8; ++i) mbar_init(bar(BAR_A_READY + i), 256);
         for (int i = 0; i < 2; ++i) mbar_init(bar(BAR_ACC_FULL + i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -123,11 +129,35 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
             for (int it = 0; it < my_tiles; ++it) {
                 const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
                 mbar_wait(bar(BAR_A_FREE), ((uint32_t)it & 1u) ^ 1u, err_flag, 52);       // last MMAs of the previous tile have read A
+                if (it > 0) mbar_wait(bar(BAR_SPILLED), ((uint32_t)(it - 1) * 9u + 8u) & 1u, err_flag, 58);   // ... and its dZ0 has been copied out
                 const unsigned char* src = dz9_tiles + (size_t)tile * bwt::tile_bytes(kHalf);
                 mbar_expect_tx(bar(BAR_A0_FULL), 4u * KBLOCK_BYTES);
                 tma_bulk_load(base + OFF_A_HI, src, 2u * KBLOCK_BYTES, bar(BAR_A0_FULL));
                 tma_bulk_load(base + OFF_A_LO, src + bwt::tile_part_bytes(kHalf), 2u * KBLOCK_BYTES, bar(BAR_A0_FULL));
             }
+        }
+    } else if (warp == 3) {
+        // ================= spill: every dZ_l the epilogue builds in shared memory IS a tile of its tile matrix; the bulk-copy engine
+        // writes it to global memory for the weight-gradient kernel, so the epilogue warps issue no global stores =================
+        if (lane == 0) {
+            const size_t dz_mat = (size_t)dz_tile_count * bwt::tile_bytes(kWidth);
+            uint32_t sgen = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+                for (int s = 0; s < 9; ++s, ++sgen) {
+                    unsigned char* gt = dz_tiles + (size_t)(8 - s) * dz_mat + (size_t)tile * bwt::tile_bytes(kWidth);
+                    for (int kb = 0; kb < 4; ++kb) {
+                        mbar_wait(bar(BAR_A_READY + 2 * kb), sgen & 1u, err_flag, 59);
+                        mbar_wait(bar(BAR_A_READY + 2 * kb + 1), sgen & 1u, err_flag, 60);
+                        bulk_store(gt + (size_t)kb * KBLOCK_BYTES, base + OFF_A_HI + kb * KBLOCK_BYTES, KBLOCK_BYTES);
+                        bulk_store(gt + (size_t)(4 + kb) * KBLOCK_BYTES, base + OFF_A_LO + kb * KBLOCK_BYTES, KBLOCK_BYTES);
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // shared memory has been read: the next epilogue may overwrite A
+                    mbar_arrive(bar(BAR_SPILLED));
+                }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -195,7 +225,6 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
         const int ch = (warp - 8) >> 2;
         const int r = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-        const size_t dz_mat = (size_t)dz_tile_count * bwt::tile_bytes(kWidth);
         uint32_t acc_uses[2] = {0, 0};
         for (int it = 0; it < my_tiles; ++it) {
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
@@ -226,7 +255,7 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
                 }
                 if (s < 9) {
                     const uint32_t acc_addr = lane_addr + (uint32_t)b * 256u + (uint32_t)ch * 16u;
-                    unsigned char* gt = dz_tiles + (size_t)(8 - s) * dz_mat + (size_t)tile * bwt::tile_bytes(kWidth);
+                    if (s >= 1) mbar_wait(bar(BAR_SPILLED), ((uint32_t)it * 9u + (uint32_t)(s - 1)) & 1u, err_flag, 61);   // A (= dZ of step s-1) copied out
                     const uint32_t mw[4] = {mbits.x, mbits.y, mbits.z, mbits.w};
                     uint32_t va[16], vb[16];
                     tc_ld16_issue(acc_addr, va);
@@ -264,8 +293,6 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
                             bwt::split8_bf16_pub(v + 8 * j, hi, lo);
                             *reinterpret_cast<uint4*>(sm + OFF_A_HI + off) = hi;
                             *reinterpret_cast<uint4*>(sm + OFF_A_LO + off) = lo;
-                            *reinterpret_cast<uint4*>(gt + off) = hi;                                   // the same words, for the wgrad kernel
-                            *reinterpret_cast<uint4*>(gt + 4 * KBLOCK_BYTES + off) = lo;
                         }
                         tc_fence_before();
                         fence_proxy_async();

@@ -129,9 +129,10 @@ def test_spline_backward_matches_autograd(eng, traj, with_transform):
         assert rel_err(d_transform, transform.grad.reshape(6)) < 2e-4
 
 
-def _build_graph(case, inp):
+def _build_graph(case, inp, gemm_mode="tc"):
     from benerf_b200 import optimize
     args = case_args(case)
+    args.gemm_mode = gemm_mode
     graph = optimize.Model(args).build_network(args)
     graph.nerf.load_state_dict(inp["coarse"])
     if case.n_importance > 0:
@@ -203,14 +204,16 @@ def test_render_backward_matches_oracle_autograd(name, n_px):
     assert report[worst] < 1e-2, report
 
 
-@pytest.mark.parametrize("name", ["unreal_rgb", "e2nerf_syn", "e2nerf_real", "gray_linear"])
-def test_training_iteration_gradients_match_reference(name):
+@pytest.mark.parametrize("name,gemm_mode", [("unreal_rgb", "tc"), ("e2nerf_syn", "tc"), ("e2nerf_real", "tc"), ("gray_linear", "tc"),
+                                            ("unreal_rgb", "tc_linear"), ("gray_linear", "tc_linear")])
+def test_training_iteration_gradients_match_reference(name, gemm_mode):
     """Full iteration (two renders + image formation + the four loss terms, train.py:163-337) -> gradients of the
-    reference itself (tests/golden): knots, transform, per-parameter norms and every 97th gradient element."""
+    reference itself (tests/golden): knots, transform, per-parameter norms and every 97th gradient element.
+    gemm_mode tc = fused dgrad chain (dgrad_chain.cu), tc_linear = one dgrad launch per linear (bwd_tiles.cu)."""
     from benerf_b200 import image_formation as IF
     case, gold = CASES[name], load_golden(name)
     inp = make_inputs(case)
-    graph, args = _build_graph(case, inp)
+    graph, args = _build_graph(case, inp, gemm_mode)
     rets = {}
     for tag, poses, idx, draws in (("evt", graph.get_pose_evt(args, torch.tensor(case.window, dtype=torch.float32)), inp["idx_evt"], inp["rng_evt"]),
                                    ("rgb", graph.get_pose_rgb(args, torch.tensor(case.exposure, dtype=torch.float32)), inp["idx_rgb"], inp["rng_rgb"])):
