@@ -9,14 +9,15 @@
 //                        exclusive cumprod, sum(w*rgb) -- one warp per ray, suffix scan
 //   heads / dgrad / wgrad the 12 linears of NeRF.forward (model/nerf.py:93-112): the 256-wide ones
 //                        through the tile kernels of bwd_tiles.cu (gradients stay bf16 hi/lo tile
-//                        matrices between layers), the narrow heads through sgemm.cu
+//                        matrices between layers; activation gradients of all ten in ONE launch,
+//                        dgrad_chain.cu), the narrow heads (rgb_linear C x 128, the 128 x 27 direction
+//                        block) through small reduction kernels here
 //   pe_ray_backward      sin/cos encoding (model/embedder.py:9-34) and pts = o + d*z
 //   viewdir_backward     direction encoding + the per-ray view bias
 //   rays_backward        ndc_rays + get_specific_rays + viewdirs (run_nerf_helpers.py:35-71) -> d poses
 // z_vals carry no gradient (stratified depths have no parameters; z_samples are detached,
 // model/nerf.py:324), exactly as in the reference.  d poses -> d knots is pose.cu (dual numbers).
 #include "common.cuh"
-#include "sgemm.cuh"
 #include "bwd_tiles.cuh"
 #include "tc_ptx.cuh"
 
@@ -179,16 +180,42 @@ __global__ void sum_samples_kernel(const float* __restrict__ dz9, int S, float* 
     dvb[ray * kHalf + j] = acc;
 }
 
-// out[n] += sum_rows X[row*ld + n]
-__global__ void colsum_kernel(const float* __restrict__ X, int64_t rows, int N, int64_t ld, int64_t rows_per_block,
-                              float* __restrict__ out) {
-    const int n = blockIdx.y * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+// ------------------------------------------------------------------ rgb_linear: weight and bias gradient
+// dW[c][j] += sum_rows d_raw[row][c] * H9[row][j],  dB[c] += sum_rows d_raw[row][c]   (C x 128: too narrow for a
+// tensor-core tile; HBM-bound at 528 B per row).  A block owns a contiguous range of rows, thread j column j.
+template <int C>
+__global__ void rgb_head_wgrad_kernel(const float* __restrict__ d_raw, const float* __restrict__ h9, int64_t rows,
+                                      int64_t rows_per_block, float* __restrict__ dW, float* __restrict__ dB) {
+    const int j = threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
+    float acc[C], bs = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+#pragma unroll 4
+    for (int64_t row = r0; row < r1; ++row) {
+        const float h = h9[row * kHalf + j];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = fmaf(d_raw[row * (C + 1) + c], h, acc[c]);
+        if (j < C) bs += d_raw[row * (C + 1) + j];
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) atomicAdd(dW + c * kHalf + j, acc[c]);
+    if (j < C) atomicAdd(dB + j, bs);
+}
+
+// ------------------------------------------------------------------ views_linears.0: direction block and bias
+// dW[j][256 + i] += sum_rays dvb[ray][j] * enc[ray][i] (i < 27),  dB[j] += sum_rays dvb[ray][j]; blockIdx.x = i (27 = bias)
+__global__ void viewdir_wgrad_kernel(const float* __restrict__ dvb, const float* __restrict__ pe_dir /*[N,32]*/, int64_t n_rays,
+                                     int64_t rays_per_block, float* __restrict__ dW /*[128, 283]*/, float* __restrict__ dB) {
+    const int j = threadIdx.x, i = blockIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * rays_per_block;
+    const int64_t r1 = (r0 + rays_per_block < n_rays) ? r0 + rays_per_block : n_rays;
     float acc = 0.f;
-    for (int64_t r = r0; r < r1; ++r) acc += X[r * ld + n];
-    atomicAdd(out + n, acc);
+#pragma unroll 4
+    for (int64_t ray = r0; ray < r1; ++ray) acc = fmaf(dvb[ray * kHalf + j], i < kDirCh ? pe_dir[ray * 32 + i] : 1.0f, acc);
+    if (i < kDirCh) atomicAdd(dW + (size_t)j * (kWidth + kDirCh) + kWidth + i, acc);
+    else atomicAdd(dB + j, acc);
 }
 
 // ------------------------------------------------------------------ view-direction branch
@@ -428,11 +455,6 @@ static int mlp_backward(bnrf_ctx* ctx, int net, int64_t n, int S, const ActPtrs&
     auto H = [&](int l) { return acts.h_tiles + (size_t)l * hmat; };                    // l = 0..7, 8 = feature
     int rc;
     if (np.dg_dirty && (rc = pack_dgrad_images(ctx, net, st))) return rc;
-    auto colsum = [&](const float* X, int N, int64_t ld, int64_t cnt, float* out) {
-        const int64_t rpb = 512;
-        colsum_kernel<<<dim3((unsigned)ceil_div(cnt, rpb), (unsigned)ceil_div(N, 128)), 128, 0, st>>>(X, cnt, N, ld, rpb, out);
-        ctx->launches++;
-    };
     auto dgrad = [&](const unsigned char* A, int K, int img, int epi, const unsigned char* mask, unsigned char* out_tiles, float* out_f32,
                      const float* r_row, int64_t r_stride, const float* r_col) {
         bwt::DgradArgs a{};
@@ -451,17 +473,16 @@ static int mlp_backward(bnrf_ctx* ctx, int net, int64_t n, int S, const ActPtrs&
         else heads_backward_kernel<1><<<grid, 256, 0, st>>>(w.d_raw, h9, np.w_rgb, rows, rows_pad, w.dz9, w.dz9_tiles);
         BNRF_LAUNCH_CHECK(ctx);
     }
-    {   // rgb_linear weight gradient: [C, rows] x [rows, 128] (too narrow for a tensor-core tile)
-        GemmArgs g{};
-        g.M = C; g.N = kHalf; g.K = rows; g.A = w.d_raw; g.lda = C + 1; g.B = h9; g.ldb = kHalf;
-        g.C = dW[BNRF_L_RGB]; g.ldc = kHalf; g.epi = GEMM_ATOMIC;
-        if ((rc = launch_sgemm(ctx, true, false, g, st))) return rc;
+    {   // rgb_linear weight + bias gradient
+        const int64_t blocks = rows < 4096 ? 1 : (ceil_div(rows, 1024) < 4 * ctx->sm_count ? ceil_div(rows, 1024) : 4 * ctx->sm_count);
+        const int64_t rpb = ceil_div(rows, blocks);
+        if (C == 3) rgb_head_wgrad_kernel<3><<<(unsigned)blocks, kHalf, 0, st>>>(w.d_raw, h9, rows, rpb, dW[BNRF_L_RGB], dB[BNRF_L_RGB]);
+        else rgb_head_wgrad_kernel<1><<<(unsigned)blocks, kHalf, 0, st>>>(w.d_raw, h9, rows, rpb, dW[BNRF_L_RGB], dB[BNRF_L_RGB]);
+        BNRF_LAUNCH_CHECK(ctx);
     }
-    colsum(w.d_raw, C, C + 1, rows, dB[BNRF_L_RGB]);
-    // ---- views_linears.0: direction block + bias per ray (the view bias is shared by the S samples of a ray) ----
+    // ---- views_linears.0: per-ray sum of dZ9 (the view bias is shared by the S samples of a ray) ----
     sum_samples_kernel<<<(unsigned)n, kHalf, 0, st>>>(w.dz9, S, w.dvb);
     BNRF_LAUNCH_CHECK(ctx);
-    colsum(w.dvb, kHalf, kHalf, n, dB[BNRF_L_VIEWS]);
     // ---- dgrad chain: dZ9 -> d feature -> dZ7 -> ... -> dZ0 -> d encoding ----
     if (ctx->cfg.gemm_mode != BNRF_GEMM_TC_PER_LINEAR) {
         // one launch, the gradient of a tile stays on the SM across all ten linears (dgrad_chain.cu)
@@ -613,11 +634,11 @@ int bnrf_render_backward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_i
         // view-direction block of views_linears.0 and d viewdirs
         viewdir_backward_kernel<<<grid, 32 * kWarps, 0, st>>>(s.view, w.b.dvb, ctx->net[net].w_dir, n, w.b.pe_dir, w.g_v);
         BNRF_LAUNCH_CHECK(ctx);
-        {
-            GemmArgs g2{};
-            g2.M = kHalf; g2.N = kDirCh; g2.K = n; g2.A = w.b.dvb; g2.lda = kHalf; g2.B = w.b.pe_dir; g2.ldb = 32;
-            g2.C = pg->weights[BNRF_L_VIEWS] + kWidth; g2.ldc = kWidth + kDirCh; g2.epi = GEMM_ATOMIC;
-            if ((rc = launch_sgemm(ctx, true, false, g2, st))) return rc;
+        {   // direction block of views_linears.0 and its bias (pe_dir is written by viewdir_backward_kernel above)
+            const int64_t rpb = 128;
+            viewdir_wgrad_kernel<<<dim3(kDirCh + 1, (unsigned)ceil_div(n, rpb)), kHalf, 0, st>>>(
+                w.b.dvb, w.b.pe_dir, n, rpb, pg->weights[BNRF_L_VIEWS], pg->biases[BNRF_L_VIEWS]);
+            BNRF_LAUNCH_CHECK(ctx);
         }
         pe_ray_backward_kernel<<<grid, 32 * kWarps, 0, st>>>(acts.pe_f32, w.b.d_pe, z, n, S, w.g_o, w.g_d);
         BNRF_LAUNCH_CHECK(ctx);

@@ -81,9 +81,14 @@ class Engine:
 
     def sync_weights(self, net, module):
         """Repack only when an optimiser step (or load_state_dict) touched the module's parameters."""
-        version = tuple((p.data_ptr(), p._version) for p in module.parameters())
+        cache = self.__dict__.setdefault("_sync_params", {})
+        if cache.get(net, (None,))[0] is not module:
+            table = dict(module.named_parameters())          # walked once per module, not once per render
+            cache[net] = (module, {n + sfx: table[n + sfx] for n in _lib.LINEAR_NAMES for sfx in (".weight", ".bias")})
+        params = cache[net][1]
+        version = tuple((p.data_ptr(), p._version) for p in params.values())
         if version != self._weights_version[net]:
-            self.set_weights(net, module)
+            self.set_weights(net, params)
             self._weights_version[net] = version
 
     def invalidate_weights(self):

@@ -123,6 +123,17 @@ class Graph(nn.Module):
                                   mlp_mode=getattr(args, "mlp_mode", "tc"), gemm_mode=getattr(args, "gemm_mode", "tc"))
         return self._engine
 
+    def _render_params(self, nets):
+        """The 24 (+24) parameters in bnrf_set_weights order; the Parameter objects live as long as the modules, so the
+        list is built once (named_parameters() walks the module tree: ~60 % of a training step's host time if redone)."""
+        if getattr(self, "_param_cache", None) is None or self._param_cache[0] != len(nets):
+            ps = []
+            for m in nets:
+                table = dict(m.named_parameters())
+                ps += [table[n + sfx] for n in LINEAR_NAMES for sfx in (".weight", ".bias")]
+            self._param_cache = (len(nets), ps)
+        return self._param_cache[1]
+
     def _sync(self, eng):
         eng.sync_weights(0, self.nerf)
         if hasattr(self, "nerf_fine"):
@@ -201,7 +212,7 @@ class Graph(nn.Module):
         self._render_calls += 1
         K_np = np.asarray(K.cpu() if isinstance(K, torch.Tensor) else K, dtype=np.float32)
         nets = [self.nerf] + ([self.nerf_fine] if hasattr(self, "nerf_fine") else [])
-        params = [dict(m.named_parameters())[n + sfx] for m in nets for n in LINEAR_NAMES for sfx in (".weight", ".bias")]
+        params = self._render_params(nets)
         if torch.is_grad_enabled() and (poses.requires_grad or any(p.requires_grad for p in params)):
             call = (eng, ray_idx, H, W, K_np, remap_t, rng, self._seed, self._render_calls, len(nets) > 1)
             outs = _RenderFn.apply(call, poses, *params)
