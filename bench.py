@@ -215,18 +215,27 @@ def bench_image_formation_stress(dev, steps=5, warmup=3):
 
 
 # ----------------------------------------------------------------------------------------------
-def bench_train_step(opts, dev, world, rank, steps=5, warmup=3):
-    """BASELINE.json configs[2] shape per GPU (weak scaling): e2nerf_synthetic 800x800, 1024 event pixels x 2 poses +
-    2048 // 19 = 107 blur pixels x 19 poses = 4081 rays, 64 + 128 samples, forward + backward + the reference's Adam
-    steps + ONE gradient all-reduce (benerf_b200.train.Trainer.step).  Device-timed, max over ranks."""
+def bench_train_step(opts, dev, world, rank, steps=5, warmup=3, config="e2nerf_synthetic"):
+    """Training step per GPU (weak scaling), forward + backward + Adam + ONE gradient all-reduce
+    (benerf_b200.train.Trainer.step), device-timed, max over ranks:
+      e2nerf_synthetic  BASELINE.json configs[2]: 800x800, 1024 event pixels x 2 poses + 2048 // 19 = 107 blur pixels x 19
+                        poses = 4081 rays, thresholded event loss
+      e2nerf_real       BASELINE.json configs[3]: 346x260, 31 virtual poses, 1024 event pixels x 2 + 1024 // 31 = 33 blur pixels
+                        x 31 = 3071 rays, NORMALISED event loss (its two batch norms are all-reduced, train.py:238-292)"""
     import torch.distributed as dist
     from benerf_b200 import optimize, run_nerf_helpers
     from benerf_b200.train import Trainer
-    Ht = Wt = 800
-    f = 1111.111
-    Kt = [[f, 0.0, 400.0], [0.0, f, 400.0], [0.0, 0.0, 1.0]]
     args = ref_args()
-    args.dataset, args.event_threshold, args.seed = "E2NeRF_Synthetic", 0.2, 1
+    if config == "e2nerf_real":
+        Ht, Wt, f, n_poses, r_rgb = 260, 346, 653.98456, 31, 1024 // 31
+        Kt = [[f, 0.0, 173.0], [0.0, f, 130.0], [0.0, 0.0, 1.0]]
+        args.dataset, args.event_threshold, args.seed, args.num_interpolated_pose = "E2NeRF_Real", -1.0, 1, n_poses
+        args.event_coeff_real = 2.0
+    else:
+        Ht = Wt = 800
+        f, n_poses, r_rgb = 1111.111, N_POSES, 2048 // N_POSES
+        Kt = [[f, 0.0, 400.0], [0.0, f, 400.0], [0.0, 0.0, 1.0]]
+        args.dataset, args.event_threshold, args.seed = "E2NeRF_Synthetic", 0.2, 1
     args.lrate, args.pose_lrate, args.transform_lrate, args.rgb_crf_lrate, args.event_crf_lrate = 5e-4, 1e-3, 1e-6, 5e-4, 5e-4
     args.optimize_nerf, args.optimize_pose, args.optimize_trans = True, True, False
     args.fused_optimizer = os.environ.get("BNRF_FUSED_TAIL", "1") != "0"
@@ -240,7 +249,7 @@ def bench_train_step(opts, dev, world, rank, steps=5, warmup=3):
     if os.environ.get("BNRF_STEP_TRACE"):
         trainer.phase_ms = []
     g = torch.Generator().manual_seed(99 + rank)
-    r_evt, r_rgb = 1024, 2048 // N_POSES
+    r_evt = 1024
     idx_evt = torch.randint(0, Ht * Wt, (r_evt,), generator=g).to(dev)
     idx_rgb = torch.randint(0, Ht * Wt, (r_rgb,), generator=g).to(dev)
     blur_t = torch.rand(r_rgb, CH, generator=g).to(dev)
@@ -275,11 +284,12 @@ def bench_train_step(opts, dev, world, rank, steps=5, warmup=3):
         ms = float(t[0])
     if trainer.phase_ms:
         print("phase trace:", trainer.phase_ms, file=sys.stderr)
-    rays = (2 * r_evt + N_POSES * r_rgb) * world
+    rays = (2 * r_evt + n_poses * r_rgb) * world
     return {"metric": "rays_per_sec (training step: forward + backward + Adam + gradient all-reduce)", "value": rays / (ms / 1e3),
             "unit": "rays/s", "ms_per_step": ms, "steps": steps, "warmup": warmup, "rays_per_step_per_gpu": rays // world,
-            "workload": "e2nerf_synthetic 800x800, 1024 event px x 2 poses + 107 blur px x 19 poses, 64+128 samples, C=3 "
-                        "(BASELINE.json configs[2], weak scaling)",
+            "workload": (f"{config} {Wt}x{Ht}, 1024 event px x 2 poses + {r_rgb} blur px x {n_poses} poses, 64+128 samples, C=3 "
+                         f"(BASELINE.json configs[{3 if config == 'e2nerf_real' else 2}], weak scaling"
+                         + (", normalised event loss with all-reduced batch norms)" if config == "e2nerf_real" else ")")),
             "algorithmic_tflops": 3 * rays / world * FLOP_PER_RAY / (ms / 1e3) / 1e12,
             "ms_each_step": per_step, "gpu_launches_per_step": launches / steps, "final_loss": float(loss),
             "mem_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 1),
@@ -310,7 +320,7 @@ def bench_ours(opts):
     graph.to(dev)
     eng = graph.engine(args)
     if opts.mode == "train":                 # development aid: only the training-step measurement
-        t = bench_train_step(opts, dev, world, rank, steps=opts.steps, warmup=opts.warmup)
+        t = bench_train_step(opts, dev, world, rank, steps=opts.steps, warmup=opts.warmup, config=opts.train_config)
         if rank == 0:
             print(json.dumps(t))
         if world > 1:
@@ -318,6 +328,7 @@ def bench_ours(opts):
         return
     # the two secondary measurements run first, on a quiet device (the headline render phase holds ~12 GB and the power cap)
     train = None if opts.no_train_step else bench_train_step(opts, dev, world, rank)
+    train_real = None if opts.no_train_step else bench_train_step(opts, dev, world, rank, config="e2nerf_real")
     stress = None if opts.no_train_step else bench_image_formation_stress(dev)
     torch.cuda.empty_cache()
     R = opts.pixels
@@ -431,6 +442,7 @@ def bench_ours(opts):
                                  "MMAs per product, so the tensor pipe issues 3x that (issued_*)"},
             "cpu_baseline": cpu,
             "train_step": train,
+            "train_step_e2nerf_real": train_real,
             "image_formation_stress": stress,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * wall_e2e / opts.steps},
@@ -453,6 +465,7 @@ def main():
     ap.add_argument("--cpu-pixels", type=int, default=128, help="pixels of the bounded CPU sample")
     ap.add_argument("--mlp-mode", default="tc", choices=["tc", "tc1", "simt"])
     ap.add_argument("--mode", default="render", choices=["render", "train"], help="train: print only the training-step line")
+    ap.add_argument("--train-config", default="e2nerf_synthetic", choices=["e2nerf_synthetic", "e2nerf_real"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-step", action="store_true", help="skip the extra training-step measurement")
     opts = ap.parse_args()

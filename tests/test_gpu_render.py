@@ -231,3 +231,50 @@ def test_config1_full_frame_psnr_vs_oracle():
     assert int(kink.sum()) <= n // 50
     if not kink.any():
         assert blur_err < TOL
+
+
+@pytest.mark.parametrize("time_window,random_window", [(True, True), (True, False), (False, True), (False, False)])
+def test_graph_forward_windows_events_and_renders_both_batches(time_window, random_window):
+    """Graph.forward (model/nerf.py:160-234), the call train.py:160 makes: the event window chosen with the reference's own
+    np.random draws (replayed here from the same seed), its accumulation against a numpy restatement of lines 170-199, the
+    shapes / pose-major order of both renders, and gradients reaching both networks, the knots and the transform."""
+    import numpy as np
+    from tests.test_gpu_backward import case_args
+    from benerf_b200 import optimize, run_nerf_helpers as rh
+    case = CASES["e2nerf_syn"]
+    inp = make_inputs(case)
+    args = case_args(case)
+    args.event_time_window, args.random_sampling_window, args.accumulate_time_length = time_window, random_window, 0.1
+    args.event_height, args.event_width, args.sampling_event_rays, args.sampling_rgb_rays = case.H, case.W, 64, 190
+    graph = optimize.Model(args).build_network(args)
+    rh.init_nerf(graph.nerf); rh.init_nerf(graph.nerf_fine)
+    graph.to(DEV)
+    ev = {k: np.asarray(v) for k, v in inp["events"].items()}
+    np.random.seed(123)
+    ret_evt, ret_rgb, idx_evt, idx_rgb, accu = graph.forward(0, ev, case.exposure, case.H, case.W, case.K, case.K, args, None, None)
+    # replay of the reference's window selection (model/nerf.py:162-189) with the same draws
+    np.random.seed(123)
+    if time_window:
+        wt = args.accumulate_time_length
+        if random_window:
+            low = np.random.rand(1) * (1 - wt); up = low + wt
+        else:
+            low = np.random.randint((1 - wt) // wt) * wt; up = np.min((low + wt, 1.0))
+        sel = np.where((low <= ev["ts"]) * (ev["ts"] <= up))
+    else:
+        num = len(ev["pol"]); nw = round(num * args.accumulate_time_length)
+        lo = np.random.randint(num - nw) if random_window else np.random.randint((num - nw) // nw) * nw
+        sel = (np.arange(lo, lo + nw),)
+    want = np.zeros((case.H, case.W))
+    np.add.at(want, (ev["y"][sel], ev["x"][sel]), ev["pol"][sel])
+    assert accu.dtype == torch.float64 and accu.shape == (case.H, case.W)
+    assert np.array_equal(accu.cpu().numpy(), want) and np.abs(want).sum() > 0
+    r_rgb = args.sampling_rgb_rays // args.num_interpolated_pose
+    assert idx_evt.shape == (64,) and idx_rgb.shape == (r_rgb,)
+    assert ret_evt["rgb_map"].shape == (2 * 64, 3) and ret_rgb["rgb_map"].shape == (case.n_poses * r_rgb, 3)
+    assert ret_rgb["rgb0"].shape == ret_rgb["rgb_map"].shape and ret_rgb["sigma"].shape == (case.n_poses * r_rgb, 128)
+    loss = ret_evt["rgb_map"].mean() + ret_rgb["rgb_map"].mean() + ret_rgb["rgb0"].mean() + ret_evt["rgb0"].mean()
+    loss.backward()
+    for p in list(graph.nerf.parameters()) + list(graph.nerf_fine.parameters()) + [graph.evt_knot_pose_se3.params.weight, graph.transform.params.weight]:
+        assert p.grad is not None and torch.isfinite(p.grad).all()
+    assert float(graph.evt_knot_pose_se3.params.weight.grad.abs().sum()) > 0 and float(graph.transform.params.weight.grad.abs().sum()) > 0
