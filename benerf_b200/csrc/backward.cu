@@ -543,7 +543,7 @@ SavedLayout carve_saved(const bnrf_cfg& c, int64_t n, void* base) {
         a.h9_f32 = take(rows * kHalf);
         a.pe_tiles = reinterpret_cast<unsigned char*>(take_bytes((size_t)a.t_alloc * bwt::tile_bytes(kPtsChPad)));
         a.h_tiles = reinterpret_cast<unsigned char*>(take_bytes(9 * (size_t)a.t_alloc * bwt::tile_bytes(kWidth)));
-        a.mask_bits = reinterpret_cast<uint4*>(take_bytes(8 * (size_t)a.t_alloc * bwt::kTileRows * 2 * sizeof(uint4)));
+        a.mask_bits = reinterpret_cast<unsigned char*>(take_bytes(8 * (size_t)a.t_alloc * 4096));
         return a;
     };
     s.o = take(n * 3); s.d = take(n * 3); s.view = take(n * 3);

@@ -51,8 +51,8 @@ struct ActPtrs {
     float* h9_f32;             // [rows, 128] view-layer activations, fp32 (rgb head)
     unsigned char* pe_tiles;   // bf16 hi/lo tile matrix of width 64 (bwd_tiles.cuh)
     unsigned char* h_tiles;    // 9 bf16 hi/lo tile matrices of width 256: h0..h7, feature; t_alloc tiles each
-    uint4* mask_bits;          // ReLU masks of h0..h7, 1 bit per activation: [8][t_alloc][128 rows][2 column halves] x 16 B
-                               // (bit j of 16-bit word kh = column kh*32 + half*16 + j, the epilogue's own chunking)
+    unsigned char* mask_bits;  // ReLU masks of h0..h7, 1 bit per activation, laid out like the tiles: [8][t_alloc][4096] bytes,
+                               // byte c = the 8 elements of 16-byte chunk c of the tile's hi part (bit e = element e)
     int64_t t_alloc;
 };
 
@@ -177,7 +177,7 @@ SavedLayout carve_saved(const bnrf_cfg& c, int64_t n, void* base);
 size_t dgrad_images_bytes();   // backward.cu: the 11 dgrad weight images of one network
 size_t dgrad_chain_stream_bytes();
 int pack_dgrad_chain_stream(bnrf_ctx*, int net, cudaStream_t);
-int launch_dgrad_chain(bnrf_ctx*, int net, const unsigned char* dz9_tiles, const uint4* mask_bits, int64_t t_alloc,
+int launch_dgrad_chain(bnrf_ctx*, int net, const unsigned char* dz9_tiles, const unsigned char* mask_bits, int64_t t_alloc,
                        const float* d_sigma, int64_t d_sigma_stride, int64_t rows, int64_t dz_tile_count, unsigned char* dz_tiles,
                        float* d_pe, cudaStream_t);
 

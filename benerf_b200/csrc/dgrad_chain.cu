@@ -13,7 +13,7 @@
 // accumulators ping-ponging between two 256-column TMEM buffers, transposed weights streaming through a 6-stage ring of
 // [N x 32] SWIZZLE_64B tiles filled by cp.async.bulk from an L2-resident image, layer hand-off per 32-column K-half.
 // Differences: the first A operand (dZ9, written by heads_backward_kernel as a tile matrix) arrives by cp.async.bulk; the
-// epilogue applies the ReLU mask from 1 bit per activation emitted by the training-mode forward pass (16 B per row and
+// epilogue applies the ReLU mask from 1 bit per activation emitted by the training-mode forward pass (32 B per row and
 // layer instead of re-reading activations); and every dZ_l, which in shared memory already IS a tile of its tile matrix,
 // is copied to global memory by the bulk-copy engine (one thread, cp.async.bulk.global.shared) for the weight-gradient
 // kernel (bwd_tiles.cu) -- the epilogue warps issue no global stores, whose completion their release-arrive would await.  HBM traffic per sample: 9 x 1 KB of
@@ -74,7 +74,7 @@ constexpr int STAGES_PER_TILE = 8 + 16 * 10;       // 168
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char* __restrict__ dz9_tiles,
-                   const uint4* __restrict__ mask_bits, int64_t t_alloc, const float* __restrict__ d_sigma, int64_t d_sigma_stride,
+                   const unsigned char* __restrict__ mask_bits, int64_t t_alloc, const float* __restrict__ d_sigma, int64_t d_sigma_stride,
                    const float* __restrict__ w_alpha, int64_t rows, int num_tiles, int64_t dz_tile_count,
                    unsigned char* __restrict__ dz_tiles, float* __restrict__ d_pe, unsigned int* err_flag) {
     extern __shared__ unsigned char smem_raw[];
@@ -234,8 +234,13 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
             for (int s = 0; s < 10; ++s) {
                 const int b = s & 1;
                 // fetched BEFORE blocking on the accumulator (no L1 behind the smem carve-out: these are L2 round trips)
-                uint4 mbits = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-                if (s >= 1 && s <= 8) mbits = __ldg(mask_bits + (((size_t)(8 - s) * (size_t)t_alloc + (size_t)tile) * TILE_M + r) * 2 + ch);
+                // ReLU mask of this row: byte p of word kb = the 8 elements of physical 16-byte chunk p of K-block kb (mlp_tc2.cu)
+                unsigned long long mrow[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+                if (s >= 1 && s <= 8) {
+                    const unsigned char* mk = mask_bits + ((size_t)(8 - s) * (size_t)t_alloc + (size_t)tile) * 4096 + (size_t)r * 8;
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) mrow[kb] = __ldg(reinterpret_cast<const unsigned long long*>(mk + kb * 1024));
+                }
                 const float rr = (s == 1 && live) ? __ldg(d_sigma + row * d_sigma_stride) : 0.0f;
                 float4 wq[4];
                 if (s == 1) {
@@ -256,7 +261,6 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
                 if (s < 9) {
                     const uint32_t acc_addr = lane_addr + (uint32_t)b * 256u + (uint32_t)ch * 16u;
                     if (s >= 1) mbar_wait(bar(BAR_SPILLED), ((uint32_t)it * 9u + (uint32_t)(s - 1)) & 1u, err_flag, 61);   // A (= dZ of step s-1) copied out
-                    const uint32_t mw[4] = {mbits.x, mbits.y, mbits.z, mbits.w};
                     uint32_t va[16], vb[16];
                     tc_ld16_issue(acc_addr, va);
 #pragma unroll
@@ -283,9 +287,14 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
                                 v[j + 2] = fmaf(rr, wv.z, v[j + 2]); v[j + 3] = fmaf(rr, wv.w, v[j + 3]);
                             }
                         }
-                        const uint32_t bits = (mw[kh >> 1] >> (16 * (kh & 1))) & 0xffffu;
+                        {
+                            const int lc = (kh & 1) * 4 + ch * 2;                                  // logical 16-byte chunk of v[0..7]; v[8..15] is lc + 1
+                            const uint32_t b0 = (uint32_t)(mrow[kh >> 1] >> (8 * (lc ^ (r & 7)))) & 0xffu;
+                            const uint32_t b1 = (uint32_t)(mrow[kh >> 1] >> (8 * ((lc + 1) ^ (r & 7)))) & 0xffu;
+                            const uint32_t bits = b0 | (b1 << 8);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.0f;
+                            for (int j = 0; j < 16; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.0f;
+                        }
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             const uint32_t off = (kh >> 1) * KBLOCK_BYTES + sw128_offset(r, (kh & 1) * 32 + ch * 16 + j * 8);
@@ -359,7 +368,7 @@ int pack_dgrad_chain_stream(bnrf_ctx* ctx, int net, cudaStream_t st) {
     return BNRF_OK;
 }
 
-int launch_dgrad_chain(bnrf_ctx* ctx, int net, const unsigned char* dz9_tiles, const uint4* mask_bits, int64_t t_alloc,
+int launch_dgrad_chain(bnrf_ctx* ctx, int net, const unsigned char* dz9_tiles, const unsigned char* mask_bits, int64_t t_alloc,
                        const float* d_sigma, int64_t d_sigma_stride, int64_t rows, int64_t dz_tile_count, unsigned char* dz_tiles,
                        float* d_pe, cudaStream_t st) {
     using namespace dgc;

@@ -217,7 +217,9 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
         const int ch = (warp - 8) >> 2;                     // column half: 16 of every 32-column K-half
         const int r = q * 32 + lane;                        // row in tile == TMEM lane
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-        float* xchg = reinterpret_cast<float*>(sm + OFF_A_HI + q * 4096);   // [32 rows][4] partial heads, inside this pair's own rows of A kb0
+        // partial heads of the row, parked in a 16-byte chunk of A kb0 that the ch = 1 warp itself owns (columns 16..23 of row r):
+        // the training-mode spill above re-reads A, and only a chunk's owner may overwrite it
+        float* xchg = reinterpret_cast<float*>(sm + OFF_A_HI + sw128_offset(r, 16));
         uint32_t acc_uses[2] = {0, 0};
         unsigned long long w_acc = 0;
         const long long e_t0 = clock64();
@@ -244,7 +246,6 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
                     // hand-off granularity = one K-half (32 columns): every warp converts 16 columns of each K-half, so the
                     // MMA of the next layer can start after 1/8 of the epilogue.
                     uint32_t va[16], vb[16];
-                    uint32_t mw[4] = {0u, 0u, 0u, 0u};          // TRAIN: ReLU mask of this thread's 128 columns, 1 bit each
                     tc_ld16_issue(acc_addr, va);
 #pragma unroll
                     for (int kh = 0; kh < 8; ++kh) {
@@ -291,26 +292,44 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(lbar(BAR_A_READY + kh));   // one arrival per warp, on the leader's barrier
                         if (tl && (kh & 1) == 0) trace[148 * 16 + 128 + t * 8 + 1 + (kh >> 1)] = (unsigned long long)clock64();
-                        if (TRAIN) {                                           // h_t (t < 8) or the feature vector (t == 8), after the
-#pragma unroll                                                                 // hand-off: the spill is off the layer-to-layer critical path
-                            for (int j = 0; j < 2; ++j) {
-                                const uint32_t off = (kh >> 1) * KBLOCK_BYTES + sw128_offset(r, (kh & 1) * 32 + ch * 16 + j * 8);
-                                unsigned char* gt = acts.h_tiles + ((size_t)t * (size_t)acts.t_alloc + (size_t)tile) * (8 * KBLOCK_BYTES) + off;
-                                split_store8_bf16_global(v + 8 * j, gt, gt + 4 * KBLOCK_BYTES);
-                            }
-                            if (t < 8) {
-                                uint32_t bits = 0;
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) bits |= (v[j] > 0.0f ? 1u : 0u) << j;
-                                mw[kh >> 1] |= bits << (16 * (kh & 1));
-                                if (kh == 7)
-                                    acts.mask_bits[(((size_t)t * (size_t)acts.t_alloc + (size_t)tile) * TILE_M + r) * 2 + ch] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-                            }
-                        }
                         if (kh < 7) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) bq[j] = bn[j];
                         }
+                    }
+                    if (TRAIN) {
+                        // Spill h_t (t < 8) / the feature vector (t == 8) for the backward pass AFTER the whole layer has been handed
+                        // over, while the tensor core is busy with the next one.  The A tile in shared memory and the bf16 tile in
+                        // global memory have the same layout, so ANY thread can convert ANY 16-byte chunk: the 8 epilogue warps
+                        // walk the 64 KB hi / lo parts in 512-byte spans (fp16 hi + lo = the value to 2^-22 -> bf16 hi / lo), which
+                        // makes both the shared-memory reads and the global stores fully coalesced.  Stored from the hand-off
+                        // loop instead (each thread its own 16-byte pieces, 128 B apart) the stores cost 32 LSU passes per
+                        // instruction and 40 % of the kernel.
+                        named_bar_sync(9, 256);                    // every epilogue warp of this CTA has written its share of A
+                        const int ew = warp - 8;
+                        unsigned char* gt = acts.h_tiles + ((size_t)t * (size_t)acts.t_alloc + (size_t)tile) * (8 * KBLOCK_BYTES);
+                        unsigned char* mk = acts.mask_bits + ((size_t)t * (size_t)acts.t_alloc + (size_t)tile) * 4096;
+#pragma unroll 4
+                        for (int i = 0; i < 16; ++i) {
+                            const uint32_t c = (uint32_t)((i * 8 + ew) * 32 + lane);      // 16-byte chunk of the 64 KB hi (and lo) part
+                            const uint32_t off = c * 16u;
+                            const uint4 hw = *reinterpret_cast<const uint4*>(sm + OFF_A_HI + off);
+                            const uint4 lw = *reinterpret_cast<const uint4*>(sm + OFF_A_LO + off);
+                            const uint32_t hh[4] = {hw.x, hw.y, hw.z, hw.w}, ll[4] = {lw.x, lw.y, lw.z, lw.w};
+                            float v[8];
+                            uint32_t bits = 0;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hh[e]));
+                                const float2 cc = __half22float2(*reinterpret_cast<const __half2*>(&ll[e]));
+                                v[2 * e] = a.x + cc.x; v[2 * e + 1] = a.y + cc.y;
+                                bits |= ((hh[e] & 0x0000ffffu) ? 1u : 0u) << (2 * e);                      // post-ReLU: h > 0 <=> hi half != 0
+                                bits |= ((hh[e] & 0xffff0000u) ? 1u : 0u) << (2 * e + 1);
+                            }
+                            split_store8_bf16_global(v, gt + off, gt + 4 * KBLOCK_BYTES + off);
+                            if (t < 8) mk[c] = (unsigned char)bits;                                       // ReLU mask, 1 bit per activation
+                        }
+                        named_bar_sync(10, 256);                   // ... and nobody overwrites A before all of it has been read
                     }
                 } else {
                     // view layer output (128 cols, 64 per warp of the pair) -> ReLU -> rgb head; write cat([rgb, sigma]) (model/nerf.py:103-110)
@@ -347,12 +366,12 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
                     // combine the two column halves of each row: the upper-half warp parks its partial sums in the pair's own
                     // rows of the (idle between t = 9 and the next tile's first epilogue) A tile, the lower-half warp adds and writes.
                     if (ch == 1) {
-                        *reinterpret_cast<float4*>(xchg + lane * 4) = make_float4(rgb[0], rgb[1], rgb[2], sigma_acc);
+                        *reinterpret_cast<float4*>(xchg) = make_float4(rgb[0], rgb[1], rgb[2], sigma_acc);
                         named_bar_arrive(1 + q, 64);
                         named_bar_sync(5 + q, 64);            // partner has read: the A rows may be overwritten again
                     } else {
                         named_bar_sync(1 + q, 64);
-                        const float4 o = *reinterpret_cast<const float4*>(xchg + lane * 4);
+                        const float4 o = *reinterpret_cast<const float4*>(xchg);
                         named_bar_arrive(5 + q, 64);
                         if (row < rows) {
                             const float sg = sigma_acc + o.w + __ldg(p.b_alpha);
