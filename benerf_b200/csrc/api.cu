@@ -35,6 +35,20 @@ __global__ void pack_all_kernel(const __grid_constant__ PackTable t) {
     }
 }
 
+// wt9m[k][j] = sum_f wt8[k][f] * wt9[f][j];  bias9m[j] = b_views[j] + sum_f b_feature[f] * wt9[f][j]   (block k, thread j;
+// block 256 computes the bias)
+__global__ void merge_views_kernel(const float* __restrict__ wt8 /*[256 k][256 f]*/, const float* __restrict__ wt9 /*[256 f][128 j]*/,
+                                   const float* __restrict__ b_feature, const float* __restrict__ b_views,
+                                   float* __restrict__ wt9m, float* __restrict__ bias9m) {
+    const int k = blockIdx.x, j = threadIdx.x;
+    const float* a = (k < kWidth) ? wt8 + (size_t)k * kWidth : b_feature;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int f = 0; f < kWidth; ++f) acc = fmaf(a[f], wt9[(size_t)f * kHalf + j], acc);
+    if (k < kWidth) wt9m[(size_t)k * kHalf + j] = acc;
+    else bias9m[j] = b_views[j] + acc;
+}
+
 int pack_tc_stream(bnrf_ctx*, int net, cudaStream_t);   // mlp_tc.cu
 
 int alloc_net(bnrf_ctx* ctx, int n) {
@@ -45,8 +59,15 @@ int alloc_net(bnrf_ctx* ctx, int n) {
         BNRF_CUDA(ctx, cudaMemset(np.wt[s], 0, (size_t)gemm_k(s) * gemm_n(s) * sizeof(float)));   // padding rows stay zero for good
         BNRF_CUDA(ctx, cudaMalloc(&np.bias[s], gemm_n(s) * sizeof(float)));
     }
-    BNRF_CUDA(ctx, cudaMalloc(&np.wt_table, 10 * sizeof(float*)));
-    BNRF_CUDA(ctx, cudaMemcpy(np.wt_table, np.wt, 10 * sizeof(float*), cudaMemcpyHostToDevice));
+    BNRF_CUDA(ctx, cudaMalloc(&np.wt9m, (size_t)kWidth * kHalf * sizeof(float)));
+    BNRF_CUDA(ctx, cudaMalloc(&np.bias9m, kHalf * sizeof(float)));
+    {
+        const float* table[11];
+        for (int s = 0; s < 10; ++s) table[s] = np.wt[s];
+        table[10] = np.wt9m;
+        BNRF_CUDA(ctx, cudaMalloc(&np.wt_table, 11 * sizeof(float*)));
+        BNRF_CUDA(ctx, cudaMemcpy(np.wt_table, table, 11 * sizeof(float*), cudaMemcpyHostToDevice));
+    }
     BNRF_CUDA(ctx, cudaMalloc(&np.absmax, 16 * sizeof(unsigned int)));
     BNRF_CUDA(ctx, cudaMemset(np.absmax, 0, 16 * sizeof(unsigned int)));
     BNRF_CUDA(ctx, cudaMalloc(&np.scale, 16 * sizeof(float)));
@@ -70,7 +91,7 @@ void free_net(bnrf_ctx* ctx, int n) {
     for (int s = 0; s < 10; ++s) { cudaFree(np.wt[s]); cudaFree(np.bias[s]); }
     cudaFree(np.w_alpha); cudaFree(np.b_alpha); cudaFree(np.w_rgb); cudaFree(np.b_rgb); cudaFree(np.w_dir);
     cudaFree(np.tc_stream); cudaFree(np.tc2_stream); cudaFree(np.tc_scale); cudaFree(np.dg_img); cudaFree(np.dgc_stream);
-    cudaFree(np.wt_table); cudaFree(np.absmax); cudaFree(np.scale);
+    cudaFree(np.wt_table); cudaFree(np.absmax); cudaFree(np.scale); cudaFree(np.wt9m); cudaFree(np.bias9m);
     memset(&np, 0, sizeof(np));
 }
 
@@ -103,6 +124,8 @@ int pack_weights(bnrf_ctx* ctx, int n, const float* const* w, const float* const
     cp(w[BNRF_L_RGB], C * kHalf, np.w_rgb);
     cp(b[BNRF_L_RGB], C, np.b_rgb);
     pack_all_kernel<<<dim3(16, t.n), 256, 0, st>>>(t);
+    BNRF_LAUNCH_CHECK(ctx);
+    merge_views_kernel<<<kWidth + 1, kHalf, 0, st>>>(np.wt[8], np.wt[9], np.bias[8], np.bias[9], np.wt9m, np.bias9m);
     BNRF_LAUNCH_CHECK(ctx);
     int rc = pack_tc_stream(ctx, n, st);
     if (rc != BNRF_OK) return rc;

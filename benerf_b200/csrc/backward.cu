@@ -218,6 +218,38 @@ __global__ void viewdir_wgrad_kernel(const float* __restrict__ dvb, const float*
     else atomicAdd(dB + j, acc);
 }
 
+// ------------------------------------------------------------------ feature_linear + feature block of views_linears.0
+// The forward pass runs them as one merged linear (common.cuh: wt9m), the backward pass contracts once, G = sum dZ9 (x) h7
+// [128, 256] and s = sum dZ9 [128]; with feature = W_f h7 + b_f:
+//   dW_views[j][f] += sum_k G[j][k] W_f[f][k] + s[j] b_f[f]      (blocks 0..127: j, thread f)
+//   dW_f[f][k]     += sum_j W_v[j][f] G[j][k]                     (blocks 128..383: f, thread k)
+//   dB_f[f]        += sum_j W_v[j][f] s[j]
+// wt8[k][f] = W_f[f][k], wt9[f][j] = W_v[j][f] (the k-major copies of the weight cache).
+__global__ void views_feature_wgrad_kernel(const float* __restrict__ G, const float* __restrict__ s, const float* __restrict__ wt8,
+                                           const float* __restrict__ wt9, const float* __restrict__ b_f,
+                                           float* __restrict__ dW_views /*[128, 283]*/, float* __restrict__ dW_f /*[256, 256]*/,
+                                           float* __restrict__ dB_f) {
+    const int t = threadIdx.x;
+    if (blockIdx.x < kHalf) {
+        const int j = blockIdx.x, f = t;
+        float acc = s[j] * b_f[f];
+#pragma unroll 8
+        for (int k = 0; k < kWidth; ++k) acc = fmaf(G[j * kWidth + k], wt8[(size_t)k * kWidth + f], acc);
+        dW_views[(size_t)j * (kWidth + kDirCh) + f] += acc;
+    } else {
+        const int f = blockIdx.x - kHalf, k = t;
+        float acc = 0.f, bs = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < kHalf; ++j) {
+            const float wv = wt9[(size_t)f * kHalf + j];
+            acc = fmaf(wv, G[j * kWidth + k], acc);
+            bs = fmaf(wv, s[j], bs);
+        }
+        dW_f[(size_t)f * kWidth + k] += acc;
+        if (k == 0) dB_f[f] += bs;
+    }
+}
+
 // ------------------------------------------------------------------ view-direction branch
 // per ray: encoding of the unit view direction (27 values, padded to 32), d enc = dvb * W_dir^T, d view
 __global__ void viewdir_backward_kernel(const float* __restrict__ view, const float* __restrict__ dvb,
@@ -407,16 +439,17 @@ __global__ void rays_backward_kernel(const float* __restrict__ poses, const int6
 // d_raw [rows, C+1] -> parameter gradients (PyTorch layouts, accumulated) and d_pe [rows,64], dvb [n,128].
 struct BwdBuffers {
     float *d_raw, *d_pe, *dz9, *dvb, *pe_dir;
-    unsigned char* dz_tiles;     // 9 bf16 tile matrices of width 256: dZ0..dZ7, d feature
+    unsigned char* dz_tiles;     // 8 bf16 tile matrices of width 256: dZ0..dZ7
+    float* g_views;              // [128, 256] fp32: sum_rows dZ9 (x) h7, from which both merged linears get their gradients
+    float* s_views;              // [128] fp32: sum_rows dZ9
     unsigned char* dz9_tiles;    // bf16 tile matrix of width 128
     int64_t tiles;
 };
 
 // dgrad B operands of one network, in the order the backward pass uses them
 struct DgImage { int step, k0, N, K; };
-static const DgImage kDgImages[11] = {
-    {9, 0, 256, 128},                                  // views_linears.0 (feature block): dZ9 -> d feature
-    {8, 0, 256, 256},                                  // feature_linear: d feature -> d h7
+static const DgImage kDgImages[10] = {
+    {10, 0, 256, 128},                                 // views_linears.0 (feature block) . feature_linear, merged: dZ9 -> d h7
     {7, 0, 256, 256}, {6, 0, 256, 256},
     {5, kPtsChPad, 256, 256}, {5, 0, 64, 256},         // pts_linears.5: h4 block, encoded-points block
     {4, 0, 256, 256}, {3, 0, 256, 256}, {2, 0, 256, 256}, {1, 0, 256, 256},
@@ -427,14 +460,15 @@ static size_t dg_image_offset(int i) {
     for (int j = 0; j < i; ++j) off += bwt::dgrad_image_bytes(kDgImages[j].N, kDgImages[j].K);
     return off;
 }
-size_t dgrad_images_bytes() { return dg_image_offset(11); }
+size_t dgrad_images_bytes() { return dg_image_offset(10); }
 
 static int pack_dgrad_images(bnrf_ctx* ctx, int net, cudaStream_t st) {
     NetParams& np = ctx->net[net];
     bwt::DgImageTable t{};
-    for (int i = 0; i < 11; ++i) {
+    for (int i = 0; i < 10; ++i) {
         const DgImage& d = kDgImages[i];
-        t.seg[t.n++] = bwt::DgImageSeg{np.wt[d.step] + (size_t)d.k0 * d.K, np.dg_img + dg_image_offset(i), d.N, d.K};
+        const float* w = d.step == 10 ? np.wt9m : np.wt[d.step];
+        t.seg[t.n++] = bwt::DgImageSeg{w + (size_t)d.k0 * d.K, np.dg_img + dg_image_offset(i), d.N, d.K};
     }
     int rc = bwt::pack_dgrad_images(ctx, t, st);
     if (rc) return rc;
@@ -451,8 +485,8 @@ static int mlp_backward(bnrf_ctx* ctx, int net, int64_t n, int S, const ActPtrs&
     const int tiles = (int)bwt::tile_count(rows);
     const size_t mat = (size_t)w.tiles * bwt::tile_bytes(kWidth);                       // one gradient tile matrix
     const size_t hmat = (size_t)acts.t_alloc * bwt::tile_bytes(kWidth);                 // one activation tile matrix
-    auto DZ = [&](int l) { return w.dz_tiles + (size_t)l * mat; };                      // l = 0..7, 8 = d feature
-    auto H = [&](int l) { return acts.h_tiles + (size_t)l * hmat; };                    // l = 0..7, 8 = feature
+    auto DZ = [&](int l) { return w.dz_tiles + (size_t)l * mat; };                      // l = 0..7
+    auto H = [&](int l) { return acts.h_tiles + (size_t)l * hmat; };                    // l = 0..7
     int rc;
     if (np.dg_dirty && (rc = pack_dgrad_images(ctx, net, st))) return rc;
     auto dgrad = [&](const unsigned char* A, int K, int img, int epi, const unsigned char* mask, unsigned char* out_tiles, float* out_f32,
@@ -489,15 +523,14 @@ static int mlp_backward(bnrf_ctx* ctx, int net, int64_t n, int S, const ActPtrs&
         if ((rc = launch_dgrad_chain(ctx, net, w.dz9_tiles, acts.mask_bits, acts.t_alloc, w.d_raw + C, C + 1, rows, w.tiles, w.dz_tiles,
                                      w.d_pe, st))) return rc;
     } else {
-        if ((rc = dgrad(w.dz9_tiles, kHalf, 0, bwt::DG_TILE, nullptr, DZ(8), nullptr, nullptr, 0, nullptr))) return rc;
-        if ((rc = dgrad(DZ(8), kWidth, 1, bwt::DG_TILE_MASKED, H(7), DZ(7), nullptr, w.d_raw + C, C + 1, np.w_alpha))) return rc;   // + alpha_linear
-        if ((rc = dgrad(DZ(7), kWidth, 2, bwt::DG_TILE_MASKED, H(6), DZ(6), nullptr, nullptr, 0, nullptr))) return rc;
-        if ((rc = dgrad(DZ(6), kWidth, 3, bwt::DG_TILE_MASKED, H(5), DZ(5), nullptr, nullptr, 0, nullptr))) return rc;
-        if ((rc = dgrad(DZ(5), kWidth, 4, bwt::DG_TILE_MASKED, H(4), DZ(4), nullptr, nullptr, 0, nullptr))) return rc;              // cat([pe, h4]) (model/nerf.py:98)
-        if ((rc = dgrad(DZ(5), kWidth, 5, bwt::DG_F32_STORE, nullptr, nullptr, w.d_pe, nullptr, 0, nullptr))) return rc;
+        if ((rc = dgrad(w.dz9_tiles, kHalf, 0, bwt::DG_TILE_MASKED, H(7), DZ(7), nullptr, w.d_raw + C, C + 1, np.w_alpha))) return rc;   // merged step + alpha_linear
+        if ((rc = dgrad(DZ(7), kWidth, 1, bwt::DG_TILE_MASKED, H(6), DZ(6), nullptr, nullptr, 0, nullptr))) return rc;
+        if ((rc = dgrad(DZ(6), kWidth, 2, bwt::DG_TILE_MASKED, H(5), DZ(5), nullptr, nullptr, 0, nullptr))) return rc;
+        if ((rc = dgrad(DZ(5), kWidth, 3, bwt::DG_TILE_MASKED, H(4), DZ(4), nullptr, nullptr, 0, nullptr))) return rc;              // cat([pe, h4]) (model/nerf.py:98)
+        if ((rc = dgrad(DZ(5), kWidth, 4, bwt::DG_F32_STORE, nullptr, nullptr, w.d_pe, nullptr, 0, nullptr))) return rc;
         for (int l = 4; l >= 1; --l)
-            if ((rc = dgrad(DZ(l), kWidth, 10 - l, bwt::DG_TILE_MASKED, H(l - 1), DZ(l - 1), nullptr, nullptr, 0, nullptr))) return rc;
-        if ((rc = dgrad(DZ(0), kWidth, 10, bwt::DG_F32_ACCUM, nullptr, nullptr, w.d_pe, nullptr, 0, nullptr))) return rc;
+            if ((rc = dgrad(DZ(l), kWidth, 9 - l, bwt::DG_TILE_MASKED, H(l - 1), DZ(l - 1), nullptr, nullptr, 0, nullptr))) return rc;
+        if ((rc = dgrad(DZ(0), kWidth, 9, bwt::DG_F32_ACCUM, nullptr, nullptr, w.d_pe, nullptr, 0, nullptr))) return rc;
     }
     // ---- every 256-wide weight / bias gradient in one launch ----
     bwt::WgradParams p{};
@@ -516,12 +549,17 @@ static int mlp_backward(bnrf_ctx* ctx, int net, int64_t n, int S, const ActPtrs&
             job(DZ(l), kWidth, H(l - 1), kWidth, dW[l], kWidth, 0, kWidth, dB[l]);
         }
     }
-    {
-        bwt::WgradJob* j = job(DZ(8), kWidth, H(7), kWidth, dW[BNRF_L_FEATURE], kWidth, 0, kWidth, dB[BNRF_L_FEATURE]);
+    {   // feature_linear and the feature block of views_linears.0 (merged in the forward pass): ONE contraction
+        // G = sum_rows dZ9 (x) h7, s = sum_rows dZ9; views_feature_wgrad_kernel below turns them into both gradients
+        BNRF_CUDA(ctx, cudaMemsetAsync(w.g_views, 0, (size_t)(kHalf * kWidth + kHalf) * sizeof(float), st));
+        bwt::WgradJob* j = job(w.dz9_tiles, kHalf, H(7), kWidth, w.g_views, kWidth, 0, kWidth, w.s_views);
         j->wrow = w.d_raw + C; j->wrow_stride = C + 1; j->dWv = dW[BNRF_L_ALPHA]; j->dBv = dB[BNRF_L_ALPHA];   // alpha_linear reads the same h7 slices
     }
-    job(w.dz9_tiles, kHalf, H(8), kWidth, dW[BNRF_L_VIEWS], kWidth + kDirCh, 0, kWidth, nullptr);
-    return bwt::launch_tile_wgrad(ctx, p, st);
+    if ((rc = bwt::launch_tile_wgrad(ctx, p, st))) return rc;
+    views_feature_wgrad_kernel<<<kHalf + kWidth, kWidth, 0, st>>>(w.g_views, w.s_views, np.wt[8], np.wt[9], np.bias[8], dW[BNRF_L_VIEWS],
+                                                                  dW[BNRF_L_FEATURE], dB[BNRF_L_FEATURE]);
+    BNRF_LAUNCH_CHECK(ctx);
+    return BNRF_OK;
 }
 
 // ------------------------------------------------------------------ saved-tensor and workspace carve-ups
@@ -542,7 +580,7 @@ SavedLayout carve_saved(const bnrf_cfg& c, int64_t n, void* base) {
         a.pe_f32 = take(rows * kPtsChPad);
         a.h9_f32 = take(rows * kHalf);
         a.pe_tiles = reinterpret_cast<unsigned char*>(take_bytes((size_t)a.t_alloc * bwt::tile_bytes(kPtsChPad)));
-        a.h_tiles = reinterpret_cast<unsigned char*>(take_bytes(9 * (size_t)a.t_alloc * bwt::tile_bytes(kWidth)));
+        a.h_tiles = reinterpret_cast<unsigned char*>(take_bytes(8 * (size_t)a.t_alloc * bwt::tile_bytes(kWidth)));
         a.mask_bits = reinterpret_cast<unsigned char*>(take_bytes(8 * (size_t)a.t_alloc * 4096));
         return a;
     };
@@ -568,7 +606,8 @@ static BwdWorkspace carve_bwd(const bnrf_cfg& c, int64_t n, void* base) {
     const int64_t rows = n * (c.n_samples + c.n_importance);
     w.b.tiles = bwt::tile_count(rows);
     w.b.d_raw = take(rows * (c.channels + 1));
-    w.b.dz_tiles = reinterpret_cast<unsigned char*>(take_bytes(9 * (size_t)w.b.tiles * bwt::tile_bytes(kWidth)));
+    w.b.dz_tiles = reinterpret_cast<unsigned char*>(take_bytes(8 * (size_t)w.b.tiles * bwt::tile_bytes(kWidth)));
+    w.b.g_views = take(kHalf * kWidth + kHalf); w.b.s_views = w.b.g_views + kHalf * kWidth;
     w.b.dz9_tiles = reinterpret_cast<unsigned char*>(take_bytes((size_t)w.b.tiles * bwt::tile_bytes(kHalf)));
     w.b.d_pe = take(rows * kPtsChPad); w.b.dz9 = take(rows * kHalf);
     w.b.dvb = take(n * kHalf); w.b.pe_dir = take(n * 32);

@@ -29,12 +29,17 @@ struct NetParams {
     float* w_rgb;         // [3][128] (rows >= C are zero)
     float* b_rgb;         // [3]
     float* w_dir;         // [27][128]  view-direction block of views_linears.0, transposed
+    // feature_linear has no activation, so it composes with the feature block of views_linears.0 into ONE linear
+    // h7 -> view layer (model/nerf.py:102-105): wt9m[k][j] = sum_f W_feature[f][k] * W_views[j][f], bias9m = b_views +
+    // W_views[:, :256] . b_feature.  The CTA-pair kernel and the backward pass run this merged step (one GEMM less).
+    float* wt9m;          // [256][128] k-major
+    float* bias9m;        // [128]
     // tensor-core stream: fp16 hi/lo tiles in the SW128 K-major shared-memory image,
     // in the exact order the TMA producer consumes them (mlp_tc.cu).
     __half* tc_stream;    // single-CTA kernel (mlp_tc.cu)
     __half* tc2_stream;   // CTA-pair kernel (mlp_tc2.cu): [rank][stage], each CTA's half of the output columns
     float* tc_scale;      // [10] 2^-s per GEMM step undoing the fp16 weight pre-scale
-    const float** wt_table;   // device copy of wt[10] (the packing kernels index it by GEMM step)
+    const float** wt_table;   // device copy of {wt[0..9], wt9m} (the packing kernels index it by GEMM step; 10 = merged)
     unsigned int* absmax;     // device [16] scratch of the per-step max |W| (self-clearing)
     float* scale;             // device [16] 2^s per GEMM step
     // backward pass (bwd_tiles.cu): the 11 dgrad B operands as bf16 hi/lo K-major blocks, packed lazily by the first
@@ -50,7 +55,7 @@ struct ActPtrs {
     float* pe_f32;             // [rows, 64] encoded points, fp32 (encoding backward)
     float* h9_f32;             // [rows, 128] view-layer activations, fp32 (rgb head)
     unsigned char* pe_tiles;   // bf16 hi/lo tile matrix of width 64 (bwd_tiles.cuh)
-    unsigned char* h_tiles;    // 9 bf16 hi/lo tile matrices of width 256: h0..h7, feature; t_alloc tiles each
+    unsigned char* h_tiles;    // 8 bf16 hi/lo tile matrices of width 256: h0..h7; t_alloc tiles each
     unsigned char* mask_bits;  // ReLU masks of h0..h7, 1 bit per activation, laid out like the tiles: [8][t_alloc][4096] bytes,
                                // byte c = the 8 elements of 16-byte chunk c of the tile's hi part (bit e = element e)
     int64_t t_alloc;

@@ -2,11 +2,11 @@
 // (autograd of model/nerf.py:93-112) with the gradient of a 128-sample tile resident on the SM from dZ9 down to the
 // encoded points -- the mirror image of the forward kernel (mlp_tc.cu):
 //
-//   s0  d feature = dZ9 . W_views[:, :256]                       (K = 128, no mask: feature_linear has no activation)
-//   s1  dZ7 = relu'(h7) * (d feature . W_feature + d sigma (x) w_alpha)
-//   s2..s8  dZ_{l-1} = relu'(h_{l-1}) * (dZ_l . W_l)              l = 7..1; at l = 5 only the h4 block of cat([pe, h4]) ...
-//   s4' d pe  = dZ5 . W_5[:, :63]                                 ... and the encoded-points block goes out as fp32
-//   s9  d pe += dZ0 . W_0
+//   s0  dZ7 = relu'(h7) * (dZ9 . (W_views[:, :256] . W_feature) + d sigma (x) w_alpha)   (K = 128; feature_linear has no
+//                                                               activation, so it is merged into the view layer: common.cuh wt9m)
+//   s1..s7  dZ_{l-1} = relu'(h_{l-1}) * (dZ_l . W_l)              l = 7..1; at l = 5 only the h4 block of cat([pe, h4]) ...
+//   s3' d pe  = dZ5 . W_5[:, :63]                                 ... and the encoded-points block goes out as fp32
+//   s8  d pe += dZ0 . W_0
 //
 // Same machinery as the forward kernel: one persistent CTA per SM, A operand (the current dZ, bf16 hi/lo, 3 MMAs per
 // K=16 slice) in shared memory in the SWIZZLE_128B K-major layout and rewritten in place by the epilogue warps, fp32
@@ -45,32 +45,31 @@ __device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t b
 }
 
 // ---- weight stream: stage i = (pass, K-block, K-half, hi/lo) in MMA consumption order ----
-// pass p: 0 = s0, 1..4 = s1..s4, 5 = s4' (encoded-points block of layer 5), 6..9 = s5..s8, 10 = s9
-struct PassInfo { int step /*forward GEMM step whose weights it uses*/, k0, N, K; };
+// pass p: 0 = s0, 1..3 = s1..s3, 4 = s3' (encoded-points block of layer 5), 5..8 = s4..s7, 9 = s8
+struct PassInfo { int step /*slot of the weight table: forward GEMM step, 10 = merged feature + view step*/, k0, N, K; };
 __host__ __device__ inline PassInfo pass_info(int p) {
     switch (p) {
-        case 0: return {9, 0, 256, 128};
-        case 1: return {8, 0, 256, 256};
-        case 2: return {7, 0, 256, 256};
-        case 3: return {6, 0, 256, 256};
-        case 4: return {5, kPtsChPad, 256, 256};
-        case 5: return {5, 0, 64, 256};
-        case 6: return {4, 0, 256, 256};
-        case 7: return {3, 0, 256, 256};
-        case 8: return {2, 0, 256, 256};
-        case 9: return {1, 0, 256, 256};
+        case 0: return {10, 0, 256, 128};
+        case 1: return {7, 0, 256, 256};
+        case 2: return {6, 0, 256, 256};
+        case 3: return {5, kPtsChPad, 256, 256};
+        case 4: return {5, 0, 64, 256};
+        case 5: return {4, 0, 256, 256};
+        case 6: return {3, 0, 256, 256};
+        case 7: return {2, 0, 256, 256};
+        case 8: return {1, 0, 256, 256};
         default: return {0, 0, 64, 256};
     }
 }
-constexpr int NUM_PASSES = 11;
+constexpr int NUM_PASSES = 10;
+constexpr int NUM_STEPS = 9;
 __host__ __device__ inline int pass_stages(int p) { return p == 0 ? 8 : 16; }            // K/64 blocks x 2 halves x (hi, lo)
-__host__ __device__ inline uint32_t pass_stage_bytes(int p) { return (p == 5 || p == 10) ? STAGE_BYTES / 4 : STAGE_BYTES; }
+__host__ __device__ inline uint32_t pass_stage_bytes(int p) { return (p == 4 || p == 9) ? STAGE_BYTES / 4 : STAGE_BYTES; }
 __host__ __device__ inline size_t pass_offset_bytes(int p) {
     size_t off = 0;
     for (int q = 0; q < p; ++q) off += (size_t)pass_stages(q) * pass_stage_bytes(q);
     return off;
 }
-constexpr int STAGES_PER_TILE = 8 + 16 * 10;       // 168
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char* __restrict__ dz9_tiles,
@@ -129,7 +128,7 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
             for (int it = 0; it < my_tiles; ++it) {
                 const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
                 mbar_wait(bar(BAR_A_FREE), ((uint32_t)it & 1u) ^ 1u, err_flag, 52);       // last MMAs of the previous tile have read A
-                if (it > 0) mbar_wait(bar(BAR_SPILLED), ((uint32_t)(it - 1) * 9u + 8u) & 1u, err_flag, 58);   // ... and its dZ0 has been copied out
+                if (it > 0) mbar_wait(bar(BAR_SPILLED), ((uint32_t)(it - 1) * 8u + 7u) & 1u, err_flag, 58);   // ... and its dZ0 has been copied out
                 const unsigned char* src = dz9_tiles + (size_t)tile * bwt::tile_bytes(kHalf);
                 mbar_expect_tx(bar(BAR_A0_FULL), 4u * KBLOCK_BYTES);
                 tma_bulk_load(base + OFF_A_HI, src, 2u * KBLOCK_BYTES, bar(BAR_A0_FULL));
@@ -144,8 +143,8 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
             uint32_t sgen = 0;
             for (int it = 0; it < my_tiles; ++it) {
                 const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
-                for (int s = 0; s < 9; ++s, ++sgen) {
-                    unsigned char* gt = dz_tiles + (size_t)(8 - s) * dz_mat + (size_t)tile * bwt::tile_bytes(kWidth);
+                for (int s = 0; s < NUM_STEPS - 1; ++s, ++sgen) {
+                    unsigned char* gt = dz_tiles + (size_t)(7 - s) * dz_mat + (size_t)tile * bwt::tile_bytes(kWidth);
                     for (int kb = 0; kb < 4; ++kb) {
                         mbar_wait(bar(BAR_A_READY + 2 * kb), sgen & 1u, err_flag, 59);
                         mbar_wait(bar(BAR_A_READY + 2 * kb + 1), sgen & 1u, err_flag, 60);
@@ -195,9 +194,10 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
             const uint32_t idesc256 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
             const uint32_t idesc64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
             for (int it = 0; it < my_tiles; ++it) {
-                for (int s = 0; s < 10; ++s) {
-                    const uint32_t d_tmem = tmem + (uint32_t)(s & 1) * 256u;
-                    const uint32_t idesc = (s == 9) ? idesc64 : idesc256;
+                for (int s = 0; s < NUM_STEPS; ++s) {
+                    const uint32_t accb = ((uint32_t)it * NUM_STEPS + (uint32_t)s) & 1u;      // accumulators alternate over ALL steps (9 per tile: odd)
+                    const uint32_t d_tmem = tmem + accb * 256u;
+                    const uint32_t idesc = (s == NUM_STEPS - 1) ? idesc64 : idesc256;
                     const int n_kb = (s == 0) ? 2 : 4;
                     uint32_t accumulate = 0;
                     if (s == 0) { mbar_wait(bar(BAR_A0_FULL), (uint32_t)it & 1u, err_flag, 55); tc_fence_after(); }
@@ -206,15 +206,15 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
                             if (s > 0) { mbar_wait(bar(BAR_A_READY + kb * 2 + hk), agen & 1u, err_flag, 56); tc_fence_after(); }
                             kblock(d_tmem, idesc, kb, hk, accumulate);
                         }
-                    if (s == 4) {
+                    if (s == 3) {
                         // encoded-points block of layer 5 from the same dZ5, into the first 64 columns of the OTHER buffer: its last
-                        // reader (the epilogue of s3) finished before A_READY[7] above, and the epilogue of s4 drains it first
+                        // reader (the epilogue of s2) finished before A_READY[7] above, and the epilogue of s3 drains it first
                         uint32_t acc2 = 0;
                         for (int kb = 0; kb < 4; ++kb)
-                            for (int hk = 0; hk < 2; ++hk) kblock(tmem + 256u, idesc64, kb, hk, acc2);
+                            for (int hk = 0; hk < 2; ++hk) kblock(tmem + (accb ^ 1u) * 256u, idesc64, kb, hk, acc2);
                     }
-                    tc_commit(bar(BAR_ACC_FULL + (s & 1)));
-                    if (s == 9) tc_commit(bar(BAR_A_FREE));
+                    tc_commit(bar(BAR_ACC_FULL + accb));
+                    if (s == NUM_STEPS - 1) tc_commit(bar(BAR_A_FREE));
                     if (s >= 1) ++agen;
                 }
             }
@@ -231,36 +231,36 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
             const int64_t row = tile * TILE_M + r;
             const bool live = row < rows;
             float* pe_row = d_pe + row * kPtsChPad + ch * 32;
-            for (int s = 0; s < 10; ++s) {
-                const int b = s & 1;
+            for (int s = 0; s < NUM_STEPS; ++s) {
+                const int b = (int)(((uint32_t)it * NUM_STEPS + (uint32_t)s) & 1u);
                 // fetched BEFORE blocking on the accumulator (no L1 behind the smem carve-out: these are L2 round trips)
                 // ReLU mask of this row: byte p of word kb = the 8 elements of physical 16-byte chunk p of K-block kb (mlp_tc2.cu)
                 unsigned long long mrow[4] = {~0ull, ~0ull, ~0ull, ~0ull};
-                if (s >= 1 && s <= 8) {
-                    const unsigned char* mk = mask_bits + ((size_t)(8 - s) * (size_t)t_alloc + (size_t)tile) * 4096 + (size_t)r * 8;
+                if (s < NUM_STEPS - 1) {
+                    const unsigned char* mk = mask_bits + ((size_t)(7 - s) * (size_t)t_alloc + (size_t)tile) * 4096 + (size_t)r * 8;
 #pragma unroll
                     for (int kb = 0; kb < 4; ++kb) mrow[kb] = __ldg(reinterpret_cast<const unsigned long long*>(mk + kb * 1024));
                 }
-                const float rr = (s == 1 && live) ? __ldg(d_sigma + row * d_sigma_stride) : 0.0f;
+                const float rr = (s == 0 && live) ? __ldg(d_sigma + row * d_sigma_stride) : 0.0f;
                 float4 wq[4];
-                if (s == 1) {
+                if (s == 0) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) wq[j] = __ldg(reinterpret_cast<const float4*>(w_alpha + ch * 16) + j);
                 }
                 mbar_wait(bar(BAR_ACC_FULL + b), acc_uses[b] & 1u, err_flag, 57);
                 ++acc_uses[b];
                 tc_fence_after();
-                if (s == 4) {           // d pe from layer 5, parked in the other buffer
+                if (s == 3) {           // d pe from layer 5, parked in the other buffer
                     float v[32];
-                    tc_ld32(lane_addr + 256u + (uint32_t)ch * 32u, v);
+                    tc_ld32(lane_addr + (uint32_t)(b ^ 1) * 256u + (uint32_t)ch * 32u, v);
                     if (live) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(pe_row)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
                 }
-                if (s < 9) {
+                if (s < NUM_STEPS - 1) {
                     const uint32_t acc_addr = lane_addr + (uint32_t)b * 256u + (uint32_t)ch * 16u;
-                    if (s >= 1) mbar_wait(bar(BAR_SPILLED), ((uint32_t)it * 9u + (uint32_t)(s - 1)) & 1u, err_flag, 61);   // A (= dZ of step s-1) copied out
+                    if (s >= 1) mbar_wait(bar(BAR_SPILLED), ((uint32_t)it * 8u + (uint32_t)(s - 1)) & 1u, err_flag, 61);   // A (= dZ of step s-1) copied out
                     uint32_t va[16], vb[16];
                     tc_ld16_issue(acc_addr, va);
 #pragma unroll
@@ -271,7 +271,7 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
                         float4 wn[4];
                         if (kh < 7) {
                             tc_ld16_issue(acc_addr + (kh + 1) * 32, nxt);
-                            if (s == 1) {
+                            if (s == 0) {
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) wn[j] = __ldg(reinterpret_cast<const float4*>(w_alpha + ch * 16 + (kh + 1) * 32) + j);
                             }
@@ -279,7 +279,7 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
                         float v[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(cur[j]);
-                        if (s == 1) {   // + d sigma (x) w_alpha (alpha_linear reads h7, model/nerf.py:101)
+                        if (s == 0) {   // + d sigma (x) w_alpha (alpha_linear reads h7, model/nerf.py:101)
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) {
                                 const float4 wv = wq[j >> 2];
@@ -306,7 +306,7 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
                         tc_fence_before();
                         fence_proxy_async();
                         mbar_arrive(bar(BAR_A_READY + kh));
-                        if (s == 1 && kh < 7) {
+                        if (s == 0 && kh < 7) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) wq[j] = wn[j];
                         }

@@ -395,8 +395,8 @@ __host__ __device__ inline StageInfo stage_info(int i) {
 
 // absmax[t] = max |wt[t]| (as uint bits; non-negative floats order like their bit patterns); blockIdx.y = GEMM step
 __global__ void absmax_kernel(const float* const* __restrict__ wt, unsigned int* out) {
-    const int t = blockIdx.y;
-    const int n = (t == 0 ? 64 : (t == 5 ? 320 : 256)) * (t == 9 ? 128 : 256);
+    const int t = blockIdx.y;                         // 0..9 = GEMM steps, 10 = the merged feature + view step (256 x 128)
+    const int n = (t == 0 ? 64 : (t == 5 ? 320 : 256)) * (t >= 9 ? 128 : 256);
     const float* w = wt[t];
     float m = 0.0f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
@@ -406,7 +406,7 @@ __global__ void absmax_kernel(const float* const* __restrict__ wt, unsigned int*
 // scale[t] = 2^s with max|W| * 2^s in [1024, 2048); inv_scale[t] = 2^-s.  Clears absmax for the next repack.
 __global__ void scale_kernel(unsigned int* __restrict__ absmax, float* __restrict__ scale, float* __restrict__ inv_scale) {
     const int t = threadIdx.x;
-    if (t >= 10) return;
+    if (t >= 11) return;
     const float m = __uint_as_float(absmax[t]);
     absmax[t] = 0u;
     int s = 0;
@@ -437,7 +437,7 @@ size_t tc_stream_halfs() { return tc::stage_offset_bytes(tc::STAGES_PER_TILE) / 
 int pack_tc_stream(bnrf_ctx* ctx, int net, cudaStream_t st) {
     using namespace tc;
     NetParams& np = ctx->net[net];
-    absmax_kernel<<<dim3(8, 10), 256, 0, st>>>(np.wt_table, np.absmax);
+    absmax_kernel<<<dim3(8, 11), 256, 0, st>>>(np.wt_table, np.absmax);
     scale_kernel<<<1, 32, 0, st>>>(np.absmax, np.scale, np.tc_scale);
     BNRF_LAUNCH_CHECK(ctx);
     // only the stream of the configured kernel is rebuilt (this runs after every optimiser step)

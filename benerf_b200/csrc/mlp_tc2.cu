@@ -38,8 +38,9 @@ constexpr uint32_t OFF_PE_LO = 9 * KBLOCK_BYTES;
 constexpr uint32_t OFF_W = 10 * KBLOCK_BYTES;
 constexpr uint32_t OFF_BAR = OFF_W + NS * STAGE_BYTES;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
-constexpr int STAGES_PER_TILE = 76;                // 38 K-blocks x (hi, lo)
-constexpr int N256_STAGES = 68;                    // stages of the nine 256-wide steps; the view layer's 8 stages are half size
+constexpr int NUM_STEPS = 9;                       // L0..L7, then feature_linear and the view layer merged into one (common.cuh: wt9m)
+constexpr int STAGES_PER_TILE = 68;                // 34 K-blocks x (hi, lo)
+constexpr int N256_STAGES = 60;                    // stages of the eight 256-wide steps; the view layer's 8 stages are half size
 constexpr uint32_t TMEM_COLS = 512;
 
 enum { BAR_W_FULL = 0, BAR_W_EMPTY = BAR_W_FULL + NS, BAR_PE_FULL = BAR_W_EMPTY + NS, BAR_PE_EMPTY,
@@ -149,10 +150,11 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
             unsigned long long w_pe = 0, w_a = 0, w_w = 0;
             const long long m_t0 = clock64();
             for (int it = 0; it < my_iters; ++it) {
-                for (int t = 0; t < 10; ++t) {
-                    const int N = (t == 9) ? 128 : 256;
+                for (int t = 0; t < NUM_STEPS; ++t) {
+                    const int N = (t == NUM_STEPS - 1) ? 128 : 256;
+                    const uint32_t accb = ((uint32_t)it * NUM_STEPS + (uint32_t)t) & 1u;   // accumulators alternate over ALL steps (9 per tile: odd)
                     const uint32_t idesc = make_idesc(2 * TILE_M, N);
-                    const uint32_t d_tmem = tmem + (uint32_t)(t & 1) * 256u;
+                    const uint32_t d_tmem = tmem + accb * 256u;
                     const bool has_pe = (t == 0 || t == 5);
                     const int n_act = (t == 0) ? 0 : 4;
                     uint32_t accumulate = 0;
@@ -201,9 +203,9 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
                         }
                         if (kb < 0 && t == 5) tc_commit_pair(bar(BAR_PE_EMPTY));   // encoded tiles no longer needed
                     }
-                    tc_commit_pair(bar(BAR_ACC_FULL + (t & 1)));
+                    tc_commit_pair(bar(BAR_ACC_FULL + accb));
                     if (trace && blockIdx.x == 0 && it == 5) trace[148 * 16 + t * 8 + 5] = (unsigned long long)clock64();
-                    if (t >= 1) ++agen;                                        // steps 1..9 each consumed one generation
+                    if (t >= 1) ++agen;                                        // steps 1..8 each consumed one generation
                 }
             }
             if (trace) {
@@ -227,12 +229,12 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
             const int64_t tile = tile_of(it);
             const int64_t row = tile * TILE_M + r;
             float sigma_acc = 0.0f;
-            for (int t = 0; t < 10; ++t) {
-                const int b = t & 1;
+            for (int t = 0; t < NUM_STEPS; ++t) {
+                const int b = (int)(((uint32_t)it * NUM_STEPS + (uint32_t)t) & 1u);
                 // the smem carve-out leaves no L1: every __ldg is an L2 round trip, so the per-layer constants of the first
                 // chunk are fetched BEFORE blocking on the accumulator and later chunks prefetch one chunk ahead
-                const float inv_scale = __ldg(p.inv_scale + t);
-                const float* bias = p.bias[t < 9 ? t : 0] + ch * 16;
+                const float inv_scale = __ldg(p.inv_scale + (t == NUM_STEPS - 1 ? 10 : t));      // slot 10 = the merged step
+                const float* bias = p.bias[t < 8 ? t : 0] + ch * 16;
                 float4 bq[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(bias) + j);
@@ -241,8 +243,8 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
                 tc_fence_after();
                 const bool tl = trace && blockIdx.x == 0 && it == 5 && threadIdx.x == 256;
                 if (tl) trace[148 * 16 + 128 + t * 8 + 0] = (unsigned long long)clock64();
-                const uint32_t acc_addr = lane_addr + (uint32_t)b * 256u + (uint32_t)ch * (t < 9 ? 16u : 32u);
-                if (t < 9) {
+                const uint32_t acc_addr = lane_addr + (uint32_t)b * 256u + (uint32_t)ch * (t < 8 ? 16u : 32u);
+                if (t < 8) {
                     // hand-off granularity = one K-half (32 columns): every warp converts 16 columns of each K-half, so the
                     // MMA of the next layer can start after 1/8 of the epilogue.
                     uint32_t va[16], vb[16];
@@ -269,10 +271,8 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
                             v[j + 2] = fmaf(__uint_as_float(cur[j + 2]), inv_scale, bv.z);
                             v[j + 3] = fmaf(__uint_as_float(cur[j + 3]), inv_scale, bv.w);
                         }
-                        if (t != 8) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);                             // ReLU
-                        }
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);                                 // ReLU
                         if (t == 7) {                                          // sigma head on h7 (model/nerf.py:101)
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) {
@@ -298,7 +298,7 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
                         }
                     }
                     if (TRAIN) {
-                        // Spill h_t (t < 8) / the feature vector (t == 8) for the backward pass AFTER the whole layer has been handed
+                        // Spill h_t for the backward pass AFTER the whole layer has been handed
                         // over, while the tensor core is busy with the next one.  The A tile in shared memory and the bf16 tile in
                         // global memory have the same layout, so ANY thread can convert ANY 16-byte chunk: the 8 epilogue warps
                         // walk the 64 KB hi / lo parts in 512-byte spans (fp16 hi + lo = the value to 2^-22 -> bf16 hi / lo), which
@@ -327,7 +327,7 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
                                 bits |= ((hh[e] & 0xffff0000u) ? 1u : 0u) << (2 * e + 1);
                             }
                             split_store8_bf16_global(v, gt + off, gt + 4 * KBLOCK_BYTES + off);
-                            if (t < 8) mk[c] = (unsigned char)bits;                                       // ReLU mask, 1 bit per activation
+                            mk[c] = (unsigned char)bits;                                                  // ReLU mask, 1 bit per activation
                         }
                         named_bar_sync(10, 256);                   // ... and nobody overwrites A before all of it has been read
                     }
@@ -460,16 +460,17 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
 struct StageInfo { int step, k0, nh, lo; };
 __host__ __device__ inline StageInfo stage_info(int i) {
     int kbi = i >> 1, lo = i & 1, t = 0;
-    const int kbs[10] = {1, 4, 4, 4, 4, 5, 4, 4, 4, 4};
+    const int kbs[NUM_STEPS] = {1, 4, 4, 4, 4, 5, 4, 4, 4};
     while (kbi >= kbs[t]) { kbi -= kbs[t]; ++t; }
-    return {t, kbi * 64, t == 9 ? 64 : 128, lo};           // wt[t] rows are already ordered [pe64 | h256]
+    return {t, kbi * 64, t == NUM_STEPS - 1 ? 64 : 128, lo};   // wt[t] rows are already ordered [pe64 | h256]; step 8 = merged
 }
 
 __global__ void pack_stream_kernel(const float* const* __restrict__ wt, const float* __restrict__ scale, __half* __restrict__ stream) {
     const int i = blockIdx.x, rank = blockIdx.y;
     const StageInfo si = stage_info(i);
-    const float* w = wt[si.step];
-    const float sc = scale[si.step];
+    const int ti = si.step == NUM_STEPS - 1 ? 10 : si.step;      // table slot 10 = the merged feature + view step (common.cuh)
+    const float* w = wt[ti];
+    const float sc = scale[ti];
     const int N = 2 * si.nh;
     unsigned char* dst = reinterpret_cast<unsigned char*>(stream) + (size_t)rank * rank_stream_bytes() + stage_offset_bytes(i);
     for (int e = threadIdx.x; e < si.nh * 64; e += blockDim.x) {

@@ -134,7 +134,9 @@ int launch_stratified(bnrf_ctx* ctx, const float* t_rand, const bnrf_rng* rng, i
 
 int launch_viewbias(bnrf_ctx* ctx, int net, const float* view, int64_t n, float* vb, cudaStream_t st) {
     const NetParams& np = ctx->net[net];
-    viewbias_kernel<<<(unsigned)ceil_div(n, 4), 128, 0, st>>>(view, np.w_dir, np.bias[9], n, vb);
+    // the CTA-pair kernel runs feature_linear merged into the view layer: its per-ray bias carries W_views . b_feature too
+    const float* bias = ctx->cfg.mlp_mode == BNRF_MLP_TC_FP16X2 ? np.bias9m : np.bias[9];
+    viewbias_kernel<<<(unsigned)ceil_div(n, 4), 128, 0, st>>>(view, np.w_dir, bias, n, vb);
     BNRF_LAUNCH_CHECK(ctx);
     return BNRF_OK;
 }
