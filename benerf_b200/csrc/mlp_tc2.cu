@@ -19,6 +19,9 @@
 //   A_READY[8], PE_FULL   on the leader only: one elected-lane arrival per producing warp of BOTH
 //                  CTAs (mapa + mbarrier.arrive.release.cluster), 16 resp. 8 per phase
 //
+// Nine GEMM steps per tile, not ten: feature_linear has no activation, so it is composed with the feature block of
+// views_linears.0 into one 256 -> 128 linear when the weights are packed (common.cuh: wt9m, bias9m); step 8 reads h7.
+//
 // Replaces model/embedder.py:9-34 + model/nerf.py:67-116.
 #include "tc_ptx.cuh"
 

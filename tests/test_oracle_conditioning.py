@@ -50,3 +50,30 @@ def test_fine_outputs_follow_the_same_split():
     err_sig = (outs[0]["sigma"] - outs[1]["sigma"]).abs().amax(-1)
     assert err_rgb[well].max() < 1e-5 and err_sig[well].max() < 1e-4
     assert err_sig[~well].max() > 1e-4
+
+
+def test_feature_linear_composes_with_the_view_layer():
+    """feature_linear has no activation (model/nerf.py:102-105), so views_linears.0(cat([feature_linear(h), dirs])) is ONE
+    linear map of cat([h, dirs]): W_m = W_views[:, :256] @ W_feature, b_m = b_views + W_views[:, :256] @ b_feature.  The CUDA
+    engine runs that merged step (csrc/common.cuh: wt9m); this pins the algebra, in fp32, on the fixtures' own weights:
+    the two evaluation orders agree to ~1e-6, two orders of magnitude inside the 1e-4 parity bound."""
+    import torch.nn.functional as F
+    from tests.cases import CASES, make_inputs
+    for name in ("unreal_rgb", "gray_linear"):
+        p = make_inputs(CASES[name])["coarse"]
+        g = torch.Generator().manual_seed(3)
+        h = torch.relu(torch.randn(4096, 256, generator=g))
+        d = torch.randn(4096, 27, generator=g).clamp(-1, 1)
+        feat = F.linear(h, p["feature_linear.weight"], p["feature_linear.bias"])
+        want = torch.relu(F.linear(torch.cat([feat, d], -1), p["views_linears.0.weight"], p["views_linears.0.bias"]))
+        wv, wd = p["views_linears.0.weight"][:, :256], p["views_linears.0.weight"][:, 256:]
+        w_m = wv @ p["feature_linear.weight"]
+        b_m = p["views_linears.0.bias"] + wv @ p["feature_linear.bias"]
+        got = torch.relu(F.linear(h, w_m, b_m) + F.linear(d, wd))
+        assert float((got - want).abs().max()) < 5e-6
+        # and in float64 the identity is exact to rounding of the inputs
+        got64 = torch.relu(F.linear(h.double(), (wv.double() @ p["feature_linear.weight"].double()),
+                                    p["views_linears.0.bias"].double() + wv.double() @ p["feature_linear.bias"].double()) + F.linear(d.double(), wd.double()))
+        want64 = torch.relu(F.linear(torch.cat([F.linear(h.double(), p["feature_linear.weight"].double(), p["feature_linear.bias"].double()), d.double()], -1),
+                                     p["views_linears.0.weight"].double(), p["views_linears.0.bias"].double()))
+        assert float((got64 - want64).abs().max()) < 1e-12

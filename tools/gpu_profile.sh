@@ -11,9 +11,12 @@ echo "launch list exit $?"
 timeout 1200 $NCU --set full --clock-control none --import-source on -k regex:mlp_tc2_kernel -s 3 -c 1 -f -o gpurun_out/prof_mlp_tc2_bench \
     python bench.py --steps 1 --warmup 1 --pixels $PIX --no-cpu-baseline --no-train-step > gpurun_out/prof_mlp_bench.log 2>&1
 echo "mlp full capture exit $?"
-# 3) the backward pass's tile kernels inside one training step (first dgrad launches + the wgrad launch of one network)
-timeout 900 $NCU --set full --clock-control none --import-source on -k regex:tile_ -s 24 -c 14 -f -o gpurun_out/prof_bwd_tiles \
+# 3) the backward pass's tensor-core kernels inside one training step (chain + wgrad of the event render's fine network)
+timeout 900 $NCU --set full --clock-control none --import-source on -k regex:"dgrad_chain|tile_wgrad|mlp_tc2" -s 4 -c 4 -f -o gpurun_out/prof_bwd_tiles \
     python bench.py --mode train --steps 1 --warmup 1 > gpurun_out/prof_bwd.log 2>&1
+# 4) launch list of one training step
+timeout 600 $NCU --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_train.csv \
+    python bench.py --mode train --steps 2 --warmup 1 > gpurun_out/launches_train.log 2>&1
 echo "backward full capture exit $?"
 for r in prof_mlp_tc2_bench prof_bwd_tiles; do
   python tools/ncu_key_metrics.py gpurun_out/$r.ncu-rep > gpurun_out/$r.csv 2>/dev/null
