@@ -186,22 +186,40 @@ __global__ void sum_samples_kernel(const float* __restrict__ dz9, int S, float* 
 template <int C>
 __global__ void rgb_head_wgrad_kernel(const float* __restrict__ d_raw, const float* __restrict__ h9, int64_t rows,
                                       int64_t rows_per_block, float* __restrict__ dW, float* __restrict__ dB) {
-    const int j = threadIdx.x;
+    // 256 threads = two interleaved row groups x 128 columns; the loop is a chain of dependent FMAs on L2-latency loads, so it
+    // is unrolled 8x (8 rows in flight per thread) and the grid is sized for ~4 blocks per SM
+    __shared__ float part[(C + 1) * kHalf];
+    const int j = threadIdx.x & (kHalf - 1), grp = threadIdx.x >> 7;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
     float acc[C], bs = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 0.f;
-#pragma unroll 4
-    for (int64_t row = r0; row < r1; ++row) {
+#pragma unroll 8
+    for (int64_t row = r0 + grp; row < r1; row += 2) {
         const float h = h9[row * kHalf + j];
+        float g[C];
+        if (C == 3) {
+            const float4 q = *reinterpret_cast<const float4*>(d_raw + row * 4);
+            g[0] = q.x; g[1 % C] = q.y; g[2 % C] = q.z;
+        } else {
+            g[0] = d_raw[row * (C + 1)];
+        }
 #pragma unroll
-        for (int c = 0; c < C; ++c) acc[c] = fmaf(d_raw[row * (C + 1) + c], h, acc[c]);
-        if (j < C) bs += d_raw[row * (C + 1) + j];
+        for (int c = 0; c < C; ++c) acc[c] = fmaf(g[c], h, acc[c]);
+        if (j < C) bs += (j == 0) ? g[0] : (j == 1 ? g[1 % C] : g[2 % C]);
     }
+    if (grp == 1) {
 #pragma unroll
-    for (int c = 0; c < C; ++c) atomicAdd(dW + c * kHalf + j, acc[c]);
-    if (j < C) atomicAdd(dB + j, bs);
+        for (int c = 0; c < C; ++c) part[c * kHalf + j] = acc[c];
+        part[C * kHalf + j] = bs;
+    }
+    __syncthreads();
+    if (grp == 0) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) atomicAdd(dW + c * kHalf + j, acc[c] + part[c * kHalf + j]);
+        if (j < C) atomicAdd(dB + j, bs + part[C * kHalf + j]);
+    }
 }
 
 // ------------------------------------------------------------------ views_linears.0: direction block and bias
@@ -508,10 +526,11 @@ static int mlp_backward(bnrf_ctx* ctx, int net, int64_t n, int S, const ActPtrs&
         BNRF_LAUNCH_CHECK(ctx);
     }
     {   // rgb_linear weight + bias gradient
-        const int64_t blocks = rows < 4096 ? 1 : (ceil_div(rows, 1024) < 4 * ctx->sm_count ? ceil_div(rows, 1024) : 4 * ctx->sm_count);
+        const int64_t want = ceil_div(rows, 256), cap = 4 * (int64_t)ctx->sm_count;
+        const int64_t blocks = want < cap ? want : cap;
         const int64_t rpb = ceil_div(rows, blocks);
-        if (C == 3) rgb_head_wgrad_kernel<3><<<(unsigned)blocks, kHalf, 0, st>>>(w.d_raw, h9, rows, rpb, dW[BNRF_L_RGB], dB[BNRF_L_RGB]);
-        else rgb_head_wgrad_kernel<1><<<(unsigned)blocks, kHalf, 0, st>>>(w.d_raw, h9, rows, rpb, dW[BNRF_L_RGB], dB[BNRF_L_RGB]);
+        if (C == 3) rgb_head_wgrad_kernel<3><<<(unsigned)blocks, 2 * kHalf, 0, st>>>(w.d_raw, h9, rows, rpb, dW[BNRF_L_RGB], dB[BNRF_L_RGB]);
+        else rgb_head_wgrad_kernel<1><<<(unsigned)blocks, 2 * kHalf, 0, st>>>(w.d_raw, h9, rows, rpb, dW[BNRF_L_RGB], dB[BNRF_L_RGB]);
         BNRF_LAUNCH_CHECK(ctx);
     }
     // ---- views_linears.0: per-ray sum of dZ9 (the view bias is shared by the S samples of a ray) ----
