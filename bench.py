@@ -133,6 +133,33 @@ def run_cpu_oracle(n_pixels, repeats=1):
     return rays / best, rays, best
 
 
+def run_cpu_oracle_train(n_evt, n_rgb):
+    """Forward + backward of one training iteration (configs[2] shape, scaled down) on the host CPU with the oracle under
+    torch autograd -- what train.py:160-340 costs per ray on the reference's CPU path.  Returns (rays/s, rays, seconds)."""
+    from oracle import pose, render as orender, image_formation as oif, mlp as omlp
+    g = torch.Generator().manual_seed(0)
+    Ht = Wt = 800
+    K = torch.tensor([[1111.111, 0.0, 400.0], [0.0, 1111.111, 400.0], [0.0, 0.0, 1.0]])
+    coarse = {k: v.requires_grad_(True) for k, v in omlp.xavier_params(CH, g).items()}
+    fine = {k: v.requires_grad_(True) for k, v in omlp.xavier_params(CH, g).items()}
+    knots = (torch.rand(4, 6, generator=g) * 0.01).requires_grad_(True)
+    transform = torch.zeros(1, 6, requires_grad=True)
+    idx_evt = torch.randint(0, Ht * Wt, (n_evt,), generator=g)
+    idx_rgb = torch.randint(0, Ht * Wt, (n_rgb,), generator=g)
+    accu = torch.randint(-3, 4, (Ht, Wt), generator=g).double()
+    blur_t = torch.rand(n_rgb, CH, generator=g)
+    t0 = time.perf_counter()
+    p_evt = pose.poses_from_knots(knots, None, *WINDOW, 2)
+    p_rgb = pose.poses_from_knots(knots, transform, *EXPOSURE, N_POSES)
+    r_evt = orender.render(coarse, fine, p_evt, idx_evt, Ht, Wt, K, orender.draw_rng(2 * n_evt, S_C, N_I, g))
+    r_rgb = orender.render(coarse, fine, p_rgb, idx_rgb, Ht, Wt, K, orender.draw_rng(N_POSES * n_rgb, S_C, N_I, g))
+    loss, _ = oif.training_loss(r_evt, r_rgb, accu, idx_evt, blur_t, n_poses=N_POSES, dataset="E2NeRF_Synthetic", channels=CH, threshold=0.2)
+    loss.backward()
+    dt = time.perf_counter() - t0
+    rays = 2 * n_evt + N_POSES * n_rgb
+    return rays / dt, rays, dt
+
+
 def bench_reference(opts):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -427,6 +454,11 @@ def bench_ours(opts):
         rps, rays, dt = run_cpu_oracle(opts.cpu_pixels)
         cpu = {"value": rps, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{opts.cpu_pixels} pixels x 21 poses = {rays} rays, one step, {dt:.1f} s, oracle/ (torch CPU fp32)"}
+    if cpu is not None and train is not None:
+        run_cpu_oracle_train(8, 1)
+        rps, rays, dt = run_cpu_oracle_train(256, 27)          # 1/4 of the configs[2] batch: 512 + 513 rays
+        train["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+                                 "sample": f"{rays} rays, forward + backward once, {dt:.1f} s, oracle/ under torch autograd (CPU fp32)"}
     if rank == 0:
         h2d = sum(t.numel() * t.element_size() for t in (host_idx_evt, host_idx_rgb, host_target_blur, host_target_evt))
         d2h = 4 * 4 + R * CH * 4 + R * 4

@@ -66,3 +66,20 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions(lib):
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP"):
         assert mnemonic in sass, mnemonic
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/benerf_b200.h must compile as C (no C++ types, no torch)."""
+    import subprocess
+    r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "benerf_b200.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_bulk_store_and_tile_kernels_are_in_the_library(lib):
+    """The backward pass's kernels are part of the shipped .so (no torch / cuBLAS fallback for dgrad / wgrad)."""
+    import subprocess
+    from benerf_b200 import _lib
+    names = subprocess.run(["cuobjdump", "-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for k in ("dgrad_chain_kernel", "tile_wgrad_kernel", "tile_dgrad_kernel", "mlp_tc2_kernel", "adam_step_kernel"):
+        assert k in names, k
