@@ -1,4 +1,6 @@
-"""Checkpoint compatibility of the mirror modules: benerf_b200.optimize.Model(args).build_network(args)
+"""Drop-in compatibility of the mirror modules: checkpoint keys and call signatures.
+
+Checkpoint compatibility: benerf_b200.optimize.Model(args).build_network(args)
 must own the reference Graph's 59 tensors under the same names and shapes, so that `{iter:06d}.tar` checkpoints written
 by train.py:443-455 load into either implementation (graph.load_state_dict, test.py:101).  No GPU needed: parameter
 holders are plain nn.Modules; the arithmetic lives in the CUDA library."""
@@ -78,3 +80,45 @@ def test_state_dict_round_trips_with_the_reference(monkeypatch):
     assert {k: tuple(v.shape) for k, v in ref_sd.items()} == {k: tuple(v.shape) for k, v in ours.state_dict().items()}
     ours.load_state_dict(ref_sd, strict=True)
     ref.load_state_dict({k: v.detach().cpu() for k, v in ours.state_dict().items()}, strict=True)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/model"), reason="reference tree not present (GPU box)")
+def test_call_signatures_match_the_reference(monkeypatch):
+    """every callable train.py / test.py / run_nerf_helpers.py reach keeps its parameter names and order
+    (extra keyword-only / defaulted parameters of the mirror are allowed at the end)."""
+    import inspect
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: False)
+    for name in ("h5py", "hdf5plugin", "imageio", "imageio.v3"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.File = m.imwrite = m.imread = None
+            monkeypatch.setitem(sys.modules, name, m)
+    monkeypatch.syspath_prepend("/root/reference")
+    for k in [k for k in sys.modules if k == "model" or k.startswith("model.") or k in ("spline", "run_nerf_helpers", "utils", "loss")]:
+        monkeypatch.delitem(sys.modules, k, raising=False)
+    try:
+        ref_nerf = __import__("model.nerf", fromlist=["Graph"])
+        ref_opt = __import__("model.optimize", fromlist=["Model"])
+        ref_spline = __import__("spline")
+        ref_helpers = __import__("run_nerf_helpers")
+    except Exception as e:
+        pytest.skip(f"reference import failed: {type(e).__name__}: {e}")
+    from benerf_b200 import nerf, optimize, spline, run_nerf_helpers
+
+    def names(fn):
+        return [p for p in inspect.signature(fn).parameters]
+
+    pairs = [(ref_nerf.Graph.forward, nerf.Graph.forward), (ref_nerf.Graph.render, nerf.Graph.render),
+             (ref_nerf.Graph.render_video, nerf.Graph.render_video),
+             (ref_opt.Graph.get_pose_evt, optimize.Graph.get_pose_evt), (ref_opt.Graph.get_pose_rgb, optimize.Graph.get_pose_rgb),
+             (ref_opt.Model.build_network, optimize.Model.build_network), (ref_opt.Model.setup_optimizer, optimize.Model.setup_optimizer),
+             (ref_spline.cubic_spline_pose_unit_time, spline.cubic_spline_pose_unit_time),
+             (ref_spline.linear_pose_unit_time, spline.linear_pose_unit_time),
+             (ref_helpers.init_nerf, run_nerf_helpers.init_nerf),
+             (ref_helpers.render_video_test, run_nerf_helpers.render_video_test),
+             (ref_helpers.render_image_test, run_nerf_helpers.render_image_test)]
+    for ref_fn, our_fn in pairs:
+        r, o = names(ref_fn), names(our_fn)
+        assert o[:len(r)] == r, (ref_fn.__qualname__, r, o)
+        for extra in o[len(r):]:
+            assert inspect.signature(our_fn).parameters[extra].default is not inspect.Parameter.empty, (our_fn.__qualname__, extra)
