@@ -245,7 +245,7 @@ def bench_image_formation_stress(dev, steps=5, warmup=3):
 
 
 # ----------------------------------------------------------------------------------------------
-def bench_train_step(opts, dev, world, rank, steps=5, warmup=3, config="e2nerf_synthetic"):
+def bench_train_step(opts, dev, world, rank, steps=5, warmup=3, config="e2nerf_synthetic", scaling="weak"):
     """Training step per GPU (weak scaling), forward + backward + Adam + ONE gradient all-reduce
     (benerf_b200.train.Trainer.step), device-timed, max over ranks:
       e2nerf_synthetic  BASELINE.json configs[2]: 800x800, 1024 event pixels x 2 poses + 2048 // 19 = 107 blur pixels x 19
@@ -280,6 +280,8 @@ def bench_train_step(opts, dev, world, rank, steps=5, warmup=3, config="e2nerf_s
         trainer.phase_ms = []
     g = torch.Generator().manual_seed(99 + rank)
     r_evt = 1024
+    if scaling == "strong":                 # ONE reference batch split by pixel over the ranks
+        r_evt, r_rgb = r_evt // world, max(r_rgb // world, 1)
     idx_evt = torch.randint(0, Ht * Wt, (r_evt,), generator=g).to(dev)
     idx_rgb = torch.randint(0, Ht * Wt, (r_rgb,), generator=g).to(dev)
     blur_t = torch.rand(r_rgb, CH, generator=g).to(dev)
@@ -317,14 +319,15 @@ def bench_train_step(opts, dev, world, rank, steps=5, warmup=3, config="e2nerf_s
     rays = (2 * r_evt + n_poses * r_rgb) * world
     return {"metric": "rays_per_sec (training step: forward + backward + Adam + gradient all-reduce)", "value": rays / (ms / 1e3),
             "unit": "rays/s", "ms_per_step": ms, "steps": steps, "warmup": warmup, "rays_per_step_per_gpu": rays // world,
-            "workload": (f"{config} {Wt}x{Ht}, 1024 event px x 2 poses + {r_rgb} blur px x {n_poses} poses, 64+128 samples, C=3 "
-                         f"(BASELINE.json configs[{3 if config == 'e2nerf_real' else 2}], weak scaling"
+            "workload": (f"{config} {Wt}x{Ht}, {r_evt} event px x 2 poses + {r_rgb} blur px x {n_poses} poses per GPU, 64+128 samples, C=3 "
+                         f"(BASELINE.json configs[{3 if config == 'e2nerf_real' else 2}], {scaling} scaling"
                          + (", normalised event loss with all-reduced batch norms)" if config == "e2nerf_real" else ")")),
             "algorithmic_tflops": 3 * rays / world * FLOP_PER_RAY / (ms / 1e3) / 1e12,
             "ms_each_step": per_step, "gpu_launches_per_step": launches / steps, "final_loss": float(loss),
             "mem_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 1),
             "optimizer_tail": "fused (bnrf_adam_step)" if args.fused_optimizer else "torch.optim.Adam x3",
-            "backward": "tcgen05 dgrad / wgrad on bf16 hi/lo tile matrices (bwd_tiles.cu), 3 MMAs per product, fp32 accumulate"}
+            "backward": "tcgen05 dgrad chain + one wgrad launch per network on bf16 hi/lo tile matrices (dgrad_chain.cu, "
+                        "bwd_tiles.cu), 3 MMAs per product, fp32 accumulate"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -359,6 +362,7 @@ def bench_ours(opts):
     # the two secondary measurements run first, on a quiet device (the headline render phase holds ~12 GB and the power cap)
     train = None if opts.no_train_step else bench_train_step(opts, dev, world, rank)
     train_real = None if opts.no_train_step else bench_train_step(opts, dev, world, rank, config="e2nerf_real")
+    train_strong = None if (opts.no_train_step or world == 1) else bench_train_step(opts, dev, world, rank, scaling="strong")
     stress = None if opts.no_train_step else bench_image_formation_stress(dev)
     torch.cuda.empty_cache()
     R = opts.pixels
@@ -481,6 +485,7 @@ def bench_ours(opts):
             "cpu_baseline": cpu,
             "train_step": train,
             "train_step_e2nerf_real": train_real,
+            "train_step_strong_scaling": train_strong,
             "image_formation_stress": stress,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * wall_e2e / opts.steps},
