@@ -278,3 +278,92 @@ def test_graph_forward_windows_events_and_renders_both_batches(time_window, rand
     for p in list(graph.nerf.parameters()) + list(graph.nerf_fine.parameters()) + [graph.evt_knot_pose_se3.params.weight, graph.transform.params.weight]:
         assert p.grad is not None and torch.isfinite(p.grad).all()
     assert float(graph.evt_knot_pose_se3.params.weight.grad.abs().sum()) > 0 and float(graph.transform.params.weight.grad.abs().sum()) > 0
+
+
+def test_full_bench_size_properties():
+    """Size-independent properties at the FULL size bench.py times (BASELINE.json configs[1] throughput shape: 65,536 pixels x
+    19 poses = 1,245,184 rays, 64 + 128 samples), where the oracle cannot follow:
+      determinism      two runs with the same injected draws are bit-identical (no atomics on the forward path)
+      shard invariance  rendering half of the pixels gives exactly the corresponding rows of the full render -- rows of an MLP
+                        tile are independent, which is what lets ranks shard by pixel
+      pose-major order  rendering ONE pose gives exactly that pose's block of the multi-pose render
+      ranges            rgb, acc in [0, 1], sigma >= 0, disparity finite or the reference's NaN (0/0) only where acc == 0
+      blur mean         of the rendered batch equals the mean of the per-pose blocks"""
+    from benerf_b200.engine import blur_mean
+    from oracle import pose
+    case = CASES["unreal_rgb"]
+    inp = make_inputs(case)
+    eng = make_engine(case, "tc")
+    eng.set_weights(0, to_dev(inp["coarse"])); eng.set_weights(1, to_dev(inp["fine"]))
+    R, P = 65536, 19
+    g = torch.Generator(device=DEV).manual_seed(5)
+    idx = torch.randint(0, case.H * case.W, (R,), device=DEV, generator=g)
+    poses = pose.poses_from_knots(inp["knots"], inp["transform"], *case.exposure, P).to(DEV).contiguous()
+    n = P * R
+    draws = {"t_rand": torch.rand(n, 64, device=DEV, generator=g), "noise_c": torch.randn(n, 64, device=DEV, generator=g),
+             "u": torch.rand(n, 64, device=DEV, generator=g), "noise_f": torch.randn(n, 128, device=DEV, generator=g)}
+    full = eng.render(poses, idx, case.H, case.W, case.K, rng=draws)
+    again = eng.render(poses, idx, case.H, case.W, case.K, rng=draws)
+    for k in full:
+        assert torch.equal(torch.nan_to_num(full[k]), torch.nan_to_num(again[k])), k
+    del again
+    # half of the pixels: rows (p, r < R/2) of every per-ray tensor
+    half = R // 2
+    sub = {k: v.reshape(P, R, -1)[:, :half].reshape(P * half, -1).contiguous() for k, v in draws.items()}
+    part = eng.render(poses, idx[:half].contiguous(), case.H, case.W, case.K, rng=sub)
+    for k in part:
+        want = full[k].reshape(P, R, -1)[:, :half].reshape(part[k].shape)
+        assert torch.equal(torch.nan_to_num(part[k]), torch.nan_to_num(want)), k
+    del part, sub
+    # one pose
+    p = 7
+    one = eng.render(poses[p:p + 1].contiguous(), idx, case.H, case.W, case.K,
+                     rng={k: v[p * R:(p + 1) * R].contiguous() for k, v in draws.items()})
+    for k in one:
+        assert torch.equal(torch.nan_to_num(one[k]), torch.nan_to_num(full[k][p * R:(p + 1) * R])), k
+    # ranges
+    for k in ("rgb_map", "rgb0"):
+        assert float(full[k].min()) >= 0.0 and float(full[k].max()) <= 1.0 + 1e-6 and not torch.isnan(full[k]).any()
+    for k in ("acc_map", "acc0"):
+        assert float(full[k].min()) >= 0.0 and float(full[k].max()) <= 1.0 + 1e-5
+    assert float(full["sigma"].min()) >= 0.0
+    bad = torch.isnan(full["disp_map"]) & (full["acc_map"] > 0)
+    assert not bad.any()
+    # blur model over the whole batch
+    blur = blur_mean(full["rgb_map"], P)
+    want = full["rgb_map"].reshape(P, R, 3).double().mean(0)
+    assert float((blur.double() - want).abs().max()) < 1e-6
+
+
+def test_image_formation_full_frame_properties():
+    """BASELINE.json configs[4] frame size (1920 x 1080 = 2,073,600 pixels), beyond what the CPU oracle covers in seconds:
+      blur mean       51 poses, against a float64 torch reduction of the same tensor
+      event model     16 bins: every bin against the formula of train.py:163-177 / utils/math_utils.py:4-23 evaluated with
+                      torch ops, and the telescoping identity sum_b diff_b = L(last frame) - L(first frame)
+      event scatter   1e6 events: exactly the integer image torch.index_put_(accumulate=True) builds (float64, Q10)"""
+    from benerf_b200 import engine as E
+    R, P, B = 1920 * 1080, 51, 16
+    g = torch.Generator(device=DEV).manual_seed(9)
+    frames = torch.rand(P, R, 3, device=DEV, generator=g)
+    blur = E.blur_mean(frames.reshape(P * R, 3), P)
+    assert float((blur.double() - frames.double().mean(0)).abs().max()) < 1e-6
+    for ds, lin in (("BeNeRF_Unreal", False), ("E2NeRF_Synthetic", True)):
+        ev = frames[:B + 1]
+        ev[0, :1000] = 0.0                                                     # log(0 + 1e-9) / the linear branch of lin-log
+        got = E.event_logdiff(ev.reshape((B + 1) * R, 3), B, ds)               # [B, R]
+        gray = ev[..., 0] * 0.299 + ev[..., 1] * 0.587 + ev[..., 2] * 0.114
+        if lin:
+            c = gray * 255.0
+            L = torch.where(c < 20.0, c * (torch.log(torch.tensor(20.0 + 1e-9, device=DEV)) / 20.0), torch.log(c + 1e-9))
+        else:
+            L = torch.log(gray + 1e-9)
+        assert float((got - (L[1:] - L[:-1])).abs().max()) < 2e-5
+        assert float((got.double().sum(0) - (L[-1].double() - L[0].double())).abs().max()) < 1e-4
+    n_ev = 1_000_000
+    x = torch.randint(0, 1920, (n_ev,), device=DEV, generator=g, dtype=torch.int32)
+    y = torch.randint(0, 1080, (n_ev,), device=DEV, generator=g, dtype=torch.int32)
+    pol = (torch.randint(0, 2, (n_ev,), device=DEV, generator=g) * 2 - 1).float()
+    img = E.accumulate_events(x, y, pol, 1080, 1920)
+    want = torch.zeros(1080, 1920, device=DEV, dtype=torch.float64)
+    want.index_put_((y.long(), x.long()), pol.double(), accumulate=True)
+    assert img.dtype == torch.float64 and torch.equal(img, want)
