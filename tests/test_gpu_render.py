@@ -367,3 +367,44 @@ def test_image_formation_full_frame_properties():
     want = torch.zeros(1080, 1920, device=DEV, dtype=torch.float64)
     want.index_put_((y.long(), x.long()), pol.double(), accumulate=True)
     assert img.dtype == torch.float64 and torch.equal(img, want)
+
+
+def test_graph_render_tum_vie_remap_branch():
+    """dataset == "TUM_VIE": Graph.render replaces every integer pixel (i, j) by remap[j, i] before building rays
+    (model/nerf.py:247-250, the undistortion LUT of undistort.py).  Forward against the oracle on identical draws, and
+    the pose gradient through the remapped rays against oracle autograd."""
+    from tests.test_gpu_backward import case_args, rel_err
+    from oracle import pose
+    from benerf_b200 import optimize
+    case = CASES["unreal_rgb"]
+    inp = make_inputs(case)
+    args = case_args(case)
+    args.dataset = "TUM_VIE"
+    g = torch.Generator().manual_seed(31)
+    jj, ii = torch.meshgrid(torch.arange(case.H, dtype=torch.float32), torch.arange(case.W, dtype=torch.float32), indexing="ij")
+    remap = torch.stack([ii + (torch.rand(case.H, case.W, generator=g) - 0.5) * 3.0, jj + (torch.rand(case.H, case.W, generator=g) - 0.5) * 3.0], -1)
+    graph = optimize.Model(args).build_network(args)
+    graph.nerf.load_state_dict(inp["coarse"]); graph.nerf_fine.load_state_dict(inp["fine"])
+    graph.evt_knot_pose_se3.params.weight.data.copy_(inp["knots"]); graph.transform.params.weight.data.copy_(inp["transform"])
+    graph.to(DEV)
+    graph.engine(args).set_sample_grid(torch.linspace(0.0, 1.0, steps=case.n_samples))
+    knots = inp["knots"].clone().requires_grad_(True)
+    transform = inp["transform"].clone().requires_grad_(True)
+    poses_o = pose.poses_from_knots(knots, transform, *case.exposure, case.n_poses)
+    draws = dict(inp["rng_rgb"])
+    want = orender.render(inp["coarse"], inp["fine"], poses_o, inp["idx_rgb"], case.H, case.W, case.K, draws, remap=remap,
+                          return_intermediates=True)
+    draws["z_fine"] = want["_extra"]["z_fine"].detach()
+    poses = graph.get_pose_rgb(args, torch.tensor(case.exposure, dtype=torch.float32))
+    got = graph.render(0, poses, inp["idx_rgb"], case.H, case.W, case.K, args, enable_crf=True, sensor_type="rgb", remap=remap,
+                       training=True, rng=to_dev(draws))
+    plain = graph.render(0, poses.detach(), inp["idx_rgb"], case.H, case.W, case.K, args, enable_crf=True, sensor_type="rgb",
+                         remap=None, training=True, rng=to_dev(draws))
+    for k in ("rgb_map", "rgb0", "acc_map"):
+        assert max_abs(got[k], want[k].detach()) < TOL, k
+    assert max_abs(plain["rgb_map"], want["rgb_map"].detach()) > 1e-3        # the LUT really moved the rays
+    cot = torch.randn(want["rgb_map"].shape, generator=g)
+    (want["rgb_map"] * cot).sum().backward()
+    (got["rgb_map"] * cot.to(DEV)).sum().backward()
+    assert rel_err(graph.evt_knot_pose_se3.params.weight.grad, knots.grad) < 1e-2
+    assert rel_err(graph.transform.params.weight.grad, transform.grad) < 1e-2
