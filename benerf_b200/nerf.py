@@ -228,7 +228,7 @@ class Graph(nn.Module):
             raise ValueError(type)
         # the reference walks the image in args.chunk-ray pieces to bound its activation memory (model/nerf.py:360); here a
         # ray costs 4 KB of scratch, so the whole image is one launch sequence (chunks of 4 M rays for very large frames)
-        chunk = max(int(args.chunk), 1 << 22)
+        chunk = max(int(args.chunk), int(getattr(args, "render_chunk_rays", 1 << 22)))
         for i in range(0, ray_idx.shape[0], chunk):
             ret = self.render(iter_step, poses, ray_idx[i:i + chunk], H, W, K, args, enable_crf=(str(type) == "rgb"),
                               sensor_type=("rgb" if str(type) == "rgb" else None), remap=remap, training=False)

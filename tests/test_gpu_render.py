@@ -408,3 +408,52 @@ def test_graph_render_tum_vie_remap_branch():
     (got["rgb_map"] * cot.to(DEV)).sum().backward()
     assert rel_err(graph.evt_knot_pose_se3.params.weight.grad, knots.grad) < 1e-2
     assert rel_err(graph.transform.params.weight.grad, transform.grad) < 1e-2
+
+
+def test_multi_bin_event_render_and_chunked_full_frame():
+    """get_pose_evt(..., seg_num=B+1) (model/optimize.py:58-71) -> Graph.render at B+1 poses -> B event maps
+    (BASELINE configs[4]'s reference API), against the oracle pair by pair; and render_video walking a frame in several
+    chunks (model/nerf.py:360-372) gives the same maps as one launch sequence."""
+    from tests.test_gpu_backward import case_args
+    from oracle import pose, image_formation as oif
+    from benerf_b200 import optimize, image_formation as IF
+    case = CASES["e2nerf_syn"]
+    inp = make_inputs(case)
+    args = case_args(case)
+    graph = optimize.Model(args).build_network(args)
+    graph.nerf.load_state_dict(inp["coarse"]); graph.nerf_fine.load_state_dict(inp["fine"])
+    graph.evt_knot_pose_se3.params.weight.data.copy_(inp["knots"]); graph.transform.params.weight.data.copy_(inp["transform"])
+    graph.to(DEV)
+    graph.engine(args).set_sample_grid(torch.linspace(0.0, 1.0, steps=case.n_samples))
+    B, R = 4, 16
+    with torch.no_grad():
+        poses = graph.get_pose_evt(args, torch.tensor(case.window, dtype=torch.float32), seg_num=B + 1)
+        want_poses = pose.poses_from_knots(inp["knots"], None, *case.window, B + 1)
+        assert max_abs(poses, want_poses) < 2e-6
+        g = torch.Generator().manual_seed(41)
+        n = (B + 1) * R
+        draws = {"t_rand": torch.rand(n, 64, generator=g), "noise_c": torch.randn(n, 64, generator=g),
+                 "u": torch.rand(n, 64, generator=g), "noise_f": torch.randn(n, 128, generator=g)}
+        idx = inp["idx_evt"][:R]
+        want = orender.render(inp["coarse"], inp["fine"], want_poses, idx, case.H, case.W, case.K, draws, return_intermediates=True)
+        draws["z_fine"] = want["_extra"]["z_fine"]
+        got = graph.render(0, poses, idx, case.H, case.W, case.K, args, enable_crf=True, sensor_type="event", remap=None,
+                           training=True, rng=to_dev(draws))
+        assert max_abs(got["rgb_map"], want["rgb_map"]) < TOL
+        maps = IF.event_logdiff(got["rgb_map"], B, args.dataset)                    # [B, R]
+        frames = want["rgb_map"].reshape(B + 1, R, 3)
+        for b in range(B):
+            ref = oif.event_log_diff(torch.cat([frames[b], frames[b + 1]]), args.dataset, 3).reshape(-1)
+            assert max_abs(maps[b], ref) < 5e-4        # log amplifies the 1e-6 render error at dark pixels
+        # chunked full-frame render: 40 x 56 frame in chunks of 512 rays vs one launch sequence (same Philox stream offsets
+        # are per call, so compare on injected draws through Graph.render directly)
+        H, W = 40, 56
+        K = [[50.0, 0, 28.0], [0, 50.0, 20.0], [0, 0, 1]]
+        args.chunk, args.render_chunk_rays = 512, 512
+        ret = graph.render_video(0, poses[:1], H, W, K, args, None, type="rgb")
+        assert ret["rgb_map"].shape == (H, W, 3) and ret["sigma"].shape == (H, W, 128) and not torch.isnan(ret["rgb_map"]).any()
+        args.render_chunk_rays = 1 << 22
+        whole = graph.render_video(0, poses[:1], H, W, K, args, None, type="rgb")
+        # different chunks draw different noise (as the reference's own chunked eval does); the scene is the same
+        assert float(((ret["rgb_map"] - whole["rgb_map"]) ** 2).mean()) < 0.05
+        assert whole["acc_map"].shape == ret["acc_map"].shape == (H, W) and torch.isfinite(ret["acc_map"]).all()
