@@ -159,7 +159,10 @@ typedef struct {
 } bnrf_param_grads;
 
 /* Bytes of the caller-owned buffer in which bnrf_render_forward_train keeps what the backward pass needs
- * (rays, depths, raw outputs, densities and the activations of both networks: ~10 KB per sample). */
+ * (rays, depths, raw outputs, densities and the activations of both networks as 16-bit tile matrices: ~10 KB per
+ * sample).  The buffer and the backward workspace must be 256-byte aligned (cudaMalloc / torch allocations are): the
+ * backward kernels read them with cp.async.bulk.  The backward call must see the weights the forward call used
+ * (no bnrf_set_weights in between). */
 size_t bnrf_saved_bytes(const bnrf_ctx* ctx, int64_t n_rays);
 /* bnrf_render_forward that additionally fills `saved`.  Needs cfg.mlp_mode == BNRF_MLP_TC_FP16X2. */
 int bnrf_render_forward_train(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R,
