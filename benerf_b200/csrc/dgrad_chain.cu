@@ -16,8 +16,9 @@
 // epilogue applies the ReLU mask from 1 bit per activation emitted by the training-mode forward pass (32 B per row and
 // layer instead of re-reading activations); and every dZ_l, which in shared memory already IS a tile of its tile matrix,
 // is copied to global memory by the bulk-copy engine (one thread, cp.async.bulk.global.shared) for the weight-gradient
-// kernel (bwd_tiles.cu) -- the epilogue warps issue no global stores, whose completion their release-arrive would await.  HBM traffic per sample: 9 x 1 KB of
-// dZ out + 0.4 KB in, against 10 x 2.5 KB for the per-linear kernels it replaces (tile_dgrad_kernel, kept as a fallback).
+// kernel (bwd_tiles.cu) -- the epilogue warps issue no global stores, whose completion their release-arrive would
+// await.  HBM traffic per sample: 8 x 1 KB of dZ out + 0.8 KB in (dZ9 tile, mask bits), against 9 x 2.5 KB for the
+// per-linear kernels it replaces (tile_dgrad_kernel, kept as a cross-check: gemm_mode BNRF_GEMM_TC_PER_LINEAR).
 #include "tc_ptx.cuh"
 #include "bwd_tiles.cuh"
 
