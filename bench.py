@@ -270,6 +270,8 @@ def bench_train_step(opts, dev, world, rank, steps=5, warmup=3, config="e2nerf_s
     args.lrate, args.pose_lrate, args.transform_lrate, args.rgb_crf_lrate, args.event_crf_lrate = 5e-4, 1e-3, 1e-6, 5e-4, 5e-4
     args.optimize_nerf, args.optimize_pose, args.optimize_trans = True, True, False
     args.fused_optimizer = os.environ.get("BNRF_FUSED_TAIL", "1") != "0"
+    if os.environ.get("BNRF_GEMM_MODE"):
+        args.gemm_mode = os.environ["BNRF_GEMM_MODE"]          # development aid: tc | tc_chain1 | tc_linear
     torch.manual_seed(0)
     model = optimize.Model(args)
     graph = model.build_network(args)
@@ -327,7 +329,7 @@ def bench_train_step(opts, dev, world, rank, steps=5, warmup=3, config="e2nerf_s
             "ms_each_step": per_step, "gpu_launches_per_step": launches / steps, "final_loss": float(loss),
             "mem_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 1),
             "optimizer_tail": "fused (bnrf_adam_step)" if args.fused_optimizer else "torch.optim.Adam x3",
-            "backward": "tcgen05 dgrad chain + one wgrad launch per network on bf16 hi/lo tile matrices (dgrad_chain.cu, "
+            "backward": "tcgen05 dgrad chain on CTA pairs + one wgrad launch per network on bf16 hi/lo tile matrices (dgrad_chain2.cu, "
                         "bwd_tiles.cu), 3 MMAs per product, fp32 accumulate"}
 
 

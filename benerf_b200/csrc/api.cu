@@ -83,6 +83,7 @@ int alloc_net(bnrf_ctx* ctx, int n) {
     BNRF_CUDA(ctx, cudaMalloc(&np.tc_scale, 16 * sizeof(float)));
     BNRF_CUDA(ctx, cudaMalloc(&np.dg_img, dgrad_images_bytes()));
     BNRF_CUDA(ctx, cudaMalloc(&np.dgc_stream, dgrad_chain_stream_bytes()));
+    BNRF_CUDA(ctx, cudaMalloc(&np.dgp_stream, dgrad_chain_pair_stream_bytes()));
     return BNRF_OK;
 }
 
@@ -90,7 +91,7 @@ void free_net(bnrf_ctx* ctx, int n) {
     NetParams& np = ctx->net[n];
     for (int s = 0; s < 10; ++s) { cudaFree(np.wt[s]); cudaFree(np.bias[s]); }
     cudaFree(np.w_alpha); cudaFree(np.b_alpha); cudaFree(np.w_rgb); cudaFree(np.b_rgb); cudaFree(np.w_dir);
-    cudaFree(np.tc_stream); cudaFree(np.tc2_stream); cudaFree(np.tc_scale); cudaFree(np.dg_img); cudaFree(np.dgc_stream);
+    cudaFree(np.tc_stream); cudaFree(np.tc2_stream); cudaFree(np.tc_scale); cudaFree(np.dg_img); cudaFree(np.dgc_stream); cudaFree(np.dgp_stream);
     cudaFree(np.wt_table); cudaFree(np.absmax); cudaFree(np.scale); cudaFree(np.wt9m); cudaFree(np.bias9m);
     memset(&np, 0, sizeof(np));
 }
@@ -185,7 +186,7 @@ int bnrf_create(bnrf_ctx** out, int device, const bnrf_cfg* cfg) {
     *out = nullptr;
     if (cfg->n_samples < 3 || cfg->n_importance < 0 || cfg->n_samples + cfg->n_importance > kMaxSamples)
         return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: need 3 <= n_samples and n_samples + n_importance <= %d", kMaxSamples);
-    if (cfg->gemm_mode != BNRF_GEMM_TC && cfg->gemm_mode != BNRF_GEMM_SIMT_FP32 && cfg->gemm_mode != BNRF_GEMM_TC_PER_LINEAR) return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: unknown gemm_mode %d", cfg->gemm_mode);
+    if (cfg->gemm_mode != BNRF_GEMM_TC && cfg->gemm_mode != BNRF_GEMM_SIMT_FP32 && cfg->gemm_mode != BNRF_GEMM_TC_PER_LINEAR && cfg->gemm_mode != BNRF_GEMM_TC_1CTA) return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: unknown gemm_mode %d", cfg->gemm_mode);
     if (cfg->channels != 1 && cfg->channels != 3) return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: channels must be 1 or 3");
     if (cfg->mlp_mode != BNRF_MLP_TC_FP16X2 && cfg->mlp_mode != BNRF_MLP_SIMT_FP32 && cfg->mlp_mode != BNRF_MLP_TC_1CTA)
         return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: unknown mlp_mode %d", cfg->mlp_mode);

@@ -491,6 +491,7 @@ static int pack_dgrad_images(bnrf_ctx* ctx, int net, cudaStream_t st) {
     int rc = bwt::pack_dgrad_images(ctx, t, st);
     if (rc) return rc;
     if ((rc = pack_dgrad_chain_stream(ctx, net, st))) return rc;
+    if ((rc = pack_dgrad_chain_pair_stream(ctx, net, st))) return rc;
     np.dg_dirty = false;
     return BNRF_OK;
 }
@@ -519,7 +520,7 @@ static int mlp_backward(bnrf_ctx* ctx, int net, int64_t n, int S, const ActPtrs&
     // ---- heads: rgb_linear (128 -> C) and the ReLU of the view layer ----
     const float* h9 = acts.h9_f32;
     {
-        const int64_t rows_pad = (int64_t)tiles * bwt::kTileRows;
+        const int64_t rows_pad = bwt::tile_alloc(rows) * bwt::kTileRows;  // incl. the pad tile of an odd tile count (CTA pairs walk tiles in pairs)
         const unsigned grid = (unsigned)ceil_div(rows_pad * (kHalf / 8), 256);
         if (C == 3) heads_backward_kernel<3><<<grid, 256, 0, st>>>(w.d_raw, h9, np.w_rgb, rows, rows_pad, w.dz9, w.dz9_tiles);
         else heads_backward_kernel<1><<<grid, 256, 0, st>>>(w.d_raw, h9, np.w_rgb, rows, rows_pad, w.dz9, w.dz9_tiles);
@@ -537,8 +538,13 @@ static int mlp_backward(bnrf_ctx* ctx, int net, int64_t n, int S, const ActPtrs&
     sum_samples_kernel<<<(unsigned)n, kHalf, 0, st>>>(w.dz9, S, w.dvb);
     BNRF_LAUNCH_CHECK(ctx);
     // ---- dgrad chain: dZ9 -> d feature -> dZ7 -> ... -> dZ0 -> d encoding ----
-    if (ctx->cfg.gemm_mode != BNRF_GEMM_TC_PER_LINEAR) {
-        // one launch, the gradient of a tile stays on the SM across all ten linears (dgrad_chain.cu)
+    if (ctx->cfg.gemm_mode == BNRF_GEMM_TC) {
+        // one launch per network: the gradient of a tile stays on the SM across all linears; CTA pairs, each CTA streams half
+        // of every weight tile (dgrad_chain2.cu)
+        if ((rc = launch_dgrad_chain_pair(ctx, net, w.dz9_tiles, acts.mask_bits, acts.t_alloc, w.d_raw + C, C + 1, rows, w.tiles,
+                                          w.dz_tiles, w.d_pe, st))) return rc;
+    } else if (ctx->cfg.gemm_mode != BNRF_GEMM_TC_PER_LINEAR) {
+        // the same chain on single CTAs (dgrad_chain.cu; BNRF_GEMM_TC_1CTA)
         if ((rc = launch_dgrad_chain(ctx, net, w.dz9_tiles, acts.mask_bits, acts.t_alloc, w.d_raw + C, C + 1, rows, w.tiles, w.dz_tiles,
                                      w.d_pe, st))) return rc;
     } else {
@@ -623,7 +629,7 @@ static BwdWorkspace carve_bwd(const bnrf_cfg& c, int64_t n, void* base) {
     };
     auto take = [&](size_t floats) { return reinterpret_cast<float*>(take_bytes(floats * sizeof(float))); };
     const int64_t rows = n * (c.n_samples + c.n_importance);
-    w.b.tiles = bwt::tile_count(rows);
+    w.b.tiles = bwt::tile_alloc(rows);
     w.b.d_raw = take(rows * (c.channels + 1));
     w.b.dz_tiles = reinterpret_cast<unsigned char*>(take_bytes(8 * (size_t)w.b.tiles * bwt::tile_bytes(kWidth)));
     w.b.g_views = take(kHalf * kWidth + kHalf); w.b.s_views = w.b.g_views + kHalf * kWidth;

@@ -46,6 +46,7 @@ struct NetParams {
     // backward call after bnrf_set_weights
     unsigned char* dg_img;
     unsigned char* dgc_stream;   // dgrad_chain.cu: the transposed weights as [N x 32] bf16 SW64 stages in consumption order
+    unsigned char* dgp_stream;   // dgrad_chain2.cu (CTA pairs): [rank][stage], each CTA's half of the output columns, SW128
     bool dg_dirty;
     bool ready;
 };
@@ -181,6 +182,11 @@ struct SavedLayout {
 SavedLayout carve_saved(const bnrf_cfg& c, int64_t n, void* base);
 size_t dgrad_images_bytes();   // backward.cu: the 11 dgrad weight images of one network
 size_t dgrad_chain_stream_bytes();
+size_t dgrad_chain_pair_stream_bytes();
+int pack_dgrad_chain_pair_stream(bnrf_ctx*, int net, cudaStream_t);
+int launch_dgrad_chain_pair(bnrf_ctx*, int net, const unsigned char* dz9_tiles, const unsigned char* mask_bits, int64_t t_alloc,
+                            const float* d_sigma, int64_t d_sigma_stride, int64_t rows, int64_t dz_tile_count, unsigned char* dz_tiles,
+                            float* d_pe, cudaStream_t);
 int pack_dgrad_chain_stream(bnrf_ctx*, int net, cudaStream_t);
 int launch_dgrad_chain(bnrf_ctx*, int net, const unsigned char* dz9_tiles, const unsigned char* mask_bits, int64_t t_alloc,
                        const float* d_sigma, int64_t d_sigma_stride, int64_t rows, int64_t dz_tile_count, unsigned char* dz_tiles,

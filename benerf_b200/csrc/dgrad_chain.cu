@@ -38,7 +38,7 @@ constexpr uint32_t OFF_BAR = OFF_W + NS * STAGE_BYTES;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr uint32_t TMEM_COLS = 512;
 
-enum { BAR_W_FULL = 0, BAR_W_EMPTY = BAR_W_FULL + NS, BAR_A0_FULL = BAR_W_EMPTY + NS, BAR_A_FREE, BAR_SPILLED, BAR_A_READY,
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = BAR_W_FULL + NS, BAR_A0_FULL = BAR_W_EMPTY + NS, BAR_A_FREE, BAR_SPILLED, BAR_A_READY = BAR_SPILLED + 4,
        BAR_ACC_FULL = BAR_A_READY + 8, BAR_COUNT = BAR_ACC_FULL + 2 };
 
 __device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
@@ -89,7 +89,7 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
         for (int i = 0; i < NS; ++i) { mbar_init(bar(BAR_W_FULL + i), 1); mbar_init(bar(BAR_W_EMPTY + i), 1); }
         mbar_init(bar(BAR_A0_FULL), 1);
         mbar_init(bar(BAR_A_FREE), 1);
-        mbar_init(bar(BAR_SPILLED), 1);
+        for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_SPILLED + i), 1);
         for (int i = 0; i < 8; ++i) mbar_init(bar(BAR_A_READY + i), 256);
         for (int i = 0; i < 2; ++i) mbar_init(bar(BAR_ACC_FULL + i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -129,7 +129,7 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
             for (int it = 0; it < my_tiles; ++it) {
                 const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
                 mbar_wait(bar(BAR_A_FREE), ((uint32_t)it & 1u) ^ 1u, err_flag, 52);       // last MMAs of the previous tile have read A
-                if (it > 0) mbar_wait(bar(BAR_SPILLED), ((uint32_t)(it - 1) * 8u + 7u) & 1u, err_flag, 58);   // ... and its dZ0 has been copied out
+                if (it > 0) mbar_wait(bar(BAR_SPILLED + 3), ((uint32_t)(it - 1) * 8u + 7u) & 1u, err_flag, 58);   // ... and its dZ0 has been copied out
                 const unsigned char* src = dz9_tiles + (size_t)tile * bwt::tile_bytes(kHalf);
                 mbar_expect_tx(bar(BAR_A0_FULL), 4u * KBLOCK_BYTES);
                 tma_bulk_load(base + OFF_A_HI, src, 2u * KBLOCK_BYTES, bar(BAR_A0_FULL));
@@ -151,10 +151,14 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
                         mbar_wait(bar(BAR_A_READY + 2 * kb + 1), sgen & 1u, err_flag, 60);
                         bulk_store(gt + (size_t)kb * KBLOCK_BYTES, base + OFF_A_HI + kb * KBLOCK_BYTES, KBLOCK_BYTES);
                         bulk_store(gt + (size_t)(4 + kb) * KBLOCK_BYTES, base + OFF_A_LO + kb * KBLOCK_BYTES, KBLOCK_BYTES);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");      // one group per 64-column block ...
+                        if (kb > 0) {                                                   // ... so that block kb-1 is released as soon as it has been read
+                            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            mbar_arrive(bar(BAR_SPILLED + kb - 1));
+                        }
                     }
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // shared memory has been read: the next epilogue may overwrite A
-                    mbar_arrive(bar(BAR_SPILLED));
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    mbar_arrive(bar(BAR_SPILLED + 3));
                 }
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -261,7 +265,6 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
                 }
                 if (s < NUM_STEPS - 1) {
                     const uint32_t acc_addr = lane_addr + (uint32_t)b * 256u + (uint32_t)ch * 16u;
-                    if (s >= 1) mbar_wait(bar(BAR_SPILLED), ((uint32_t)it * 8u + (uint32_t)(s - 1)) & 1u, err_flag, 61);   // A (= dZ of step s-1) copied out
                     uint32_t va[16], vb[16];
                     tc_ld16_issue(acc_addr, va);
 #pragma unroll
@@ -269,6 +272,8 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
                         uint32_t (&cur)[16] = (kh & 1) ? vb : va;
                         uint32_t (&nxt)[16] = (kh & 1) ? va : vb;
                         tc_ld16_wait(cur);
+                        // the 64-column block this chunk overwrites (dZ of the previous step) has been copied out
+                        if (s >= 1 && (kh & 1) == 0) mbar_wait(bar(BAR_SPILLED + (kh >> 1)), ((uint32_t)it * 8u + (uint32_t)(s - 1)) & 1u, err_flag, 61);
                         float4 wn[4];
                         if (kh < 7) {
                             tc_ld16_issue(acc_addr + (kh + 1) * 32, nxt);

@@ -39,7 +39,7 @@ class Engine:
         if not torch.cuda.is_available():
             raise BnrfError("benerf_b200 needs a CUDA (sm_100a) device; there is no CPU path")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else torch.device(device).index or 0)
-        self.cfg = _lib.Cfg(n_samples, n_importance, channels, int(bool(ndc)), near, far, MLP_MODES[mlp_mode], {"tc": 0, "simt": 1, "tc_linear": 2}[gemm_mode])
+        self.cfg = _lib.Cfg(n_samples, n_importance, channels, int(bool(ndc)), near, far, MLP_MODES[mlp_mode], {"tc": 0, "simt": 1, "tc_linear": 2, "tc_chain1": 3}[gemm_mode])
         self.n_samples, self.n_importance, self.channels = n_samples, n_importance, channels
         self.mlp_mode, self.gemm_mode = mlp_mode, gemm_mode
         self._ctx = C.c_void_p()

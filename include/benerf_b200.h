@@ -51,6 +51,8 @@ typedef enum {
 #define BNRF_GEMM_TC 0         /* tcgen05.mma kind::f16 on bf16 hi/lo split operands (3 MMAs per product), fp32 accumulate */
 #define BNRF_GEMM_TC_PER_LINEAR 2   /* like BNRF_GEMM_TC, but the activation gradients take one launch per linear (tile_dgrad_kernel)
                                      * instead of the fused chain (dgrad_chain_kernel); kept as an on-device cross-check */
+#define BNRF_GEMM_TC_1CTA 3         /* like BNRF_GEMM_TC with the dgrad chain on single CTAs (dgrad_chain_kernel) instead of CTA pairs
+                                     * (dgrad_chain_pair_kernel, cta_group::2); kept as an on-device cross-check */
 #define BNRF_GEMM_SIMT_FP32 1  /* plain fp32 FFMA (on-device cross-check; also used for shapes too small for a 128-row tile) */
 
 /* Order of the 12 linears in bnrf_set_weights (the reference's state-dict order). */

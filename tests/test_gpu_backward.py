@@ -205,11 +205,13 @@ def test_render_backward_matches_oracle_autograd(name, n_px):
 
 
 @pytest.mark.parametrize("name,gemm_mode", [("unreal_rgb", "tc"), ("e2nerf_syn", "tc"), ("e2nerf_real", "tc"), ("gray_linear", "tc"),
-                                            ("unreal_rgb", "tc_linear"), ("gray_linear", "tc_linear")])
+                                            ("unreal_rgb", "tc_linear"), ("gray_linear", "tc_linear"),
+                                            ("unreal_rgb", "tc_chain1"), ("e2nerf_real", "tc_chain1"), ("gray_linear", "tc_chain1")])
 def test_training_iteration_gradients_match_reference(name, gemm_mode):
     """Full iteration (two renders + image formation + the four loss terms, train.py:163-337) -> gradients of the
     reference itself (tests/golden): knots, transform, per-parameter norms and every 97th gradient element.
-    gemm_mode tc = fused dgrad chain (dgrad_chain.cu), tc_linear = one dgrad launch per linear (bwd_tiles.cu)."""
+    gemm_mode tc = fused dgrad chain on CTA pairs (dgrad_chain2.cu), tc_chain1 = the chain on single CTAs (dgrad_chain.cu),
+    tc_linear = one dgrad launch per linear (bwd_tiles.cu)."""
     from benerf_b200 import image_formation as IF
     case, gold = CASES[name], load_golden(name)
     inp = make_inputs(case)
