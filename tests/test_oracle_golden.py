@@ -65,6 +65,21 @@ def test_rays_and_ndc_match_reference(fn):
     torch.testing.assert_close(view.norm(dim=-1), torch.ones(H * W), rtol=0, atol=1e-6)
 
 
+def test_tum_vie_remap_branch_matches_reference(fn):
+    """model/nerf.py:241-252 with dataset == "TUM_VIE": pixel (i, j) -> remap[j, i] before get_specific_rays (two poses,
+    pose-major order), then ndc_rays -- reference outputs in functions.npz."""
+    H, W, f = 10, 14, 11.0
+    K = torch.tensor([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=torch.float32)
+    o, d, _ = rays.ray_batch(fn["remap_poses"], fn["remap_idx"], H, W, K, remap=fn["remap_lut"], ndc=False)
+    assert torch.equal(o, fn["remap_rays_o"]) and torch.equal(d, fn["remap_rays_d"])
+    on, dn, _ = rays.ray_batch(fn["remap_poses"], fn["remap_idx"], H, W, K, remap=fn["remap_lut"], ndc=True)
+    assert torch.equal(on, fn["remap_rays_o_ndc"]) and torch.equal(dn, fn["remap_rays_d_ndc"])
+    plain, _, _ = rays.ray_batch(fn["remap_poses"], fn["remap_idx"], H, W, K, ndc=False)
+    assert torch.equal(plain, o)                      # origins do not depend on the pixel ...
+    _, d_plain, _ = rays.ray_batch(fn["remap_poses"], fn["remap_idx"], H, W, K, ndc=False)
+    assert not torch.equal(d_plain, d)                # ... directions do
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_full_iteration_matches_reference(name):
     """get_pose_* -> two renders -> image formation -> loss (+ gradients) per BASELINE config."""

@@ -266,15 +266,39 @@ def run_functions(ref):
     o, d = ref.helpers.get_rays(H, W, K, pose, Namespace(dataset="x"), None)
     on, dn = ref.helpers.ndc_rays(H, W, K[0][0], 1.0, o, d)
     out["rays_pose"], out["rays_o"], out["rays_d"], out["rays_o_ndc"], out["rays_d_ndc"] = pose, o, d, on, dn
+    # f4: the TUM-VIE undistortion-LUT branch of Graph.render's training path (model/nerf.py:241-252): every integer pixel is
+    # replaced by remap[j, i] before get_specific_rays; two poses, pose-major ray order
+    Hr, Wr, fr = 10, 14, 11.0
+    Kr = torch.tensor([[fr, 0, Wr / 2], [0, fr, Hr / 2], [0, 0, 1]], dtype=torch.float32)
+    jj, ii = torch.meshgrid(torch.arange(Hr, dtype=torch.float32), torch.arange(Wr, dtype=torch.float32), indexing="ij")
+    remap = torch.stack([ii + torch.from_numpy((rng.random((Hr, Wr)) - 0.5).astype(np.float32)) * 2.0,
+                         jj + torch.from_numpy((rng.random((Hr, Wr)) - 0.5).astype(np.float32)) * 2.0], -1)
+    idx = torch.from_numpy(rng.permutation(Hr * Wr)[:40].astype(np.int64))
+    poses2 = ref.spline.cubic_spline_pose_unit_time(
+        *[out["spline_knots_1"][i].reshape(1, 1, 6) for i in range(4)], torch.tensor([0.2, 0.7]))
+    ray_idx_ = idx.repeat(poses2.shape[0])
+    poses_rep = poses2.unsqueeze(1).repeat(1, idx.shape[0], 1, 1).reshape(-1, 3, 4)
+    j = ray_idx_.reshape(-1, 1).squeeze() // Wr
+    i = ray_idx_.reshape(-1, 1).squeeze() % Wr
+    rect = remap[j, i]
+    i, j = rect[..., 0], rect[..., 1]
+    ro, rd = ref.helpers.get_specific_rays(i, j, Kr, poses_rep)
+    ron, rdn = ref.helpers.ndc_rays(Hr, Wr, Kr[0][0], 1.0, ro, rd)
+    out["remap_lut"], out["remap_idx"], out["remap_poses"] = remap, idx, poses2
+    out["remap_rays_o"], out["remap_rays_d"], out["remap_rays_o_ndc"], out["remap_rays_d_ndc"] = ro, rd, ron, rdn
     return {k: v.detach().cpu().numpy() for k, v in out.items()}
 
 
 def main():
     ref = import_reference()
     os.makedirs(os.path.dirname(golden_path("x")), exist_ok=True)
-    np.savez_compressed(golden_path("functions"), **run_functions(ref))
-    print("functions", os.path.getsize(golden_path("functions")))
+    only = set(sys.argv[1:])              # e.g. `python tools/make_golden.py functions` regenerates that fixture alone
+    if not only or "functions" in only:
+        np.savez_compressed(golden_path("functions"), **run_functions(ref))
+        print("functions", os.path.getsize(golden_path("functions")))
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         data = run_case(ref, case)
         np.savez_compressed(golden_path(name), **data)
         print(name, os.path.getsize(golden_path(name)), "bytes;", len(data), "arrays")
