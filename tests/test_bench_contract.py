@@ -1,0 +1,58 @@
+"""The committed bench lines (profiles/r01_bench_*.json, written by bench.py on the B200 pool) carry every key of the
+bench contract and are internally consistent.  Runs on CPU: it checks the evidence files, not the GPU."""
+import json
+import os
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _line(name):
+    path = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(path):
+        pytest.skip(f"{name} not recorded yet")
+    text = open(path).read().strip().splitlines()
+    return json.loads([t for t in text if t.startswith("{")][-1])
+
+
+@pytest.mark.parametrize("name,n", [("r01_bench_n1.json", 1), ("r01_bench_n2.json", 2), ("r01_bench_n8.json", 8)])
+def test_bench_line_has_the_contract_keys(name, n):
+    d = _line(name)
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["n_gpus"] == n and d["metric"] == "rays_per_sec" and d["unit"] == "rays/s" and d["higher_is_better"] is True
+    assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic" and d["warmup"] >= 3
+    assert "workload" in d["config"] and "model" not in d["config"] and "l2" in d["config"]
+    rays = d["config"]["rays_per_step_per_gpu"] * n
+    assert abs(d["value"] - rays / (d["ms_per_step"] / 1e3)) < 1e-6 * d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert 0.2 < r["frac"] < 0.4 and 0.8 < r["issued_frac"] < 1.0 and r["mlp_share_of_step"] > 0.95
+    e = d["e2e"]
+    assert e["unit"] == "rays/s" and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] != d["value"]
+    assert 0.9 * d["value"] < e["value"] <= 1.02 * d["value"]
+    assert d["gpu_launches"] > 0
+    c = d["clocks"]
+    assert c["sm_mhz"] and c["sm_max_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if n == 1:
+        b = d["cpu_baseline"]
+        assert b["kind"] == "port" and b["cores"] >= 1 and b["value"] > 0 and "sample" in b
+        assert r["traffic"] is not None and r["traffic"]["bytes_per_launch"] > 0
+    else:
+        assert d["cpu_baseline"] is None          # rank 0 at N = 1 only
+
+
+def test_scaling_of_the_recorded_lines():
+    one, eight = _line("r01_bench_n1.json"), _line("r01_bench_n8.json")
+    assert eight["value"] / one["value"] > 6.0                     # north_star: >= 6x at 8 GPUs
+    t1, t8 = one["train_step"], eight["train_step"]
+    assert t8["value"] / t1["value"] > 6.0
+
+
+def test_reference_arm_line():
+    d = _line("r01_bench_reference.json")
+    assert d["impl"] == "reference" and d["metric"] == "rays_per_sec" and d["unit"] == "rays/s"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
