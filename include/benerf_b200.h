@@ -263,6 +263,11 @@ int bnrf_profile_read(bnrf_ctx* ctx, double* mlp_ms, int64_t* mlp_timed, double*
  * fp16 row-major; D device fp32 [128,N]; lbo_field = raw 14-bit leading-byte-offset field. */
 int bnrf_debug_umma_probe(const void* A_half, const void* B_half, int N, int lbo_field, float* D, void* stream);
 
+/* Bring-up probe (tests only) of the ".ts" MMA form on a CTA pair: D[256,N] = A[256,64] * B[N,64]^T with the A operand in
+ * tensor memory (written with tcgen05.st at column a_col, lane = row, one 32-bit column = two consecutive K elements) and
+ * each CTA holding N/2 rows of B in shared memory; N = 128 | 256, N <= a_col <= 480. */
+int bnrf_debug_umma_ts_probe(const void* A_half, const void* B_half, int N, int a_col, float* D, void* stream);
+
 /* Test hook: C[M,N] (op)= A_op * B_op through the backward pass's fp32 GEMM (sgemm.cu).  ta/tb: operand stored
  * transposed; epi 0 store, 1 accumulate, 2 atomic add (split contraction), 3 masked store with optional rank-1 term. */
 int bnrf_debug_sgemm(bnrf_ctx* ctx, int ta, int tb, int64_t M, int N, int64_t K, const float* A, int64_t lda,

@@ -21,3 +21,21 @@ def test_umma_probe_matches_integer_gemm(N):
     torch.cuda.synchronize()
     want = A.float() @ B.float().t()          # small integers: exact in fp16 inputs / fp32 accumulate
     assert torch.equal(D, want), f"max abs diff {(D - want).abs().max().item()}"
+
+
+@pytest.mark.parametrize("N,a_col", [(256, 256), (128, 128), (128, 480), (256, 288)])
+def test_umma_ts_probe_a_operand_in_tensor_memory(N, a_col):
+    """tcgen05.mma cta_group::2 with A read from TMEM (tcgen05.st: lane = row, 32-bit column = 2 consecutive K elements)
+    and N/2 rows of B per CTA: the conventions of the forward kernel's in-TMEM hand-off."""
+    from benerf_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(N + a_col)
+    A = torch.randint(-4, 5, (256, 64), generator=g).half().cuda()
+    B = torch.randint(-4, 5, (N, 64), generator=g).half().cuda()
+    D = torch.full((256, N), float("nan"), device="cuda")
+    rc = lib.bnrf_debug_umma_ts_probe(C.c_void_p(A.data_ptr()), C.c_void_p(B.data_ptr()), N, a_col, C.c_void_p(D.data_ptr()),
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    want = A.float() @ B.float().t()
+    assert torch.equal(D, want), f"max abs diff {(D - want).abs().max().item()}"
