@@ -313,6 +313,8 @@ def bench_train_step(opts, dev, world, rank, steps=5, warmup=3, config="e2nerf_s
     per_step = [round(evs[i].elapsed_time(evs[i + 1]), 2) for i in range(steps)]
     launches = eng.profile_read()["launches"]
     eng.profile(False)
+    if trainer.launches_per_step is not None:            # the iteration is a replayed CUDA graph: count the kernels it holds
+        launches = trainer.launches_per_step * steps
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -328,7 +330,8 @@ def bench_train_step(opts, dev, world, rank, steps=5, warmup=3, config="e2nerf_s
             "algorithmic_tflops": 3 * rays / world * FLOP_PER_RAY / (ms / 1e3) / 1e12,
             "ms_each_step": per_step, "gpu_launches_per_step": launches / steps, "final_loss": float(loss),
             "mem_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 1),
-            "optimizer_tail": "fused (bnrf_adam_step)" if args.fused_optimizer else "torch.optim.Adam x3",
+            "optimizer_tail": "fused (bnrf_adam_step_sched)" if args.fused_optimizer else "torch.optim.Adam x3",
+            "cuda_graph": trainer._cg is not None,
             "backward": "tcgen05 dgrad chain on CTA pairs + one wgrad launch per network on bf16 hi/lo tile matrices (dgrad_chain2.cu, "
                         "bwd_tiles.cu), 3 MMAs per product, fp32 accumulate"}
 
@@ -453,7 +456,7 @@ def bench_ours(opts):
     mlp_ms_per_launch = prof["mlp_ms"] / max(prof["mlp_timed"], 1)
     achieved = prof["mlp_flops"] / max(prof["mlp_ms"], 1e-9) / 1e9          # algorithmic TFLOP/s of the MLP kernel
     # tensor-core MACs per algorithmic MAC: the pair kernel merges feature_linear into the view layer
-    issued_ratio = MACS_ISSUED_PER_SAMPLE / MACS_PER_SAMPLE if opts.mlp_mode == "tc" else (MACS_PER_SAMPLE - 3456 - 640) / MACS_PER_SAMPLE
+    issued_ratio = MACS_ISSUED_PER_SAMPLE / MACS_PER_SAMPLE if opts.mlp_mode in ("tc", "tc2") else (MACS_PER_SAMPLE - 3456 - 640) / MACS_PER_SAMPLE
     cpu = None
     if rank == 0 and world == 1 and not opts.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
@@ -478,7 +481,7 @@ def bench_ours(opts):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (tcgen05 fp16 hi/lo split operands, 3 MMAs per product, fp32 TMEM accumulate)" if opts.mlp_mode != "simt" else "f32 (SIMT)",
             "data": "synthetic", "config": workload_config(R, world),
-            "roofline": {"bound": "tensor", "kernel": {"tc": "bnrf::tc2::mlp_tc2_kernel<3> (CTA pairs, cta_group::2)", "tc1": "bnrf::tc::mlp_tc_kernel<3>", "simt": "bnrf::mlp_simt_kernel<3>"}[opts.mlp_mode],
+            "roofline": {"bound": "tensor", "kernel": {"tc": "bnrf::tc3::mlp_tc3_kernel<3> (CTA pairs, cta_group::2, A operand in tensor memory)", "tc2": "bnrf::tc2::mlp_tc2_kernel<3> (CTA pairs, cta_group::2)", "tc1": "bnrf::tc::mlp_tc_kernel<3>", "simt": "bnrf::mlp_simt_kernel<3>"}[opts.mlp_mode],
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": ncu_traffic(prof["mlp_flops"] / max(prof["mlp_timed"], 1)), "peak_source": peak_src,
                          "algorithmic_flop_per_launch": prof["mlp_flops"] / max(prof["mlp_timed"], 1),
@@ -513,7 +516,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pixels", type=int, default=65536, help="pixels per GPU per step (R)")
     ap.add_argument("--cpu-pixels", type=int, default=128, help="pixels of the bounded CPU sample")
-    ap.add_argument("--mlp-mode", default="tc", choices=["tc", "tc1", "simt"])
+    ap.add_argument("--mlp-mode", default="tc", choices=["tc", "tc2", "tc1", "simt"])
     ap.add_argument("--mode", default="render", choices=["render", "train"], help="train: print only the training-step line")
     ap.add_argument("--train-config", default="e2nerf_synthetic", choices=["e2nerf_synthetic", "e2nerf_real"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libbenerf_b200.so")
 
 OK, ERR_ARG, ERR_DEVICE, ERR_CUDA, ERR_STATE, ERR_NCCL = 0, -1, -2, -3, -4, -5
-MLP_TC_FP16X2, MLP_SIMT_FP32, MLP_TC_1CTA = 0, 1, 2
+MLP_TC_FP16X2, MLP_SIMT_FP32, MLP_TC_1CTA, MLP_TC_PAIR_SS = 0, 1, 2, 3
 NUM_LINEARS = 12
 # order of the 12 linears expected by bnrf_set_weights (reference state-dict order)
 LINEAR_NAMES = [f"pts_linears.{i}" for i in range(8)] + ["views_linears.0", "feature_linear", "alpha_linear", "rgb_linear"]
@@ -23,7 +23,7 @@ class Cfg(C.Structure):
 
 class Rng(C.Structure):
     _fields_ = [("t_rand", C.c_void_p), ("noise_c", C.c_void_p), ("u", C.c_void_p), ("noise_f", C.c_void_p),
-                ("z_fine", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64)]
+                ("z_fine", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64), ("offset_dev", C.c_void_p)]
 
 
 class Outputs(C.Structure):
@@ -32,6 +32,16 @@ class Outputs(C.Structure):
 
 class AdamGroup(C.Structure):
     _fields_ = [("begin", C.c_int64), ("end", C.c_int64), ("lr", C.c_float), ("active", C.c_int32)]
+
+
+class LossCfg(C.Structure):
+    _fields_ = [("channels", C.c_int32), ("n_poses", C.c_int32), ("log_mode", C.c_int32), ("event_loss", C.c_int32),
+                ("rgb_loss", C.c_int32), ("event_threshold", C.c_float), ("event_coeff_syn", C.c_float),
+                ("event_coeff_real", C.c_float), ("rgb_coeff", C.c_float)]
+
+
+class AdamSchedGroup(C.Structure):
+    _fields_ = [("begin", C.c_int64), ("end", C.c_int64), ("lr0", C.c_float), ("decay_rate", C.c_float), ("active", C.c_int32)]
 
 
 class ParamGrads(C.Structure):
@@ -67,7 +77,12 @@ PROTOTYPES = {
     "bnrf_blur_mean_backward": (_I, [_P, _I, _L, _I, _P, _P]),
     "bnrf_event_logdiff_backward": (_I, [_P, _P, _I, _L, _I, _I, _P, _P]),
     "bnrf_accumulate_events": (_I, [_P, _P, _P, _L, _I, _I, _P, _P]),
+    "bnrf_training_loss_workspace_bytes": (_Z, [_L]),
+    "bnrf_training_loss": (_I, [C.POINTER(LossCfg), _P, _P, _P, _P, _L, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P]),
+    "bnrf_training_loss_finish": (_I, [C.POINTER(LossCfg), _P, _P, _P, _P, _L, _L, _P, _P, _P, _P, _P]),
     "bnrf_adam_step": (_I, [_P, _P, _P, _P, _L, C.POINTER(AdamGroup), _I, _L, C.c_float, C.c_float, C.c_float, C.c_float, _I, _P]),
+    "bnrf_adam_step_sched": (_I, [_P, _P, _P, _P, _L, C.POINTER(AdamSchedGroup), _I, _P, C.c_double, C.c_float, C.c_float, C.c_float, C.c_float, _I, _P]),
+    "bnrf_step_advance": (_I, [_P, _P]),
     "bnrf_profile": (_I, [_P, _I]),
     "bnrf_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "bnrf_debug_mlp_trace": (_I, [_P, _P]),

@@ -80,6 +80,7 @@ int alloc_net(bnrf_ctx* ctx, int n) {
     BNRF_CUDA(ctx, cudaMalloc(&np.w_dir, kDirCh * kHalf * sizeof(float)));
     BNRF_CUDA(ctx, cudaMalloc(&np.tc_stream, tc_stream_halfs() * sizeof(__half)));
     BNRF_CUDA(ctx, cudaMalloc(&np.tc2_stream, tc2_stream_halfs() * sizeof(__half)));
+    BNRF_CUDA(ctx, cudaMalloc(&np.tc3_stream, tc3_stream_halfs() * sizeof(__half)));
     BNRF_CUDA(ctx, cudaMalloc(&np.tc_scale, 16 * sizeof(float)));
     BNRF_CUDA(ctx, cudaMalloc(&np.dg_img, dgrad_images_bytes()));
     BNRF_CUDA(ctx, cudaMalloc(&np.dgc_stream, dgrad_chain_stream_bytes()));
@@ -91,7 +92,7 @@ void free_net(bnrf_ctx* ctx, int n) {
     NetParams& np = ctx->net[n];
     for (int s = 0; s < 10; ++s) { cudaFree(np.wt[s]); cudaFree(np.bias[s]); }
     cudaFree(np.w_alpha); cudaFree(np.b_alpha); cudaFree(np.w_rgb); cudaFree(np.b_rgb); cudaFree(np.w_dir);
-    cudaFree(np.tc_stream); cudaFree(np.tc2_stream); cudaFree(np.tc_scale); cudaFree(np.dg_img); cudaFree(np.dgc_stream); cudaFree(np.dgp_stream);
+    cudaFree(np.tc_stream); cudaFree(np.tc2_stream); cudaFree(np.tc3_stream); cudaFree(np.tc_scale); cudaFree(np.dg_img); cudaFree(np.dgc_stream); cudaFree(np.dgp_stream);
     cudaFree(np.wt_table); cudaFree(np.absmax); cudaFree(np.scale); cudaFree(np.wt9m); cudaFree(np.bias9m);
     memset(&np, 0, sizeof(np));
 }
@@ -164,11 +165,12 @@ static int run_mlp(bnrf_ctx* ctx, int net, const float* o, const float* d, const
     if (!ctx->net[net].ready) return fail(ctx, BNRF_ERR_STATE, "weights of network %d not set (bnrf_set_weights)", net);
     const double macs = 63.0 * 256 + 4 * 65536.0 + 319.0 * 256 + 2 * 65536.0 + 256 + 65536.0 + 283.0 * 128 + 128.0 * ctx->cfg.channels;
     MlpTimer timer(ctx, st, 2.0 * macs * (double)n * (double)S);
-    if (acts && ctx->cfg.mlp_mode != BNRF_MLP_TC_FP16X2)
-        return fail(ctx, BNRF_ERR_STATE, "training mode (saved activations) needs mlp_mode BNRF_MLP_TC_FP16X2");
+    if (acts && !mlp_mode_is_pair(ctx->cfg.mlp_mode))
+        return fail(ctx, BNRF_ERR_STATE, "training mode (saved activations) needs mlp_mode BNRF_MLP_TC_FP16X2 or BNRF_MLP_TC_PAIR_SS");
     if (ctx->cfg.mlp_mode == BNRF_MLP_SIMT_FP32) return launch_mlp_simt(ctx, net, o, d, vb, z, n, S, raw, st);
     if (ctx->cfg.mlp_mode == BNRF_MLP_TC_1CTA) return launch_mlp_tc(ctx, net, o, d, vb, z, n, S, raw, st);
-    return launch_mlp_tc2(ctx, net, o, d, vb, z, n, S, raw, acts, st);
+    if (ctx->cfg.mlp_mode == BNRF_MLP_TC_PAIR_SS) return launch_mlp_tc2(ctx, net, o, d, vb, z, n, S, raw, acts, st);
+    return launch_mlp_tc3(ctx, net, o, d, vb, z, n, S, raw, acts, st);
 }
 
 }  // namespace bnrf
@@ -188,7 +190,7 @@ int bnrf_create(bnrf_ctx** out, int device, const bnrf_cfg* cfg) {
         return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: need 3 <= n_samples and n_samples + n_importance <= %d", kMaxSamples);
     if (cfg->gemm_mode != BNRF_GEMM_TC && cfg->gemm_mode != BNRF_GEMM_SIMT_FP32 && cfg->gemm_mode != BNRF_GEMM_TC_PER_LINEAR && cfg->gemm_mode != BNRF_GEMM_TC_1CTA) return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: unknown gemm_mode %d", cfg->gemm_mode);
     if (cfg->channels != 1 && cfg->channels != 3) return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: channels must be 1 or 3");
-    if (cfg->mlp_mode != BNRF_MLP_TC_FP16X2 && cfg->mlp_mode != BNRF_MLP_SIMT_FP32 && cfg->mlp_mode != BNRF_MLP_TC_1CTA)
+    if (cfg->mlp_mode != BNRF_MLP_TC_FP16X2 && cfg->mlp_mode != BNRF_MLP_SIMT_FP32 && cfg->mlp_mode != BNRF_MLP_TC_1CTA && cfg->mlp_mode != BNRF_MLP_TC_PAIR_SS)
         return fail(nullptr, BNRF_ERR_ARG, "bnrf_create: unknown mlp_mode %d", cfg->mlp_mode);
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)

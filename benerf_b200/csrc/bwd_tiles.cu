@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(dg::THREADS, 1) tile_dgrad_kernel(const __grid
     const uint32_t b_part = (uint32_t)g.N * 128u;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             const size_t a_tile = tile_bytes(g.K), a_part = tile_part_bytes(g.K);
             uint32_t cnt = 0;
             for (int it = 0; it < my_tiles; ++it) {
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(dg::THREADS, 1) tile_dgrad_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = make_idesc_x(128, g.N, 1, 1, 0, 0);
             uint32_t cnt = 0;
             for (int it = 0; it < my_tiles; ++it) {
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) tile_wgrad_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = make_idesc_x(128, jb.N, 1, 1, 1, 1);      // bf16 x bf16 (kind::f16 rejects mixed formats), both MN-major
             const int mhalves = jb.M / 128;
             for (uint32_t i = 0; i < iters; ++i) {

@@ -38,6 +38,7 @@ struct NetParams {
     // in the exact order the TMA producer consumes them (mlp_tc.cu).
     __half* tc_stream;    // single-CTA kernel (mlp_tc.cu)
     __half* tc2_stream;   // CTA-pair kernel (mlp_tc2.cu): [rank][stage], each CTA's half of the output columns
+    __half* tc3_stream;   // CTA-pair kernel with A in tensor memory (mlp_tc3.cu): [rank][stage], 8 KB stages in N-half issue order
     float* tc_scale;      // [10] 2^-s per GEMM step undoing the fp16 weight pre-scale
     const float** wt_table;   // device copy of {wt[0..9], wt9m} (the packing kernels index it by GEMM step; 10 = merged)
     unsigned int* absmax;     // device [16] scratch of the per-step max |W| (self-clearing)
@@ -142,6 +143,8 @@ struct Philox {
         return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
     }
 };
+// effective Philox stream offset of a render call: host-side call counter + 64 x the device-resident iteration counter
+__device__ inline uint64_t rng_offset(const bnrf_rng& r) { return r.offset + (r.offset_dev ? 64ull * __ldg(r.offset_dev) : 0ull); }
 enum : uint32_t { kStreamTRand = 1, kStreamNoiseC = 2, kStreamU = 3, kStreamNoiseF = 4 };
 
 // ---- launchers implemented in the individual .cu files ---------------------------------
@@ -170,6 +173,12 @@ size_t tc2_stream_halfs();
 int pack_tc2_stream(bnrf_ctx*, int net, const float* const* table_dev, const float* scale_dev, cudaStream_t);
 int launch_mlp_tc2(bnrf_ctx*, int net, const float* o, const float* d, const float* vb, const float* z,
                    int64_t n, int S, float* raw, const ActPtrs* acts /*NULL unless training*/, cudaStream_t);
+size_t tc3_stream_halfs();
+int pack_tc3_stream(bnrf_ctx*, int net, const float* const* table_dev, const float* scale_dev, cudaStream_t);
+int launch_mlp_tc3(bnrf_ctx*, int net, const float* o, const float* d, const float* vb, const float* z,
+                   int64_t n, int S, float* raw, const ActPtrs* acts /*NULL unless training*/, cudaStream_t);
+// the two CTA-pair kernels run nine GEMM steps (feature_linear merged into the view layer) and take the merged view bias
+inline bool mlp_mode_is_pair(int mode) { return mode == BNRF_MLP_TC_FP16X2 || mode == BNRF_MLP_TC_PAIR_SS; }
 
 // Tensors the forward pass keeps for the backward pass (bnrf_render_forward_train), carved from the caller's buffer.
 struct SavedLayout {

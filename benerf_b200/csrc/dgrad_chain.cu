@@ -165,7 +165,7 @@ dgrad_chain_kernel(const unsigned char* __restrict__ stream, const unsigned char
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t wcnt = 0, agen = 0;
             auto kblock = [&](uint32_t d_tmem, uint32_t idesc, int kb, int hk, uint32_t& accumulate) {
                 const uint32_t a_hi = base + OFF_A_HI + kb * KBLOCK_BYTES, a_lo = base + OFF_A_LO + kb * KBLOCK_BYTES;

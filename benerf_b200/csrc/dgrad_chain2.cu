@@ -108,7 +108,7 @@ dgrad_chain_pair_kernel(const unsigned char* __restrict__ stream, const unsigned
 
     if (warp == 0) {
         // ================= weight producer (both CTAs: own half of every weight tile) =================
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t cnt = 0;
             for (int it = 0; it < my_iters; ++it) {
                 const unsigned char* src = stream + (size_t)rank * rank_stream_bytes();
@@ -136,7 +136,7 @@ dgrad_chain_pair_kernel(const unsigned char* __restrict__ stream, const unsigned
         }
     } else if (warp == 4) {
         // ================= dZ9 loader: this CTA's first A operand (K = 128: two K-blocks, hi and lo parts) =================
-        if (lane == 0) {
+        if (elect_one()) {
             const int full_bar = rank == 0 ? BAR_A0_FULL : BAR_A0_LOCAL;
             for (int it = 0; it < my_iters; ++it) {
                 const int64_t tile = tile_of(it);
@@ -158,7 +158,7 @@ dgrad_chain_pair_kernel(const unsigned char* __restrict__ stream, const unsigned
         }
     } else if (warp == 3) {
         // ================= spill: this CTA's dZ_l tiles -> global memory through the bulk-copy engine =================
-        if (lane == 0) {
+        if (elect_one()) {
             const size_t dz_mat = (size_t)dz_tile_count * bwt::tile_bytes(kWidth);
             uint32_t sgen = 0;
             for (int it = 0; it < my_iters; ++it) {
@@ -183,7 +183,7 @@ dgrad_chain_pair_kernel(const unsigned char* __restrict__ stream, const unsigned
         }
     } else if (warp == 1) {
         // ================= MMA issuer (leader CTA, one thread) =================
-        if (lane == 0 && rank == 0) {
+        if (rank == 0 && elect_one()) {
             uint32_t wcnt = 0, agen = 0;
             const uint32_t idesc256 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)((2 * TILE_M) >> 4) << 24);
             const uint32_t idesc64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)((2 * TILE_M) >> 4) << 24);

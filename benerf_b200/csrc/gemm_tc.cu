@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(GemmArgs g, int ta,
         }
     } else if (warp == MMA_WARP) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(TM, NT);
             uint32_t cnt = 0;
             for (int it = 0; it < my_tiles; ++it) {

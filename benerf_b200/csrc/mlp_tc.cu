@@ -124,7 +124,7 @@ mlp_tc_kernel(TcParams p, const float* __restrict__ rays_o, const float* __restr
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t wcnt = 0;           // weight stages consumed
             uint32_t agen = 0;           // generation of the a_ready barriers (one per producing epilogue)
             unsigned long long w_pe = 0, w_a = 0, w_w = 0;
@@ -444,8 +444,10 @@ int pack_tc_stream(bnrf_ctx* ctx, int net, cudaStream_t st) {
     if (ctx->cfg.mlp_mode == BNRF_MLP_TC_1CTA) {
         pack_stream_kernel<<<STAGES_PER_TILE, 256, 0, st>>>(np.wt_table, np.scale, np.tc_stream);
         BNRF_LAUNCH_CHECK(ctx);
-    } else if (ctx->cfg.mlp_mode == BNRF_MLP_TC_FP16X2) {
+    } else if (ctx->cfg.mlp_mode == BNRF_MLP_TC_PAIR_SS) {
         return pack_tc2_stream(ctx, net, np.wt_table, np.scale, st);
+    } else if (ctx->cfg.mlp_mode == BNRF_MLP_TC_FP16X2) {
+        return pack_tc3_stream(ctx, net, np.wt_table, np.scale, st);
     }
     return BNRF_OK;
 }

@@ -119,7 +119,7 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs: own half of every weight tile) =================
-        if (lane == 0) {
+        if (elect_one()) {
             const unsigned char* src = reinterpret_cast<const unsigned char*>(p.stream) + (size_t)rank * rank_stream_bytes();
             uint32_t cnt = 0;
             unsigned long long w_empty = 0;
@@ -147,7 +147,7 @@ mlp_tc2_kernel(TcParams p, const float* __restrict__ rays_o, const float* __rest
         }
     } else if (warp == 1) {
         // ================= MMA issuer (leader CTA, one thread) =================
-        if (lane == 0 && rank == 0) {
+        if (rank == 0 && elect_one()) {
             uint32_t wcnt = 0;           // weight stages consumed
             uint32_t agen = 0;           // generation of the a_ready barriers (one per producing epilogue)
             unsigned long long w_pe = 0, w_a = 0, w_w = 0;

@@ -32,6 +32,45 @@ __global__ void adam_step_kernel(float* __restrict__ p, float* __restrict__ g, f
     }
 }
 
+struct AdamSched { bnrf_adam_sched_group g[8]; int n; };
+
+__global__ void adam_step_sched_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                       const __grid_constant__ AdamSched groups, const uint64_t* __restrict__ step_dev, double decay_steps,
+                                       float beta1, float beta2, float eps, float grad_scale, int zero_grads) {
+    __shared__ float s_lr[8];
+    __shared__ float s_bc1, s_bc2_sqrt;
+    if (threadIdx.x < groups.n) {
+        const uint64_t gs = *step_dev;                       // global_step of this iteration
+        const double e = gs == 0 ? 0.0 : (double)(gs - 1) / decay_steps;
+        s_lr[threadIdx.x] = (float)((double)groups.g[threadIdx.x].lr0 * pow((double)groups.g[threadIdx.x].decay_rate, e));
+    } else if (threadIdx.x == 32) {
+        const double step = (double)(*step_dev + 1);
+        s_bc1 = (float)(1.0 - pow((double)beta1, step));
+        s_bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, step));
+    }
+    __syncthreads();
+    const float bc1 = s_bc1, bc2_sqrt = s_bc2_sqrt;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float lr = 0.f;
+        bool active = false;
+#pragma unroll 1
+        for (int k = 0; k < groups.n; ++k)
+            if (i >= groups.g[k].begin && i < groups.g[k].end) { lr = s_lr[k]; active = groups.g[k].active != 0; }
+        if (active) {
+            const float gr = g[i] * grad_scale;
+            const float mi = beta1 * m[i] + (1.0f - beta1) * gr;
+            const float vi = beta2 * v[i] + (1.0f - beta2) * gr * gr;
+            m[i] = mi; v[i] = vi;
+            const float denom = sqrtf(vi) / bc2_sqrt + eps;
+            p[i] = p[i] - (lr / bc1) * (mi / denom);
+        }
+        if (zero_grads) g[i] = 0.0f;
+    }
+}
+
+__global__ void step_advance_kernel(uint64_t* step_dev) { *step_dev += 1; }
+
 }  // namespace bnrf
 
 using namespace bnrf;
@@ -50,5 +89,27 @@ extern "C" int bnrf_adam_step(float* params, float* grads, float* exp_avg, float
     const int64_t want = (n + 255) / 256, cap = (int64_t)sms * 8;
     adam_step_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
         params, grads, exp_avg, exp_avg_sq, n, gs, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale, zero_grads);
+    return cudaGetLastError() == cudaSuccess ? BNRF_OK : BNRF_ERR_CUDA;
+}
+
+extern "C" int bnrf_adam_step_sched(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                    const bnrf_adam_sched_group* groups, int n_groups, const uint64_t* step_dev, double decay_steps,
+                                    float beta1, float beta2, float eps, float grad_scale, int zero_grads, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || !groups || n_groups <= 0 || n_groups > 8 || !step_dev || decay_steps <= 0) return BNRF_ERR_ARG;
+    AdamSched gs{};
+    gs.n = n_groups;
+    for (int k = 0; k < n_groups; ++k) gs.g[k] = groups[k];
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = (n + 255) / 256, cap = (int64_t)sms * 8;
+    adam_step_sched_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+        params, grads, exp_avg, exp_avg_sq, n, gs, step_dev, decay_steps, beta1, beta2, eps, grad_scale, zero_grads);
+    return cudaGetLastError() == cudaSuccess ? BNRF_OK : BNRF_ERR_CUDA;
+}
+
+extern "C" int bnrf_step_advance(uint64_t* step_dev, void* stream) {
+    if (!step_dev) return BNRF_ERR_ARG;
+    step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
     return cudaGetLastError() == cudaSuccess ? BNRF_OK : BNRF_ERR_CUDA;
 }

@@ -76,7 +76,7 @@ __global__ void stratified_kernel(const float* __restrict__ t_vals, const float*
         r = t_rand[e];
     } else {
         uint32_t w[4];
-        Philox::draw(rng.seed, rng.offset, (uint64_t)(e / S), (uint32_t)s, kStreamTRand, w);
+        Philox::draw(rng.seed, rng_offset(rng), (uint64_t)(e / S), (uint32_t)s, kStreamTRand, w);
         r = Philox::uniform(w[0]);
     }
     z[e] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), r));
@@ -135,7 +135,7 @@ int launch_stratified(bnrf_ctx* ctx, const float* t_rand, const bnrf_rng* rng, i
 int launch_viewbias(bnrf_ctx* ctx, int net, const float* view, int64_t n, float* vb, cudaStream_t st) {
     const NetParams& np = ctx->net[net];
     // the CTA-pair kernel runs feature_linear merged into the view layer: its per-ray bias carries W_views . b_feature too
-    const float* bias = ctx->cfg.mlp_mode == BNRF_MLP_TC_FP16X2 ? np.bias9m : np.bias[9];
+    const float* bias = mlp_mode_is_pair(ctx->cfg.mlp_mode) ? np.bias9m : np.bias[9];
     viewbias_kernel<<<(unsigned)ceil_div(n, 4), 128, 0, st>>>(view, np.w_dir, bias, n, vb);
     BNRF_LAUNCH_CHECK(ctx);
     return BNRF_OK;

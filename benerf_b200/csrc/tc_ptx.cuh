@@ -34,6 +34,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigne
         }
     }
 }
+// One thread of a converged warp (elect.sync).  The MMA issuer MUST be chosen this way, not with `lane == 0`: ptxas then knows
+// the region runs in a single thread and emits back-to-back UTCHMMA; behind a lane test it wraps EVERY tcgen05.mma in an
+// ELECT / R2UR / BRA.U.ANY uniformisation loop (~150-200 issue cycles per MMA, measured: a 64-cycle N = 128 MMA took 200).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tma_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");

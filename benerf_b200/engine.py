@@ -12,7 +12,7 @@ from ._lib import BnrfError
 
 TRAJ = {"spline": 0, "linear": 1}
 LOG_MODE = {"BeNeRF_Blender": 0, "BeNeRF_Unreal": 0, "E2NeRF_Synthetic": 1, "E2NeRF_Real": 1, "safelog": 0, "linlog": 1}
-MLP_MODES = {"tc": _lib.MLP_TC_FP16X2, "simt": _lib.MLP_SIMT_FP32, "tc1": _lib.MLP_TC_1CTA}
+MLP_MODES = {"tc": _lib.MLP_TC_FP16X2, "simt": _lib.MLP_SIMT_FP32, "tc1": _lib.MLP_TC_1CTA, "tc2": _lib.MLP_TC_PAIR_SS}
 
 
 def _stream():
@@ -109,6 +109,10 @@ class Engine:
         self._check(self.lib.bnrf_profile_read(self._ctx, C.byref(ms), C.byref(timed), C.byref(flops), C.byref(launches)), "bnrf_profile_read")
         return {"mlp_ms": ms.value, "mlp_timed": timed.value, "mlp_flops": flops.value, "launches": launches.value}
 
+    def launch_count(self):
+        """Kernel launches issued through this context since the last profile(True) (or since it was created)."""
+        return self.profile_read()["launches"]
+
     def mlp_trace(self, enable=True):
         """Debug: per-CTA stall counters of the tensor-core MLP kernel (bnrf_debug_mlp_trace)."""
         self._trace = torch.zeros(148 * 2, 16, device=self.device, dtype=torch.int64) if enable else None
@@ -129,7 +133,7 @@ class Engine:
         return (C.c_float * 9)(*flat)
 
     def render(self, poses, ray_idx, H, W, K, remap=None, rng=None, seed=0, offset=0, want_sigma=True, want_depth=False, want_z=False,
-               saved=None):
+               saved=None, offset_dev=None):
         """Graph.render (model/nerf.py:236-343).  rng: dict of the four draws (parity mode) or None (Philox).
         saved: uint8 device tensor of saved_bytes(N) bytes -> training mode (bnrf_render_forward_train)."""
         P, R = poses.shape[0], ray_idx.numel()
@@ -146,7 +150,7 @@ class Engine:
         z_vals = new(n, Sf) if want_z else None
         outs = _lib.Outputs(*[_ptr(ret.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0", "sigma")],
                             _ptr(depth), _ptr(z_vals))
-        r = _lib.Rng(None, None, None, None, None, int(seed), int(offset))
+        r = _lib.Rng(None, None, None, None, None, int(seed), int(offset), _ptr(offset_dev, torch.int64, name="offset_dev"))
         if rng is not None:
             r.t_rand, r.noise_c = _ptr(rng["t_rand"], name="t_rand"), _ptr(rng["noise_c"], name="noise_c")
             if self.n_importance > 0:
@@ -187,8 +191,9 @@ class Engine:
         need = self.lib.bnrf_backward_workspace_bytes(self._ctx, P * R)
         if getattr(self, "_bwd_workspace", None) is None or self._bwd_workspace.numel() < need:
             self._bwd_workspace = torch.empty(need, device=self.device, dtype=torch.uint8)
-        gc = self._grad_table(grads_coarse) if grads_coarse is not None else None
-        gf = self._grad_table(grads_fine) if grads_fine is not None else None
+        # gradient tables: {name: tensor} dicts, or bnrf_param_grads structs built once by the caller (_grad_table)
+        as_table = lambda g: g if g is None or isinstance(g, _lib.ParamGrads) else self._grad_table(g)
+        gc, gf = as_table(grads_coarse), as_table(grads_fine)
         self._check(self.lib.bnrf_render_backward(
             self._ctx, _ptr(poses, name="poses"), _ptr(ray_idx, torch.int64, name="ray_idx"), P, R, int(H), int(W), self._K(K),
             _ptr(remap, name="remap"), _ptr(d_rgb_map, name="d_rgb_map"), _ptr(d_rgb0, name="d_rgb0"),
@@ -196,9 +201,12 @@ class Engine:
             C.byref(gf) if gf is not None else None, _ptr(d_poses, name="d_poses"),
             C.c_void_p(self._bwd_workspace.data_ptr()), self._bwd_workspace.numel(), _stream()), "bnrf_render_backward")
 
-    def spline_poses_backward(self, knots, transform, ts, d_poses, traj="spline"):
-        d_knots = torch.zeros(4, 6, device=self.device, dtype=torch.float32)
-        d_transform = torch.zeros(6, device=self.device, dtype=torch.float32) if transform is not None else None
+    def spline_poses_backward(self, knots, transform, ts, d_poses, traj="spline", d_knots=None, d_transform=None):
+        """d_knots [4,6] / d_transform [6]: ADDED into when given (the kernel accumulates), else fresh zero tensors."""
+        if d_knots is None:
+            d_knots = torch.zeros(4, 6, device=self.device, dtype=torch.float32)
+        if d_transform is None and transform is not None:
+            d_transform = torch.zeros(6, device=self.device, dtype=torch.float32)
         self._check(self.lib.bnrf_spline_poses_backward(
             self._ctx, _ptr(knots, name="knots"), _ptr(transform, name="transform"), _ptr(ts, name="ts"), ts.numel(), TRAJ[traj],
             _ptr(d_poses, name="d_poses"), _ptr(d_knots), _ptr(d_transform), _stream()), "bnrf_spline_poses_backward")
@@ -277,6 +285,55 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, groups, step, betas=(0.9, 0.99
     _rc(lib.bnrf_adam_step(_ptr(params, name="params"), _ptr(grads, name="grads"), _ptr(exp_avg, name="exp_avg"),
                            _ptr(exp_avg_sq, name="exp_avg_sq"), n, arr, len(groups), int(step), float(betas[0]), float(betas[1]),
                            float(eps), float(grad_scale), int(bool(zero_grads)), _stream()), "bnrf_adam_step")
+
+
+def adam_step_sched(params, grads, exp_avg, exp_avg_sq, groups, step_dev, decay_steps, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0,
+                    zero_grads=True):
+    """bnrf_adam_step_sched: groups [(begin, end, lr0, decay_rate, active), ...]; step_dev: int64 device scalar = global_step."""
+    lib = _lib.load()
+    arr = (_lib.AdamSchedGroup * len(groups))(*[_lib.AdamSchedGroup(int(b), int(e), float(lr0), float(rate), int(bool(a)))
+                                                for b, e, lr0, rate, a in groups])
+    _rc(lib.bnrf_adam_step_sched(_ptr(params, name="params"), _ptr(grads, name="grads"), _ptr(exp_avg, name="exp_avg"),
+                                 _ptr(exp_avg_sq, name="exp_avg_sq"), params.numel(), arr, len(groups),
+                                 _ptr(step_dev, torch.int64, name="step_dev"), float(decay_steps), float(betas[0]), float(betas[1]),
+                                 float(eps), float(grad_scale), int(bool(zero_grads)), _stream()), "bnrf_adam_step_sched")
+
+
+def step_advance(step_dev):
+    _rc(_lib.load().bnrf_step_advance(_ptr(step_dev, torch.int64, name="step_dev"), _stream()), "bnrf_step_advance")
+
+
+def loss_cfg(args):
+    """The flags of train.py:205-331 as a bnrf_loss_cfg.  event_loss / rgb_loss are store_true flags upstream (config.py:215-218)."""
+    return _lib.LossCfg(int(args.channels), int(args.num_interpolated_pose), LOG_MODE[args.dataset],
+                        int(bool(getattr(args, "event_loss", True))), int(bool(getattr(args, "rgb_loss", True))),
+                        float(args.event_threshold), float(getattr(args, "event_coeff_syn", 0.1)),
+                        float(getattr(args, "event_coeff_real", 2.0)), float(getattr(args, "rgb_coeff", 1.0)))
+
+
+def training_loss_fused(cfg, evt_fine, evt_coarse, events_accu, idx_evt, blur_fine, blur_coarse, blur_target, all_reduce=None):
+    """bnrf_training_loss (+ bnrf_training_loss_finish): the loss block of train.py:163-331 and its gradients w.r.t. the four
+    renders in one or two launches.  all_reduce: callable summing a float64 device tensor over the ranks in place (the five batch
+    sums of the normalised event loss), or None.  Returns (loss_out float64 [5], (d_evt_fine, d_evt_coarse, d_blur_fine, d_blur_coarse))."""
+    lib = _lib.load()
+    dev = evt_fine.device
+    R_e, R_b = idx_evt.numel(), blur_target.shape[0]
+    ws = torch.empty(lib.bnrf_training_loss_workspace_bytes(R_e) // 8 + 1, device=dev, dtype=torch.float64)
+    grads = tuple(torch.empty_like(t) for t in (evt_fine, evt_coarse, blur_fine, blur_coarse))
+    loss_out = torch.empty(5, device=dev, dtype=torch.float64)
+    ev = events_accu.reshape(-1)
+    _rc(lib.bnrf_training_loss(C.byref(cfg), _ptr(evt_fine, name="evt_fine"), _ptr(evt_coarse, name="evt_coarse"),
+                               _ptr(ev, torch.float64, name="events_accu"), _ptr(idx_evt, torch.int64, name="idx_evt"), R_e,
+                               _ptr(blur_fine, name="blur_fine"), _ptr(blur_coarse, name="blur_coarse"),
+                               _ptr(blur_target, name="blur_target"), R_b, _ptr(ws, torch.float64), *[_ptr(g) for g in grads],
+                               _ptr(loss_out, torch.float64), _stream()), "bnrf_training_loss")
+    if cfg.event_loss and cfg.event_threshold <= 0:
+        if all_reduce is not None:
+            all_reduce(ws[:5])
+        _rc(lib.bnrf_training_loss_finish(C.byref(cfg), _ptr(evt_fine), _ptr(evt_coarse), _ptr(ev, torch.float64),
+                                          _ptr(idx_evt, torch.int64), R_e, R_b, _ptr(ws, torch.float64), _ptr(grads[0]), _ptr(grads[1]),
+                                          _ptr(loss_out, torch.float64), _stream()), "bnrf_training_loss_finish")
+    return loss_out, grads
 
 
 def _rc(rc, what):

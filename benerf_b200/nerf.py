@@ -123,6 +123,12 @@ class Graph(nn.Module):
                                   mlp_mode=getattr(args, "mlp_mode", "tc"), gemm_mode=getattr(args, "gemm_mode", "tc"))
         return self._engine
 
+    def seed(self):
+        """Philox key of this process: args.seed with the data-parallel rank folded into the upper half, so that pixel shards
+        draw independent jitter / density noise / inverse-CDF samples, as the reference's draws over a full batch are."""
+        from .parallel import rank
+        return self._seed ^ (rank() << 32)
+
     def _render_params(self, nets):
         """The 24 (+24) parameters in bnrf_set_weights order; the Parameter objects live as long as the modules, so the
         list is built once (named_parameters() walks the module tree: ~60 % of a training step's host time if redone)."""
@@ -214,10 +220,10 @@ class Graph(nn.Module):
         nets = [self.nerf] + ([self.nerf_fine] if hasattr(self, "nerf_fine") else [])
         params = self._render_params(nets)
         if torch.is_grad_enabled() and (poses.requires_grad or any(p.requires_grad for p in params)):
-            call = (eng, ray_idx, H, W, K_np, remap_t, rng, self._seed, self._render_calls, len(nets) > 1)
+            call = (eng, ray_idx, H, W, K_np, remap_t, rng, self.seed(), self._render_calls, len(nets) > 1)
             outs = _RenderFn.apply(call, poses, *params)
             return dict(zip([k for k in _OUT_KEYS if len(nets) > 1 or k in ("rgb_map", "disp_map", "acc_map")], outs))
-        return eng.render(poses.detach(), ray_idx, H, W, K_np, remap=remap_t, rng=rng, seed=self._seed, offset=self._render_calls)
+        return eng.render(poses.detach(), ray_idx, H, W, K_np, remap=remap_t, rng=rng, seed=self.seed(), offset=self._render_calls)
 
     @torch.no_grad()
     def render_video(self, iter_step, poses, H, W, K, args, remap, type):

@@ -3,12 +3,24 @@
 train.py itself stays the caller's script; this helper is the step it performs per iteration, used by
 bench.py and the tests: poses -> two Graph.render calls -> image formation + the four loss terms -> backward ->
 ONE gradient all-reduce -> the reference's Adam steps and exponential learning-rate decay (Q17).
+
+Two executions of the same arithmetic:
+  * the DIRECT step (default, fused_optimizer=True): every stage is an explicit call into libbenerf_b200.so -- spline poses,
+    bnrf_render_forward_train x2, bnrf_training_loss (loss + the gradients w.r.t. the renders), bnrf_render_backward x2,
+    bnrf_spline_poses_backward x2, all-reduce, bnrf_adam_step_sched -- with no autograd graph in between.  Everything that
+    changes from iteration to iteration (global_step -> Adam bias corrections, the three decayed learning rates, the Philox
+    stream offset) lives in DEVICE memory, so after two eager iterations the step is captured in a CUDA graph and replayed:
+    the host enqueues one graph launch instead of ~80 kernel launches (the strong-scaled 8-GPU step was bounded by the
+    2.6 ms the host needed for those).
+  * the AUTOGRAD step (fused_optimizer=False, or a tone-mapper being optimised): Graph.render / image_formation.training_loss
+    under torch autograd and the reference's own torch.optim.Adam objects; the reference-shaped cross-check of the former.
 """
 import torch
 
 from . import image_formation as IF
-from .engine import adam_step
-from .parallel import FlatGrads, world
+from .engine import adam_step_sched, step_advance, loss_cfg, training_loss_fused
+from .parallel import FlatGrads, world, rank
+from ._lib import LINEAR_NAMES
 
 
 class Trainer:
@@ -17,12 +29,19 @@ class Trainer:
         self.model, self.graph, self.args = model, model.graph, args
         self.optims = model.setup_optimizer(args)                       # nerf, pose, transform, rgb_crf, event_crf (optimize.py:36-55)
         g = self.graph
-        params = list(g.nerf.parameters()) + (list(g.nerf_fine.parameters()) if hasattr(g, "nerf_fine") else [])
+        self.nets = [g.nerf] + ([g.nerf_fine] if hasattr(g, "nerf_fine") else [])
+        params = [p for m in self.nets for p in m.parameters()]
         params += [g.evt_knot_pose_se3.params.weight, g.transform.params.weight]
+        if not all(p.requires_grad for p in params):
+            raise ValueError("Trainer lays parameters, gradients and moments out as flat buffers in one order: freeze an optimiser "
+                             "with args.optimize_nerf / optimize_pose / optimize_trans, not with requires_grad=False")
+        self.params = params
+        self.crf = bool(getattr(args, "optimize_rgb_crf", False) or getattr(args, "optimize_event_crf", False))
         self.fused = bool(getattr(args, "fused_optimizer", True))
+        self.use_graph = self.fused and not self.crf and bool(getattr(args, "cuda_graph", True))
         if self.fused:
             # parameters, like their gradients, become views of ONE flat buffer (same order), so that the optimiser tail is a
-            # single launch (bnrf_adam_step); state_dict / load_state_dict / init_nerf keep working on the views
+            # single launch (bnrf_adam_step_sched); state_dict / load_state_dict / init_nerf keep working on the views
             self.flat_params = torch.cat([p.data.reshape(-1) for p in params])
             off, n_nerf = 0, sum(p.numel() for p in params[:-2])
             for p in params:
@@ -30,56 +49,275 @@ class Trainer:
                 off += p.numel()
             self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.flat_params), torch.zeros_like(self.flat_params)
             self.group_ranges = [(0, n_nerf), (n_nerf, n_nerf + 24), (n_nerf + 24, n_nerf + 30)]      # nerf(s), knots [4,6], transform [1,6]
+            self.step_dev = torch.zeros(1, device=self.flat_params.device, dtype=torch.int64)        # train.py's global_step, on the device
         self.flat = FlatGrads(params)
         self.base_lr = [[grp["lr"] for grp in o.param_groups] for o in self.optims]
         self.global_step = 0
         self.phase_ms = None           # set to a list to get synchronised per-phase wall times (debug aid; serialises the step)
+        self._cg = None                # captured iteration: (CUDAGraph, signature, static inputs, outputs)
+        self._eager_direct_steps = 0
+        self.launches_per_step = None  # kernels in one captured iteration (library launches + the torch ops of the step)
 
-    def step(self, events_accu, idx_evt, idx_rgb, blur_target, ts_evt, ts_rgb, H, W, K, K_event, H_ev=None, W_ev=None):
+    # ---------------------------------------------------------------------------------------------------------------------------
+    def step(self, events_accu, idx_evt, idx_rgb, blur_target, ts_evt, ts_rgb, H, W, K, K_event, H_ev=None, W_ev=None, remap_evt=None,
+             remap_rgb=None):
         """idx_* are THIS rank's pixels; events_accu [H_ev, W_ev] float64; blur_target [R_rgb, C].  Returns (loss, parts)."""
+        if self.fused:
+            p0, p1 = self.params[0], self.params[-1]
+            if p0.data_ptr() != self.flat_params.data_ptr() or p1.data_ptr() != self.flat_params[-p1.numel():].data_ptr():
+                raise RuntimeError("a parameter no longer aliases Trainer.flat_params (graph.to() / p.data = ... after Trainer was built)")
+        if not self.fused or self.crf:
+            return self._step_autograd(events_accu, idx_evt, idx_rgb, blur_target, ts_evt, ts_rgb, H, W, K, K_event, H_ev, W_ev, remap_evt, remap_rgb)
+        H_ev, W_ev = H_ev or H, W_ev or W
+        a = self.args
+        dev = self.flat_params.device
+        use_remap = a.dataset == "TUM_VIE"
+        inputs = {"events_accu": events_accu, "idx_evt": idx_evt, "idx_rgb": idx_rgb, "blur_target": blur_target,
+                  "ts_evt": self._linspace(ts_evt, 2), "ts_rgb": self._linspace(ts_rgb, a.num_interpolated_pose),
+                  "remap_evt": remap_evt if use_remap else None, "remap_rgb": remap_rgb if use_remap else None}
+        consts = (int(H), int(W), int(H_ev), int(W_ev), _as_tuple(K), _as_tuple(K_event))
+        if self.use_graph and self.phase_ms is None:
+            sig = (consts, tuple((k, None if v is None else (tuple(v.shape), v.dtype)) for k, v in inputs.items()))
+            if self._cg is not None and self._cg[1] == sig:
+                out = self._replay(inputs)
+            elif self._eager_direct_steps >= 2:
+                out = self._capture(sig, inputs, consts)
+            else:
+                out = self._step_direct({k: _dev(v, dev) for k, v in inputs.items()}, consts)
+                self._eager_direct_steps += 1
+        else:
+            out = self._step_direct({k: _dev(v, dev) for k, v in inputs.items()}, consts)
+        self._host_bookkeeping()
+        loss_out = out
+        return loss_out[0], dict(zip(IF.PART_KEYS, (loss_out[1], loss_out[2], loss_out[3], loss_out[4])))
+
+    def _linspace(self, ts2, num):
+        """get_pose_evt / get_pose_rgb (model/optimize.py:58-111): linspace(ts[0], ts[1], num); device tensors pass through."""
+        if isinstance(ts2, torch.Tensor) and ts2.is_cuda and ts2.numel() == num:
+            return ts2
+        return torch.linspace(float(ts2[0]), float(ts2[1]), num)
+
+    def _host_bookkeeping(self):
+        # lr = lr0 * rate ** (step / (lrate_decay * 1000)) with one rate per optimiser, applied after the step (train.py:355-394);
+        # the fused tail evaluates the same expression on the device, these mirrors keep optimizer.param_groups readable
+        a = self.args
+        decay_steps = getattr(a, "lrate_decay", 200) * 1000
+        for o, base, rate in zip(self.optims, self.base_lr, self._rates()):
+            for grp, lr0 in zip(o.param_groups, base):
+                grp["lr"] = lr0 * rate ** (self.global_step / decay_steps)
+        self.global_step += 1
+
+    def _rates(self):
+        a = self.args
+        return [getattr(a, k, d) for k, d in (("decay_rate", 0.1), ("decay_rate_pose", 0.01), ("decay_rate_transform", 0.01),
+                                              ("decay_rate_rgb_crf", 0.1), ("decay_rate_event_crf", 0.1))]
+
+    # ---------------------------------------------------------------------------------------------------------------------------
+    def _tables(self, eng):
+        """ctypes pointer tables into the flat buffers (they never move): weights for bnrf_set_weights, gradients for
+        bnrf_render_backward; built once."""
+        if getattr(self, "_tab", None) is None:
+            names = [n + sfx for n in LINEAR_NAMES for sfx in (".weight", ".bias")]
+            w, gt = [], []
+            for m in self.nets:
+                table = dict(m.named_parameters())
+                w.append({n: table[n] for n in names})
+                gt.append(eng._grad_table({n: table[n].grad for n in names}))
+            self._tab = (w, gt)
+        return self._tab
+
+    def _step_direct(self, t, consts):
+        """One iteration as explicit library calls on the current stream; t: device tensors, consts: host constants."""
+        g, a = self.graph, self.args
+        H, W, H_ev, W_ev, K, K_event = consts
+        eng = g.engine(a)
+        mark = self._mark
+        mark(None)
+        weights, grad_tabs = self._tables(eng)
+        for net, params in enumerate(weights):                           # the parameters changed (bnrf_adam_step_sched wrote them in place)
+            eng.set_weights(net, params)
+        knots = g.evt_knot_pose_se3.params.weight.data
+        transform = g.transform.params.weight.data.reshape(6)
+        seed = g.seed()
+        poses_evt = eng.spline_poses(knots, None, t["ts_evt"], a.traj)
+        poses_rgb = eng.spline_poses(knots, transform, t["ts_rgb"], a.traj)
+        fine = len(self.nets) > 1
+        rets, saved = {}, {}
+        for i, (tag, poses, idx, hh, ww, kk) in enumerate((("evt", poses_evt, t["idx_evt"], H_ev, W_ev, K_event),
+                                                          ("rgb", poses_rgb, t["idx_rgb"], H, W, K))):
+            n = poses.shape[0] * idx.numel()
+            saved[tag] = self._buffer("saved_" + tag, eng.saved_bytes(n))
+            rets[tag] = eng.render(poses, idx, hh, ww, kk, remap=t["remap_" + tag], seed=seed, offset=i + 1, saved=saved[tag],
+                                   offset_dev=self.step_dev, want_sigma=False)
+        mark("forward")
+        coarse_key = "rgb0" if fine else "rgb_map"
+        loss_out, (d_ef, d_ec, d_bf, d_bc) = training_loss_fused(
+            loss_cfg(a), rets["evt"]["rgb_map"], rets["evt"][coarse_key], t["events_accu"], t["idx_evt"], rets["rgb"]["rgb_map"],
+            rets["rgb"][coarse_key], t["blur_target"], all_reduce=IF._rank_sum())
+        mark("loss")
+        d_poses = torch.zeros(poses_evt.shape[0] + poses_rgb.shape[0], 3, 4, device=eng.device)
+        d_pe, d_pr = d_poses[:poses_evt.shape[0]], d_poses[poses_evt.shape[0]:]
+        gc, gf = grad_tabs[0], grad_tabs[1] if fine else None
+        eng.render_backward(poses_rgb, t["idx_rgb"], H, W, K, saved["rgb"], d_bf, d_bc if fine else None, gc, gf, d_pr, remap=t["remap_rgb"])
+        eng.render_backward(poses_evt, t["idx_evt"], H_ev, W_ev, K_event, saved["evt"], d_ef, d_ec if fine else None, gc, gf, d_pe,
+                            remap=t["remap_evt"])
+        gk, gt = g.evt_knot_pose_se3.params.weight.grad, g.transform.params.weight.grad.reshape(6)
+        eng.spline_poses_backward(knots, transform, t["ts_rgb"], d_pr, a.traj, d_knots=gk, d_transform=gt)
+        eng.spline_poses_backward(knots, None, t["ts_evt"], d_pe, a.traj, d_knots=gk)
+        mark("backward")
+        self.flat.all_reduce_sum()                                       # the single exchange of the step
+        mark("all_reduce")
+        flags = [getattr(a, "optimize_nerf", True), getattr(a, "optimize_pose", True), getattr(a, "optimize_trans", False)]
+        rates = self._rates()
+        groups = [(b, e, self.base_lr[k][0], rates[k], flags[k]) for k, (b, e) in enumerate(self.group_ranges)]
+        adam_step_sched(self.flat_params, self.flat.flat, self.exp_avg, self.exp_avg_sq, groups, self.step_dev,
+                        getattr(a, "lrate_decay", 200) * 1000, grad_scale=1.0 / world(), zero_grads=True)
+        step_advance(self.step_dev)                                      # global_step += 1
+        eng.invalidate_weights()                                         # for Graph.render callers outside this step (evaluation)
+        mark("optimizer")
+        return loss_out
+
+    def _buffer(self, name, nbytes):
+        bufs = self.__dict__.setdefault("_bufs", {})
+        if name not in bufs or bufs[name].numel() < nbytes:
+            bufs[name] = torch.empty(nbytes, device=self.flat_params.device, dtype=torch.uint8)
+        return bufs[name]
+
+    # ---------------------------------------------------------------------------------------------------------------------------
+    def _capture(self, sig, inputs, consts):
+        dev = self.flat_params.device
+        static = {k: (None if v is None else _dev(v, dev).clone()) for k, v in inputs.items()}
+        eng = self.graph.engine(self.args)
+        torch.cuda.synchronize()
+        before = eng.launch_count()
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg, capture_error_mode="thread_local"):
+            out = self._step_direct(static, consts)
+        # library kernels + torch's own nodes: the d_poses fill and the NCCL all-reduce(s) of the gradient buffer / batch norms
+        self.launches_per_step = eng.launch_count() - before + 1 + (world() > 1) * (1 + (self.args.event_threshold <= 0))
+        self._cg = (cg, sig, static, out, {k: None for k in static})
+        return self._replay(inputs)
+
+    def _replay(self, inputs):
+        cg, _, static, out, seen = self._cg
+        for k, v in inputs.items():
+            if v is None:
+                continue
+            # small host tensors (the two timestamp vectors) are compared by value, device tensors by identity + version
+            key = ("v", tuple(v.tolist())) if (not v.is_cuda and v.numel() <= 64) else (v.data_ptr(), v._version, v.device)
+            if seen[k] != key:                       # the caller passed new data: refresh the captured iteration's input
+                static[k].copy_(v, non_blocking=True)
+                seen[k] = key
+        cg.replay()
+        return out
+
+    # ---------------------------------------------------------------------------------------------------------------------------
+    def _step_autograd(self, events_accu, idx_evt, idx_rgb, blur_target, ts_evt, ts_rgb, H, W, K, K_event, H_ev, W_ev, remap_evt, remap_rgb):
         g, a = self.graph, self.args
         mark = self._mark
         mark(None)
         poses_evt = g.get_pose_evt(a, ts_evt)
         poses_rgb = g.get_pose_rgb(a, ts_rgb)
+        g._render_calls = 64 * self.global_step          # same Philox stream offsets as the direct step: 64 * global_step + call index
         ret_evt = g.render(self.global_step, poses_evt, idx_evt, H_ev or H, W_ev or W, K_event, a, enable_crf=True, sensor_type="event",
-                           remap=None, training=True)
-        ret_rgb = g.render(self.global_step, poses_rgb, idx_rgb, H, W, K, a, enable_crf=True, sensor_type="rgb", remap=None, training=True)
+                           remap=remap_evt, training=True)
+        ret_rgb = g.render(self.global_step, poses_rgb, idx_rgb, H, W, K, a, enable_crf=True, sensor_type="rgb", remap=remap_rgb, training=True)
         mark("forward")
+        if getattr(a, "optimize_event_crf", False):                      # train.py:176-185
+            ret_evt = {k: g.event_crf.forward(ret_evt[k]) for k in ("rgb_map", "rgb0")}
+        if getattr(a, "optimize_rgb_crf", False):                        # train.py:186-192
+            ret_rgb = {k: g.rgb_crf.forward(ret_rgb[k]) for k in ("rgb_map", "rgb0")}
         loss, parts = IF.training_loss(ret_evt, ret_rgb, events_accu, idx_evt, blur_target, a)
+        for o in self.optims[3:]:
+            o.zero_grad()
         if not self.fused:
             self.flat.zero()
         mark("loss")
         loss.backward()
         mark("backward")
-        opt_nerf, opt_pose, opt_trans = self.optims[0], self.optims[1], self.optims[2]
-        flags = [getattr(a, "optimize_nerf", True), getattr(a, "optimize_pose", True), getattr(a, "optimize_trans", False)]
+        flags = [getattr(a, "optimize_nerf", True), getattr(a, "optimize_pose", True), getattr(a, "optimize_trans", False),
+                 getattr(a, "optimize_rgb_crf", False), getattr(a, "optimize_event_crf", False)]
         if self.fused:
-            self.flat.all_reduce_sum()                                   # the single exchange of the step
+            self.flat.all_reduce_sum()
             mark("all_reduce")
-            groups = [(b, e, o.param_groups[0]["lr"], f) for (b, e), o, f in zip(self.group_ranges, self.optims[:3], flags)]
-            adam_step(self.flat_params, self.flat.flat, self.exp_avg, self.exp_avg_sq, groups, self.global_step + 1,
-                      grad_scale=1.0 / world(), zero_grads=True)         # averages, steps all three optimisers, clears the gradients
+            rates = self._rates()
+            groups = [(b, e, self.base_lr[k][0], rates[k], flags[k]) for k, (b, e) in enumerate(self.group_ranges)]
+            adam_step_sched(self.flat_params, self.flat.flat, self.exp_avg, self.exp_avg_sq, groups, self.step_dev,
+                            getattr(a, "lrate_decay", 200) * 1000, grad_scale=1.0 / world(), zero_grads=True)
+            step_advance(self.step_dev)
             g.engine(a).invalidate_weights()                             # in-place update torch's version counters do not see
         else:
             self.flat.all_reduce_mean()
             mark("all_reduce")
-            if flags[0]:
-                opt_nerf.step()
-            if flags[1]:
-                opt_pose.step()
-            if flags[2]:
-                opt_trans.step()
-        # lr = lr0 * rate ** (step / (lrate_decay * 1000)) with one rate per optimiser, applied after the step (train.py:355-394)
-        decay_steps = getattr(a, "lrate_decay", 200) * 1000
-        rates = [getattr(a, k, d) for k, d in (("decay_rate", 0.1), ("decay_rate_pose", 0.01), ("decay_rate_transform", 0.01),
-                                               ("decay_rate_rgb_crf", 0.1), ("decay_rate_event_crf", 0.1))]
-        for o, base, rate in zip(self.optims, self.base_lr, rates):
-            for grp, lr0 in zip(o.param_groups, base):
-                grp["lr"] = lr0 * rate ** (self.global_step / decay_steps)
+            for o, f in zip(self.optims[:3], flags[:3]):
+                if f:
+                    o.step()
+        for o, f in zip(self.optims[3:], flags[3:]):                     # tone-mapper optimisers (train.py:349-352); their few hundred
+            if f:                                                        # parameters are averaged over the ranks like the rest
+                if world() > 1:
+                    import torch.distributed as dist
+                    for grp in o.param_groups:
+                        for p in grp["params"]:
+                            if p.grad is not None:
+                                dist.all_reduce(p.grad)
+                                p.grad.div_(world())
+                o.step()
         mark("optimizer")
-        self.global_step += 1
+        self._host_bookkeeping()
         return loss.detach(), parts
+
+    # ---------------------------------------------------------------------------------------------------------------------------
+    # Reference-format optimiser state (train.py:443-455 saves optimizer.state_dict() x5, test.py:102-106 reloads them): the fused
+    # tail keeps the Adam moments in flat buffers, these two calls mirror them into / out of the torch.optim.Adam objects.
+    def export_optimizer_state(self):
+        """Flat moments + step count -> optimizer.state of the three Adam objects (so optimizer.state_dict() is a checkpoint)."""
+        if not self.fused:
+            return
+        step = float(self.global_step)
+        off = 0
+        owners = [self.optims[0]] * (len(self.params) - 2) + [self.optims[1], self.optims[2]]
+        for p, o in zip(self.params, owners):
+            n = p.numel()
+            o.state[p] = {"step": torch.tensor(step), "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
+                          "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p).clone()}
+            off += n
+
+    def import_optimizer_state(self):
+        """optimizer.state (e.g. after optimizer.load_state_dict of a reference checkpoint) -> flat moments + step count."""
+        if not self.fused:
+            return
+        off, step = 0, None
+        owners = [self.optims[0]] * (len(self.params) - 2) + [self.optims[1], self.optims[2]]
+        for p, o in zip(self.params, owners):
+            n = p.numel()
+            st = o.state.get(p)
+            if st:
+                self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                step = int(st["step"]) if step is None else step
+            off += n
+        if step is not None:
+            self.global_step = step
+            self.step_dev.fill_(step)
+
+    def state_dict(self):
+        """The optimiser part of the reference's checkpoint (train.py:447-452) + the step counter."""
+        self.export_optimizer_state()
+        keys = ("optimizer_nerf", "optimizer_pose", "optimizer_trans", "optimizer_rgb_crf", "optimizer_event_crf")
+        sd = {k: o.state_dict() for k, o in zip(keys, self.optims)}
+        sd["global_step"] = self.global_step
+        return sd
+
+    def load_state_dict(self, sd):
+        keys = ("optimizer_nerf", "optimizer_pose", "optimizer_trans", "optimizer_rgb_crf", "optimizer_event_crf")
+        for k, o in zip(keys, self.optims):
+            if k in sd:
+                o.load_state_dict(sd[k])
+        self.import_optimizer_state()
+        if "global_step" in sd:
+            self.global_step = int(sd["global_step"])
+            if self.fused:
+                self.step_dev.fill_(self.global_step)
 
     def _mark(self, name):
         if self.phase_ms is None:
@@ -90,3 +328,16 @@ class Trainer:
         if name is not None:
             self.phase_ms.append((self.global_step, name, round((now - self._t_prev) * 1e3, 2)))
         self._t_prev = now
+
+
+def _dev(v, dev):
+    if v is None:
+        return None
+    if not isinstance(v, torch.Tensor):
+        v = torch.as_tensor(v)
+    return v.to(device=dev).contiguous()
+
+
+def _as_tuple(K):
+    import numpy as np
+    return tuple(float(x) for x in np.asarray(K.cpu() if isinstance(K, torch.Tensor) else K, dtype=np.float32).reshape(-1))

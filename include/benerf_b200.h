@@ -43,8 +43,10 @@ typedef enum {
 } bnrf_status;
 
 /* MLP arithmetic (cfg.mlp_mode).  Both run on the GPU; there is no host path. */
-#define BNRF_MLP_TC_FP16X2 0  /* tcgen05.mma kind::f16, 2-term split operands (hi*hi + lo*hi + hi*lo), fp32 TMEM accumulate */
+#define BNRF_MLP_TC_FP16X2 0  /* tcgen05.mma kind::f16 on CTA pairs, 2-term split operands (hi*hi + lo*hi + hi*lo), fp32 TMEM accumulate;
+                               * hidden state kept in tensor memory, A operand read from TMEM (mlp_tc3.cu) */
 #define BNRF_MLP_SIMT_FP32 1  /* plain fp32 FFMA; on-device cross-check of the tensor-core path */
+#define BNRF_MLP_TC_PAIR_SS 3 /* round-1 CTA-pair kernel: activations as a shared-memory A operand (mlp_tc2.cu); cross-check of mode 0 */
 #define BNRF_MLP_TC_1CTA 2    /* same arithmetic as mode 0 on single CTAs (cta_group::1); mode 0 runs CTA pairs (cta_group::2) */
 
 /* Backward-pass GEMMs (cfg.gemm_mode). */
@@ -93,6 +95,9 @@ typedef struct {
      * depths lets the fine network be compared on identical samples.  NULL in production. */
     const float* z_fine;
     uint64_t seed, offset;
+    const uint64_t* offset_dev; /* NULL, or a device counter: the effective stream offset is offset + 64 * (*offset_dev).  A training
+                                 * loop captured in a CUDA graph keeps its iteration count there (bnrf_step_advance), so that
+                                 * replays draw fresh numbers although the launch arguments are frozen */
 } bnrf_rng;
 
 /* Outputs of Graph.render (model/nerf.py:336-343); any pointer may be NULL to skip it. */
@@ -166,7 +171,7 @@ typedef struct {
  * backward kernels read them with cp.async.bulk.  The backward call must see the weights the forward call used
  * (no bnrf_set_weights in between). */
 size_t bnrf_saved_bytes(const bnrf_ctx* ctx, int64_t n_rays);
-/* bnrf_render_forward that additionally fills `saved`.  Needs cfg.mlp_mode == BNRF_MLP_TC_FP16X2. */
+/* bnrf_render_forward that additionally fills `saved`.  Needs cfg.mlp_mode == BNRF_MLP_TC_FP16X2 or BNRF_MLP_TC_PAIR_SS. */
 int bnrf_render_forward_train(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R,
                               int H, int W, const float* K, const float* remap, const bnrf_rng* rng,
                               const bnrf_outputs* out, void* workspace, size_t workspace_bytes,
@@ -228,6 +233,40 @@ int bnrf_accumulate_events(const int32_t* x, const int32_t* y, const float* pol,
                            int H, int W, double* out, void* stream);
 
 /* -------------------------------------------------------------------------------------- */
+/* a14, a15: the loss block of one iteration, forward + gradients w.r.t. the rendered tensors -- train.py:163-177 (event pair,
+ * target gather), 205-292 (event loss), 294-331 (blur mean + rgb loss), loss/imgloss.py:3-5 */
+
+typedef struct {
+    int32_t channels;         /* C: 1 | 3 */
+    int32_t n_poses;          /* P: virtual poses of the blur render (args.num_interpolated_pose) */
+    int32_t log_mode;         /* 0 = log(x + 1e-9) (BeNeRF_*), 1 = lin-log on 255 x (E2NeRF_*), utils/math_utils.py:4-23 */
+    int32_t event_loss;       /* args.event_loss (train.py:205); 0: the event terms are 0 and get no gradient */
+    int32_t rgb_loss;         /* args.rgb_loss (train.py:294) */
+    float event_threshold;    /* > 0: mse(d, t * threshold) * event_coeff_syn (train.py:207-236); else both sides divided by their
+                               * L2 norm over the ray batch, * event_coeff_real (train.py:238-292) */
+    float event_coeff_syn, event_coeff_real, rgb_coeff;
+} bnrf_loss_cfg;
+
+/* Bytes of the device workspace of the two calls below (sums + the event differences of both levels). */
+size_t bnrf_training_loss_workspace_bytes(int64_t R_e);
+/* Stage 1.  evt_fine / evt_coarse: rgb_map / rgb0 of the event render, device [2 R_e, C] (start poses first); events_accu:
+ * device float64 accumulated event image, gathered at idx_evt (device int64 [R_e]); blur_fine / blur_coarse: rgb_map / rgb0 of
+ * the blur render, device [P R_b, C] pose-major; blur_target device [R_b, C].  Writes the gradients of the total loss w.r.t.
+ * the four renders (same shapes; any may be NULL) and loss_out (device double [5]: total, event fine, event coarse, rgb fine,
+ * rgb coarse) -- except, for the NORMALISED event loss, the event gradients and loss_out, which bnrf_training_loss_finish
+ * writes.  workspace[0..4] then hold sum d^2 (fine), sum d t (fine), sum d^2 (coarse), sum d t (coarse), sum t^2 of THIS
+ * rank's pixels as doubles: with pixel-sharded ranks the caller all-reduces these five numbers between the two calls, so that
+ * every rank normalises by the norms of the whole batch exactly as a single process would. */
+int bnrf_training_loss(const bnrf_loss_cfg* cfg, const float* evt_fine, const float* evt_coarse, const double* events_accu,
+                       const int64_t* idx_evt, int64_t R_e, const float* blur_fine, const float* blur_coarse,
+                       const float* blur_target, int64_t R_b, void* workspace, float* d_evt_fine, float* d_evt_coarse,
+                       float* d_blur_fine, float* d_blur_coarse, double* loss_out, void* stream);
+/* Stage 2 (a no-op unless cfg->event_loss and cfg->event_threshold <= 0): event gradients and loss_out of the normalised loss. */
+int bnrf_training_loss_finish(const bnrf_loss_cfg* cfg, const float* evt_fine, const float* evt_coarse, const double* events_accu,
+                              const int64_t* idx_evt, int64_t R_e, int64_t R_b, void* workspace, float* d_evt_fine,
+                              float* d_evt_coarse, double* loss_out, void* stream);
+
+/* -------------------------------------------------------------------------------------- */
 /* f3: fused optimiser tail -- train.py:343-394 (optimizer.step() x3, learning-rate decay, zero_grad),
  * model/optimize.py:36-55 (torch.optim.Adam, default betas / eps, no weight decay) */
 
@@ -244,6 +283,24 @@ typedef struct {
 int bnrf_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                    const bnrf_adam_group* groups, int n_groups, int64_t step, float beta1, float beta2, float eps,
                    float grad_scale, int zero_grads, void* stream);
+
+typedef struct {
+    int64_t begin, end;   /* element range of the group */
+    float lr0;            /* initial learning rate (args.lrate / pose_lrate / transform_lrate) */
+    float decay_rate;     /* args.decay_rate / decay_rate_pose / decay_rate_transform */
+    int32_t active;
+} bnrf_adam_sched_group;
+
+/* bnrf_adam_step for a training loop captured in a CUDA graph: nothing that changes from iteration to iteration is a launch
+ * argument.  step_dev: device counter holding train.py's global_step (0-based) of THIS iteration; the kernel derives the
+ * 1-based Adam step count (bias corrections) and each group's learning rate of train.py:355-394 from it on the device:
+ * lr = lr0 for the first iteration, lr0 * decay_rate ** ((global_step - 1) / decay_steps) afterwards (the reference updates the
+ * rate AFTER optimizer.step(), with the not yet incremented global_step). */
+int bnrf_adam_step_sched(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                         const bnrf_adam_sched_group* groups, int n_groups, const uint64_t* step_dev, double decay_steps,
+                         float beta1, float beta2, float eps, float grad_scale, int zero_grads, void* stream);
+/* *step_dev += 1 (train.py: global_step += 1), enqueued as the last node of the captured iteration. */
+int bnrf_step_advance(uint64_t* step_dev, void* stream);
 
 /* -------------------------------------------------------------------------------------- */
 /* measurement hooks (bench.py): CUDA-event timing of the dominant kernel on its own stream */

@@ -118,7 +118,7 @@ def test_resample_matches_oracle_including_degenerate_rows(fn, eng3):
           f"overall max {err.max():.2e}; {int(on_guard.sum())} rays on the 1e-5 guard")
 
 
-@pytest.mark.parametrize("mode,tol", [("simt", 5e-6), ("tc", 2e-5), ("tc1", 2e-5)])
+@pytest.mark.parametrize("mode,tol", [("simt", 5e-6), ("tc", 2e-5), ("tc2", 2e-5), ("tc1", 2e-5)])
 @pytest.mark.parametrize("name", ["unreal_rgb", "gray_linear"])
 def test_mlp_raw_outputs(name, mode, tol):
     case = CASES[name]
@@ -146,7 +146,7 @@ def test_mlp_tail_tile_and_odd_sample_count():
     v = d / d.norm(dim=-1, keepdim=True)
     z = torch.sort(torch.rand(n, S, generator=g), -1)[0]
     want = mlp.mlp_forward(inp["coarse"], rays.sample_points(o, d, z), v)
-    for mode, tol in (("simt", 5e-6), ("tc", 2e-5), ("tc1", 2e-5)):
+    for mode, tol in (("simt", 5e-6), ("tc", 2e-5), ("tc2", 2e-5), ("tc1", 2e-5)):
         eng = make_engine(case, mode)
         eng.set_weights(0, to_dev(inp["coarse"]))
         raw = eng.op_mlp(0, o.to(DEV), d.to(DEV), v.to(DEV), z.to(DEV))

@@ -23,7 +23,7 @@ def main():
             ret = eng.render(poses, idx, case.H, case.W, case.K, seed=1)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        iters = 5 if mode == "tc" else 2
+        iters = 5 if mode.startswith("tc") else 2
         e0.record()
         for i in range(iters):
             ret = eng.render(poses, idx, case.H, case.W, case.K, seed=2 + i)
