@@ -27,11 +27,6 @@ namespace {
 
 constexpr int kWarps = 4;
 
-__device__ inline double wsum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 __device__ inline float wsumf(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -130,95 +125,109 @@ __global__ void composite_backward_kernel(const float* __restrict__ raw, const f
     if (lane == 0) d_dnorm[ray] += dn_acc;
 }
 
-// ------------------------------------------------------------------ rgb head backward + ReLU of the view layer
-// dZ9[row][j] = (H9[row][j] > 0) * sum_c d_raw[row][c] * W_rgb[c][j]; a thread owns 8 columns of one row and writes them
-// as fp32 (per-ray view-bias sum) and as bf16 hi/lo into the width-128 tile matrix the dgrad / wgrad kernels read.
-// Rows of the last tile beyond `rows` are written as zeros (they take part in the wgrad contraction).
+// ------------------------------------------------------------------ rgb head backward, fused
+// One pass over d_raw [rows, C+1] and the saved view-layer activations H9 [rows, 128] (528 B per row) does what
+// heads_backward_kernel + rgb_head_wgrad_kernel + sum_samples_kernel do in three (2.6 KB per row, the fp32 dZ9 matrix written
+// and re-read): dZ9 as a bf16 hi/lo tile matrix (for the dgrad chain and the weight-gradient contraction), the per-ray sum
+// dvb [n, 128] (gradient of the view bias), its total s [128] (bias of the merged view step), and rgb_linear's weight / bias
+// gradient.  A block of 256 threads = 16 row slots x 16 column chunks of 8 walks whole rays (their S rows are consecutive).
 template <int C>
-__global__ void heads_backward_kernel(const float* __restrict__ d_raw, const float* __restrict__ h9,
-                                      const float* __restrict__ w_rgb, int64_t rows, int64_t rows_pad,
-                                      float* __restrict__ dz9, unsigned char* __restrict__ dz9_tiles) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= rows_pad * (kHalf / 8)) return;
-    const int64_t row = e / (kHalf / 8);
-    const int c8 = (int)(e % (kHalf / 8));
-    float v[8];
+__global__ void __launch_bounds__(256) heads_fused_kernel(const float* __restrict__ d_raw, const float* __restrict__ h9,
+                                                          const float* __restrict__ w_rgb, int64_t n_rays, int S, int64_t rows,
+                                                          int64_t rows_pad, unsigned char* __restrict__ dz9_tiles, float* __restrict__ dvb,
+                                                          float* __restrict__ s_views, float* __restrict__ dW, float* __restrict__ dB) {
+    __shared__ float red[16][kHalf];
+    const int slot = threadIdx.x >> 4, c8 = threadIdx.x & 15;
+    float wr[C][8], accW[C][8], accB[C], tot[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    if (row < rows) {
-        float g[C];
+    for (int c = 0; c < C; ++c) {
+        accB[c] = 0.f;
 #pragma unroll
-        for (int c = 0; c < C; ++c) g[c] = d_raw[row * (C + 1) + c];
-        const float4 a = *reinterpret_cast<const float4*>(h9 + row * kHalf + c8 * 8), b = *reinterpret_cast<const float4*>(h9 + row * kHalf + c8 * 8 + 4);
-        const float h[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float x = 0.f;
-#pragma unroll
-            for (int c = 0; c < C; ++c) x = fmaf(g[c], w_rgb[c * kHalf + c8 * 8 + j], x);
-            v[j] = (h[j] > 0.0f) ? x : 0.0f;
-        }
-        float4* dst = reinterpret_cast<float4*>(dz9 + row * kHalf + c8 * 8);
-        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        for (int j = 0; j < 8; ++j) { wr[c][j] = w_rgb[c * kHalf + c8 * 8 + j]; accW[c][j] = 0.f; }
     }
-    uint4 hi, lo;
-    bwt::split8_bf16_pub(v, hi, lo);
-    const int64_t tile = row / bwt::kTileRows;
-    const int r = (int)(row % bwt::kTileRows);
-    unsigned char* t = dz9_tiles + (size_t)tile * bwt::tile_bytes(kHalf) + (size_t)(c8 / 8) * bwt::kKbBytes + (size_t)r * 128 + ((uint32_t)((c8 & 7) ^ (r & 7)) << 4);
-    *reinterpret_cast<uint4*>(t) = hi;
-    *reinterpret_cast<uint4*>(t + bwt::tile_part_bytes(kHalf)) = lo;
-}
-
-// dvb[ray][j] = sum_s dZ9[ray*S + s][j]  (the view bias is shared by the S samples of a ray)
-__global__ void sum_samples_kernel(const float* __restrict__ dz9, int S, float* __restrict__ dvb) {
-    const int64_t ray = blockIdx.x;
-    const int j = threadIdx.x;
-    float acc = 0.f;
-    for (int s = 0; s < S; ++s) acc += dz9[(ray * S + s) * kHalf + j];
-    dvb[ray * kHalf + j] = acc;
-}
-
-// ------------------------------------------------------------------ rgb_linear: weight and bias gradient
-// dW[c][j] += sum_rows d_raw[row][c] * H9[row][j],  dB[c] += sum_rows d_raw[row][c]   (C x 128: too narrow for a
-// tensor-core tile; HBM-bound at 528 B per row).  A block owns a contiguous range of rows, thread j column j.
-template <int C>
-__global__ void rgb_head_wgrad_kernel(const float* __restrict__ d_raw, const float* __restrict__ h9, int64_t rows,
-                                      int64_t rows_per_block, float* __restrict__ dW, float* __restrict__ dB) {
-    // 256 threads = two interleaved row groups x 128 columns; the loop is a chain of dependent FMAs on L2-latency loads, so it
-    // is unrolled 8x (8 rows in flight per thread) and the grid is sized for ~4 blocks per SM
-    __shared__ float part[(C + 1) * kHalf];
-    const int j = threadIdx.x & (kHalf - 1), grp = threadIdx.x >> 7;
-    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-    const int64_t r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
-    float acc[C], bs = 0.f;
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = 0.f;
-#pragma unroll 8
-    for (int64_t row = r0 + grp; row < r1; row += 2) {
-        const float h = h9[row * kHalf + j];
-        float g[C];
-        if (C == 3) {
-            const float4 q = *reinterpret_cast<const float4*>(d_raw + row * 4);
-            g[0] = q.x; g[1 % C] = q.y; g[2 % C] = q.z;
-        } else {
-            g[0] = d_raw[row * (C + 1)];
+    for (int j = 0; j < 8; ++j) tot[j] = 0.f;
+    auto store_tile = [&](int64_t row, const float* v) {
+        uint4 hi, lo;
+        bwt::split8_bf16_pub(v, hi, lo);
+        const int64_t tile = row / bwt::kTileRows;
+        const int r = (int)(row % bwt::kTileRows);
+        unsigned char* t = dz9_tiles + (size_t)tile * bwt::tile_bytes(kHalf) + (size_t)(c8 / 8) * bwt::kKbBytes + (size_t)r * 128 + ((uint32_t)((c8 & 7) ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(t) = hi;
+        *reinterpret_cast<uint4*>(t + bwt::tile_part_bytes(kHalf)) = lo;
+    };
+    for (int64_t ray = blockIdx.x; ray < n_rays; ray += gridDim.x) {
+        float sum[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum[j] = 0.f;
+        for (int sidx = slot; sidx < S; sidx += 16) {
+            const int64_t row = ray * S + sidx;
+            float g[C];
+            if (C == 3) {
+                const float4 q = *reinterpret_cast<const float4*>(d_raw + row * 4);
+                g[0] = q.x; g[1 % C] = q.y; g[2 % C] = q.z;
+            } else {
+                g[0] = d_raw[row * (C + 1)];
+            }
+            const float4 a = *reinterpret_cast<const float4*>(h9 + row * kHalf + c8 * 8), b = *reinterpret_cast<const float4*>(h9 + row * kHalf + c8 * 8 + 4);
+            const float h[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float x = 0.f;
+#pragma unroll
+                for (int c = 0; c < C; ++c) { x = fmaf(g[c], wr[c][j], x); accW[c][j] = fmaf(g[c], h[j], accW[c][j]); }
+                v[j] = (h[j] > 0.0f) ? x : 0.0f;
+                sum[j] += v[j];
+            }
+            if (c8 == 0) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) accB[c] += g[c];
+            }
+            store_tile(row, v);
         }
 #pragma unroll
-        for (int c = 0; c < C; ++c) acc[c] = fmaf(g[c], h, acc[c]);
-        if (j < C) bs += (j == 0) ? g[0] : (j == 1 ? g[1 % C] : g[2 % C]);
-    }
-    if (grp == 1) {
+        for (int j = 0; j < 8; ++j) { red[slot][c8 * 8 + j] = sum[j]; tot[j] += sum[j]; }
+        __syncthreads();
+        if (threadIdx.x < kHalf) {
+            float t = 0.f;
 #pragma unroll
-        for (int c = 0; c < C; ++c) part[c * kHalf + j] = acc[c];
-        part[C * kHalf + j] = bs;
+            for (int q = 0; q < 16; ++q) t += red[q][threadIdx.x];
+            dvb[ray * kHalf + threadIdx.x] = t;
+        }
+        __syncthreads();
+    }
+    // block totals: the merged view step's bias gradient s, then rgb_linear's weight and bias gradient
+    auto block_reduce_add = [&](const float* vals, float* dst) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[slot][c8 * 8 + j] = vals[j];
+        __syncthreads();
+        if (threadIdx.x < kHalf) {
+            float t = 0.f;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) t += red[q][threadIdx.x];
+            if (t != 0.0f) atomicAdd(dst + threadIdx.x, t);
+        }
+        __syncthreads();
+    };
+    if (s_views) block_reduce_add(tot, s_views);
+#pragma unroll
+    for (int c = 0; c < C; ++c) block_reduce_add(accW[c], dW + c * kHalf);
+    if (c8 == 0) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) red[slot][c] = accB[c];
     }
     __syncthreads();
-    if (grp == 0) {
+    if (threadIdx.x < C) {
+        float t = 0.f;
 #pragma unroll
-        for (int c = 0; c < C; ++c) atomicAdd(dW + c * kHalf + j, acc[c] + part[c * kHalf + j]);
-        if (j < C) atomicAdd(dB + j, bs + part[C * kHalf + j]);
+        for (int q = 0; q < 16; ++q) t += red[q][threadIdx.x];
+        atomicAdd(dB + threadIdx.x, t);
+    }
+    // rows of the last tile (pair) beyond `rows` take part in the weight-gradient contraction: zeros
+    if (blockIdx.x == 0) {
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int64_t row = rows + slot; row < rows_pad; row += 16) store_tile(row, z);
     }
 }
 
@@ -481,17 +490,23 @@ static size_t dg_image_offset(int i) {
 size_t dgrad_images_bytes() { return dg_image_offset(10); }
 
 static int pack_dgrad_images(bnrf_ctx* ctx, int net, cudaStream_t st) {
+    // only the operand image of the configured dgrad path is rebuilt (this runs after every optimiser step)
     NetParams& np = ctx->net[net];
-    bwt::DgImageTable t{};
-    for (int i = 0; i < 10; ++i) {
-        const DgImage& d = kDgImages[i];
-        const float* w = d.step == 10 ? np.wt9m : np.wt[d.step];
-        t.seg[t.n++] = bwt::DgImageSeg{w + (size_t)d.k0 * d.K, np.dg_img + dg_image_offset(i), d.N, d.K};
+    int rc = BNRF_OK;
+    if (ctx->cfg.gemm_mode == BNRF_GEMM_TC) {
+        rc = pack_dgrad_chain_pair_stream(ctx, net, st);
+    } else if (ctx->cfg.gemm_mode == BNRF_GEMM_TC_1CTA) {
+        rc = pack_dgrad_chain_stream(ctx, net, st);
+    } else {
+        bwt::DgImageTable t{};
+        for (int i = 0; i < 10; ++i) {
+            const DgImage& d = kDgImages[i];
+            const float* w = d.step == 10 ? np.wt9m : np.wt[d.step];
+            t.seg[t.n++] = bwt::DgImageSeg{w + (size_t)d.k0 * d.K, np.dg_img + dg_image_offset(i), d.N, d.K};
+        }
+        rc = bwt::pack_dgrad_images(ctx, t, st);
     }
-    int rc = bwt::pack_dgrad_images(ctx, t, st);
     if (rc) return rc;
-    if ((rc = pack_dgrad_chain_stream(ctx, net, st))) return rc;
-    if ((rc = pack_dgrad_chain_pair_stream(ctx, net, st))) return rc;
     np.dg_dirty = false;
     return BNRF_OK;
 }
@@ -517,26 +532,18 @@ static int mlp_backward(bnrf_ctx* ctx, int net, int64_t n, int S, const ActPtrs&
         return bwt::launch_tile_dgrad(ctx, a, st);
     };
 
-    // ---- heads: rgb_linear (128 -> C) and the ReLU of the view layer ----
-    const float* h9 = acts.h9_f32;
+    // ---- heads: rgb_linear (128 -> C) backward, the ReLU of the view layer, the per-ray view-bias gradient: ONE pass ----
+    BNRF_CUDA(ctx, cudaMemsetAsync(w.g_views, 0, (size_t)(kHalf * kWidth + kHalf) * sizeof(float), st));
     {
         const int64_t rows_pad = bwt::tile_alloc(rows) * bwt::kTileRows;  // incl. the pad tile of an odd tile count (CTA pairs walk tiles in pairs)
-        const unsigned grid = (unsigned)ceil_div(rows_pad * (kHalf / 8), 256);
-        if (C == 3) heads_backward_kernel<3><<<grid, 256, 0, st>>>(w.d_raw, h9, np.w_rgb, rows, rows_pad, w.dz9, w.dz9_tiles);
-        else heads_backward_kernel<1><<<grid, 256, 0, st>>>(w.d_raw, h9, np.w_rgb, rows, rows_pad, w.dz9, w.dz9_tiles);
+        const int64_t cap = 4 * (int64_t)ctx->sm_count;
+        const unsigned grid = (unsigned)(n < cap ? n : cap);
+        if (C == 3) heads_fused_kernel<3><<<grid, 256, 0, st>>>(w.d_raw, acts.h9_f32, np.w_rgb, n, S, rows, rows_pad, w.dz9_tiles, w.dvb, w.s_views,
+                                                                dW[BNRF_L_RGB], dB[BNRF_L_RGB]);
+        else heads_fused_kernel<1><<<grid, 256, 0, st>>>(w.d_raw, acts.h9_f32, np.w_rgb, n, S, rows, rows_pad, w.dz9_tiles, w.dvb, w.s_views,
+                                                         dW[BNRF_L_RGB], dB[BNRF_L_RGB]);
         BNRF_LAUNCH_CHECK(ctx);
     }
-    {   // rgb_linear weight + bias gradient
-        const int64_t want = ceil_div(rows, 256), cap = 4 * (int64_t)ctx->sm_count;
-        const int64_t blocks = want < cap ? want : cap;
-        const int64_t rpb = ceil_div(rows, blocks);
-        if (C == 3) rgb_head_wgrad_kernel<3><<<(unsigned)blocks, 2 * kHalf, 0, st>>>(w.d_raw, h9, rows, rpb, dW[BNRF_L_RGB], dB[BNRF_L_RGB]);
-        else rgb_head_wgrad_kernel<1><<<(unsigned)blocks, 2 * kHalf, 0, st>>>(w.d_raw, h9, rows, rpb, dW[BNRF_L_RGB], dB[BNRF_L_RGB]);
-        BNRF_LAUNCH_CHECK(ctx);
-    }
-    // ---- views_linears.0: per-ray sum of dZ9 (the view bias is shared by the S samples of a ray) ----
-    sum_samples_kernel<<<(unsigned)n, kHalf, 0, st>>>(w.dz9, S, w.dvb);
-    BNRF_LAUNCH_CHECK(ctx);
     // ---- dgrad chain: dZ9 -> d feature -> dZ7 -> ... -> dZ0 -> d encoding ----
     if (ctx->cfg.gemm_mode == BNRF_GEMM_TC) {
         // one launch per network: the gradient of a tile stays on the SM across all linears; CTA pairs, each CTA streams half
@@ -557,28 +564,41 @@ static int mlp_backward(bnrf_ctx* ctx, int net, int64_t n, int S, const ActPtrs&
             if ((rc = dgrad(DZ(l), kWidth, 9 - l, bwt::DG_TILE_MASKED, H(l - 1), DZ(l - 1), nullptr, nullptr, 0, nullptr))) return rc;
         if ((rc = dgrad(DZ(0), kWidth, 9, bwt::DG_F32_ACCUM, nullptr, nullptr, w.d_pe, nullptr, 0, nullptr))) return rc;
     }
-    // ---- every 256-wide weight / bias gradient in one launch ----
+    // ---- weight / bias gradients: the eight wide contractions on CTA pairs (wgrad_pair.cu), the two encoded-points blocks on
+    //      single CTAs (bwd_tiles.cu); gemm_mode tc_linear / tc_chain1 keep everything on the single-CTA kernel (cross-check) ----
+    const bool pair = ctx->cfg.gemm_mode == BNRF_GEMM_TC;
     bwt::WgradParams p{};
     p.tiles = tiles; p.rows = rows;
+    bwt::WgradPairParams pp{};
+    pp.tiles = tiles; pp.rows = rows;
     auto job = [&](const unsigned char* dz, int M, const unsigned char* h, int N, float* dWl, int ldw, int col0, int n_valid, float* dBl) {
         bwt::WgradJob& j = p.job[p.n_jobs++];
         j.dz_tiles = dz; j.M = M; j.h_tiles = h; j.N = N; j.dW = dWl; j.ldw = ldw; j.col0 = col0; j.n_valid = n_valid; j.dB = dBl;
         return &j;
     };
+    auto wide = [&](const unsigned char* dz, const unsigned char* h, float* dWl, int ldw, int col0, float* dBl) {
+        if (!pair) { job(dz, kWidth, h, kWidth, dWl, ldw, col0, kWidth, dBl); return; }
+        bwt::WgradPairJob& j = pp.job[pp.n_jobs++];
+        j.a_tiles = dz; j.b_tiles = h; j.NB = kWidth; j.dW = dWl; j.ldw = ldw; j.col0 = col0; j.n_valid = kWidth; j.dB = dBl;
+    };
+    // the bias of layer 5 rides on its wide block when that runs on the pair kernel (bias off the tensor core), else on the narrow one
     job(DZ(0), kWidth, acts.pe_tiles, kPtsChPad, dW[0], kPtsCh, 0, kPtsCh, dB[0]);
+    job(DZ(5), kWidth, acts.pe_tiles, kPtsChPad, dW[5], kPtsCh + kWidth, 0, kPtsCh, pair ? nullptr : dB[5]);
     for (int l = 1; l < 8; ++l) {
-        if (l == 5) {
-            job(DZ(5), kWidth, acts.pe_tiles, kPtsChPad, dW[5], kPtsCh + kWidth, 0, kPtsCh, dB[5]);
-            job(DZ(5), kWidth, H(4), kWidth, dW[5], kPtsCh + kWidth, kPtsCh, kWidth, nullptr);
-        } else {
-            job(DZ(l), kWidth, H(l - 1), kWidth, dW[l], kWidth, 0, kWidth, dB[l]);
-        }
+        if (l == 5) wide(DZ(5), H(4), dW[5], kPtsCh + kWidth, kPtsCh, pair ? dB[5] : nullptr);
+        else wide(DZ(l), H(l - 1), dW[l], kWidth, 0, dB[l]);
     }
-    {   // feature_linear and the feature block of views_linears.0 (merged in the forward pass): ONE contraction
-        // G = sum_rows dZ9 (x) h7, s = sum_rows dZ9; views_feature_wgrad_kernel below turns them into both gradients
-        BNRF_CUDA(ctx, cudaMemsetAsync(w.g_views, 0, (size_t)(kHalf * kWidth + kHalf) * sizeof(float), st));
-        bwt::WgradJob* j = job(w.dz9_tiles, kHalf, H(7), kWidth, w.g_views, kWidth, 0, kWidth, w.s_views);
-        j->wrow = w.d_raw + C; j->wrow_stride = C + 1; j->dWv = dW[BNRF_L_ALPHA]; j->dBv = dB[BNRF_L_ALPHA];   // alpha_linear reads the same h7 slices
+    // feature_linear and the feature block of views_linears.0 (merged in the forward pass): ONE contraction G = sum_rows dZ9 (x) h7
+    // (s = sum_rows dZ9 comes from heads_fused_kernel); views_feature_wgrad_kernel below turns them into both gradients.
+    // alpha_linear reads the same h7 slices.
+    if (pair) {
+        bwt::WgradPairJob& j = pp.job[pp.n_jobs++];
+        j.a_tiles = H(7); j.b_tiles = w.dz9_tiles; j.NB = kHalf; j.dW = w.g_views; j.ldw = kWidth; j.transposed = 1;
+        j.wrow = w.d_raw + C; j.wrow_base = w.d_raw; j.wrow_col = C; j.wrow_stride = C + 1; j.dWv = dW[BNRF_L_ALPHA]; j.dBv = dB[BNRF_L_ALPHA];
+        if ((rc = bwt::launch_tile_wgrad_pair(ctx, pp, st))) return rc;
+    } else {
+        bwt::WgradJob* j = job(w.dz9_tiles, kHalf, H(7), kWidth, w.g_views, kWidth, 0, kWidth, nullptr);
+        j->wrow = w.d_raw + C; j->wrow_stride = C + 1; j->dWv = dW[BNRF_L_ALPHA]; j->dBv = dB[BNRF_L_ALPHA];
     }
     if ((rc = bwt::launch_tile_wgrad(ctx, p, st))) return rc;
     views_feature_wgrad_kernel<<<kHalf + kWidth, kWidth, 0, st>>>(w.g_views, w.s_views, np.wt[8], np.wt[9], np.bias[8], dW[BNRF_L_VIEWS],
@@ -634,7 +654,7 @@ static BwdWorkspace carve_bwd(const bnrf_cfg& c, int64_t n, void* base) {
     w.b.dz_tiles = reinterpret_cast<unsigned char*>(take_bytes(8 * (size_t)w.b.tiles * bwt::tile_bytes(kWidth)));
     w.b.g_views = take(kHalf * kWidth + kHalf); w.b.s_views = w.b.g_views + kHalf * kWidth;
     w.b.dz9_tiles = reinterpret_cast<unsigned char*>(take_bytes((size_t)w.b.tiles * bwt::tile_bytes(kHalf)));
-    w.b.d_pe = take(rows * kPtsChPad); w.b.dz9 = take(rows * kHalf);
+    w.b.d_pe = take(rows * kPtsChPad); w.b.dz9 = nullptr;
     w.b.dvb = take(n * kHalf); w.b.pe_dir = take(n * 32);
     w.g_o = take(n * 3); w.g_d = take(n * 3); w.g_v = take(n * 3); w.g_dn = take(n);
     w.bytes = off;

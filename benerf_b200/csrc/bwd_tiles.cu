@@ -281,32 +281,25 @@ __global__ void __launch_bounds__(wg::THREADS, 1) tile_wgrad_kernel(const __grid
     const int na = jb.M / 64, nb = jb.N / 64;
 
     if (warp == 0) {
-        // producer: lane l moves one 4 KB slice (operand, hi/lo part, 64-column block) per stage
-        const int ncopy = 2 * (na + nb);
-        const unsigned char* src = nullptr;
-        uint32_t dst_off = 0;
-        size_t tile_stride = 0;
-        if (lane < 2 * na) {
-            const int part = lane / na, blk = lane % na;
-            src = jb.dz_tiles + (size_t)part * tile_part_bytes(jb.M) + (size_t)blk * kKbBytes;
-            dst_off = (part ? OFF_A_LO : OFF_A_HI) + (uint32_t)blk * SLICE;
-            tile_stride = tile_bytes(jb.M);
-        } else if (lane < ncopy) {
-            const int l2 = lane - 2 * na, part = l2 / nb, blk = l2 % nb;
-            src = jb.h_tiles + (size_t)part * tile_part_bytes(jb.N) + (size_t)blk * kKbBytes;
-            dst_off = (part ? OFF_B_LO : OFF_B_HI) + (uint32_t)blk * SLICE;
-            tile_stride = tile_bytes(jb.N);
-        }
-        for (uint32_t i = 0; i < iters; ++i) {
-            const uint32_t s = i % NSTAGE, ph = (i / NSTAGE) & 1u;
-            if (lane == 0) {
+        // producer: ONE elected thread issues the 4 KB slices (operand, hi/lo part, 64-column block) of a stage back to back (from
+        // different lanes every cp.async.bulk sits in a ~150-cycle uniformisation loop, which paced the whole kernel)
+        if (elect_one()) {
+            for (uint32_t i = 0; i < iters; ++i) {
+                const uint32_t s = i % NSTAGE, ph = (i / NSTAGE) & 1u;
                 mbar_wait(bar(EMPTY + s), ph ^ 1u, err_flag, 41);
-                mbar_expect_tx(bar(FULL + s), (uint32_t)ncopy * SLICE);
-            }
-            __syncwarp();
-            if (lane < ncopy) {
+                mbar_expect_tx(bar(FULL + s), (uint32_t)(2 * (na + nb)) * SLICE);
                 const size_t t = (size_t)t0 + (i >> 2);
-                tma_bulk_load(base + s * STAGE + dst_off, src + t * tile_stride + (size_t)(i & 3u) * SLICE, SLICE, bar(FULL + s));
+                const uint32_t st = base + s * STAGE;
+                const unsigned char* a = jb.dz_tiles + t * tile_bytes(jb.M) + (size_t)(i & 3u) * SLICE;
+                const unsigned char* h = jb.h_tiles + t * tile_bytes(jb.N) + (size_t)(i & 3u) * SLICE;
+                for (int blk = 0; blk < na; ++blk) {
+                    tma_bulk_load(st + OFF_A_HI + (uint32_t)blk * SLICE, a + (size_t)blk * kKbBytes, SLICE, bar(FULL + s));
+                    tma_bulk_load(st + OFF_A_LO + (uint32_t)blk * SLICE, a + tile_part_bytes(jb.M) + (size_t)blk * kKbBytes, SLICE, bar(FULL + s));
+                }
+                for (int blk = 0; blk < nb; ++blk) {
+                    tma_bulk_load(st + OFF_B_HI + (uint32_t)blk * SLICE, h + (size_t)blk * kKbBytes, SLICE, bar(FULL + s));
+                    tma_bulk_load(st + OFF_B_LO + (uint32_t)blk * SLICE, h + tile_part_bytes(jb.N) + (size_t)blk * kKbBytes, SLICE, bar(FULL + s));
+                }
             }
         }
     } else if (warp == 1) {

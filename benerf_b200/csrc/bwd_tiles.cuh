@@ -66,6 +66,21 @@ struct WgradJob {
 constexpr int kMaxWgradJobs = 12;
 struct WgradParams { WgradJob job[kMaxWgradJobs]; int n_jobs; int tiles; int64_t rows; };
 
+// wgrad_pair.cu: the wide jobs on CTA pairs.  a_tiles: the M-side operand (width 256 = accumulator rows), b_tiles: the N-side
+// operand (width NB = 256 | 128).
+struct WgradPairJob {
+    const unsigned char* a_tiles; const unsigned char* b_tiles; int NB;
+    float* dW; int ldw; int col0; int n_valid;   // !transposed: dW[m * ldw + col0 + n] += D[m][n] for n < n_valid
+    int transposed;                              //  transposed: dW[n * ldw + m] += D[m][n]  (the merged view step's G)
+    float* dB;                                   // += colsum(A operand) (nullable)
+    const float* wrow; int wrow_stride; float* dWv; float* dBv;   // nullable: dWv[m] += sum_rows wrow[row] * A[row][m], dBv += sum wrow
+    const float* wrow_base; int wrow_col;        // wrow == wrow_base + wrow_col: column wrow_col of a [rows, wrow_stride] fp32 matrix (16-byte aligned rows)
+    int64_t unit0; int weight;                   // assigned by the launcher: position on the work line, units per row tile
+};
+constexpr int kMaxPairJobs = 8;
+struct WgradPairParams { WgradPairJob job[kMaxPairJobs]; int n_jobs; int tiles; int64_t rows; int64_t units; };
+int launch_tile_wgrad_pair(bnrf_ctx* ctx, WgradPairParams& p, cudaStream_t st);
+
 int launch_tile_dgrad(bnrf_ctx* ctx, const DgradArgs& a, cudaStream_t st);
 int launch_tile_wgrad(bnrf_ctx* ctx, WgradParams& p, cudaStream_t st);   // assigns cta0 / ctas
 // fp32 [rows, W] (row stride ld) -> tile matrix (fmt 0 = fp16 hi/lo, 1 = bf16 hi/lo); rows beyond `rows` are zero
