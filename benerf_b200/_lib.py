@@ -23,11 +23,16 @@ class Cfg(C.Structure):
 
 class Rng(C.Structure):
     _fields_ = [("t_rand", C.c_void_p), ("noise_c", C.c_void_p), ("u", C.c_void_p), ("noise_f", C.c_void_p),
-                ("z_fine", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64), ("offset_dev", C.c_void_p)]
+                ("z_fine", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64), ("ray_base", C.c_uint64), ("offset_dev", C.c_void_p)]
 
 
 class Outputs(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0", "sigma", "depth_map", "z_vals")]
+
+
+class RenderSeg(C.Structure):
+    _fields_ = [("poses", C.c_void_p), ("ray_idx", C.c_void_p), ("P", C.c_int32), ("R", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("K", C.c_float * 9), ("remap", C.c_void_p)]
 
 
 class AdamGroup(C.Structure):
@@ -65,6 +70,9 @@ PROTOTYPES = {
     "bnrf_backward_workspace_bytes": (_Z, [_P, _L]),
     "bnrf_render_forward_train": (_I, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(C.c_float), _P, C.POINTER(Rng), C.POINTER(Outputs), _P, _Z, _P, _Z, _P]),
     "bnrf_render_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(C.c_float), _P, _P, _P, _P, _Z, C.POINTER(ParamGrads), C.POINTER(ParamGrads), _P, _P, _Z, _P]),
+    "bnrf_render_forward_multi": (_I, [_P, C.POINTER(RenderSeg), _I, C.POINTER(Rng), C.POINTER(Outputs), _P, _Z, _P, _Z, _P]),
+    "bnrf_render_backward_multi": (_I, [_P, C.POINTER(RenderSeg), _I, _P, _P, _P, _Z, C.POINTER(ParamGrads), C.POINTER(ParamGrads),
+                                        C.POINTER(_P), _P, _Z, _P]),
     "bnrf_spline_poses_backward": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "bnrf_debug_sgemm": (_I, [_P, _I, _I, _L, _I, _L, _P, _L, _P, _L, _P, _L, _I, _P, _L, _P, _L, _P, _P]),
     "bnrf_op_rays": (_I, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(C.c_float), _P, _P, _P, _P, _P]),

@@ -300,14 +300,17 @@ size_t bnrf_workspace_bytes(const bnrf_ctx* ctx, int64_t n_rays) {
 // Shared body of bnrf_render_forward / bnrf_render_forward_train.  With `saved` the per-ray tensors the backward pass
 // needs (rays, depths, raw outputs, densities) are placed in the caller's saved buffer instead of the scratch
 // workspace and the MLP kernel also writes its activations there.
-static int render_impl(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W,
-                       const float* K, const float* remap, const bnrf_rng* rng, const bnrf_outputs* out,
+static int render_impl(bnrf_ctx* ctx, const bnrf_render_seg* segs, int n_segs, const bnrf_rng* rng, const bnrf_outputs* out,
                        void* workspace, size_t workspace_bytes, void* saved, size_t saved_bytes, void* stream) {
     if (!ctx) return BNRF_ERR_ARG;
-    if (!poses || !ray_idx || !K || !out || !workspace || P <= 0 || R <= 0) return fail(ctx, BNRF_ERR_ARG, "render_forward: bad argument");
+    if (!segs || n_segs <= 0 || n_segs > 4 || !out || !workspace) return fail(ctx, BNRF_ERR_ARG, "render_forward: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     const bnrf_cfg& c = ctx->cfg;
-    const int64_t n = (int64_t)P * R;
+    int64_t n = 0;
+    for (int i = 0; i < n_segs; ++i) {
+        if (!segs[i].poses || !segs[i].ray_idx || segs[i].P <= 0 || segs[i].R <= 0) return fail(ctx, BNRF_ERR_ARG, "render_forward: bad segment %d", i);
+        n += (int64_t)segs[i].P * segs[i].R;
+    }
     Workspace w = carve(c, n, workspace);
     if (workspace_bytes < w.bytes) return fail(ctx, BNRF_ERR_STATE, "render_forward: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
     SavedLayout s{};
@@ -323,7 +326,14 @@ static int render_impl(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx
     const bool fine = c.n_importance > 0;
     const int Sc = c.n_samples, Sf = c.n_samples + c.n_importance;
     int rc;
-    if ((rc = launch_rays(ctx, poses, ray_idx, P, R, H, W, K, remap, w.o, w.d, w.view, st))) return rc;
+    {
+        int64_t off = 0;                    // segments are laid out one after the other, each pose-major
+        for (int i = 0; i < n_segs; ++i) {
+            const bnrf_render_seg& sg = segs[i];
+            if ((rc = launch_rays(ctx, sg.poses, sg.ray_idx, sg.P, sg.R, sg.H, sg.W, sg.K, sg.remap, w.o + 3 * off, w.d + 3 * off, w.view + 3 * off, st))) return rc;
+            off += (int64_t)sg.P * sg.R;
+        }
+    }
     if ((rc = launch_stratified(ctx, r.t_rand, &r, n, Sc, w.z_c, st))) return rc;
     if ((rc = launch_viewbias(ctx, 0, w.view, n, w.vb, st))) return rc;
     if ((rc = run_mlp(ctx, 0, w.o, w.d, w.vb, w.z_c, n, Sc, raw_c, saved ? &s.acts_c : nullptr, st))) return rc;
@@ -351,17 +361,32 @@ static int render_impl(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx
     return BNRF_OK;
 }
 
+static bnrf_render_seg one_seg(const float* poses, const int64_t* ray_idx, int P, int R, int H, int W, const float* K, const float* remap) {
+    bnrf_render_seg s{};
+    s.poses = poses; s.ray_idx = ray_idx; s.P = P; s.R = R; s.H = H; s.W = W; s.remap = remap;
+    if (K) memcpy(s.K, K, sizeof(s.K));
+    return s;
+}
+
 int bnrf_render_forward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W,
                         const float* K, const float* remap, const bnrf_rng* rng, const bnrf_outputs* out,
                         void* workspace, size_t workspace_bytes, void* stream) {
-    return render_impl(ctx, poses, ray_idx, P, R, H, W, K, remap, rng, out, workspace, workspace_bytes, nullptr, 0, stream);
+    if (!K) return fail(ctx, BNRF_ERR_ARG, "render_forward: K is null");
+    const bnrf_render_seg s = one_seg(poses, ray_idx, P, R, H, W, K, remap);
+    return render_impl(ctx, &s, 1, rng, out, workspace, workspace_bytes, nullptr, 0, stream);
+}
+
+int bnrf_render_forward_multi(bnrf_ctx* ctx, const bnrf_render_seg* segs, int n_segs, const bnrf_rng* rng, const bnrf_outputs* out,
+                              void* workspace, size_t workspace_bytes, void* saved, size_t saved_bytes, void* stream) {
+    return render_impl(ctx, segs, n_segs, rng, out, workspace, workspace_bytes, saved, saved_bytes, stream);
 }
 
 int bnrf_render_forward_train(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W,
                               const float* K, const float* remap, const bnrf_rng* rng, const bnrf_outputs* out,
                               void* workspace, size_t workspace_bytes, void* saved, size_t saved_bytes, void* stream) {
-    if (!saved) return fail(ctx, BNRF_ERR_ARG, "render_forward_train: saved buffer is null");
-    return render_impl(ctx, poses, ray_idx, P, R, H, W, K, remap, rng, out, workspace, workspace_bytes, saved, saved_bytes, stream);
+    if (!saved || !K) return fail(ctx, BNRF_ERR_ARG, "render_forward_train: saved buffer / K is null");
+    const bnrf_render_seg s = one_seg(poses, ray_idx, P, R, H, W, K, remap);
+    return render_impl(ctx, &s, 1, rng, out, workspace, workspace_bytes, saved, saved_bytes, stream);
 }
 
 int bnrf_op_rays(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W, const float* K,

@@ -677,17 +677,19 @@ size_t bnrf_backward_workspace_bytes(const bnrf_ctx* ctx, int64_t n_rays) {
     return carve_bwd(ctx->cfg, n_rays, nullptr).bytes;
 }
 
-int bnrf_render_backward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W,
-                         const float* K, const float* remap, const float* d_rgb_map, const float* d_rgb0,
-                         const void* saved, size_t saved_bytes, const bnrf_param_grads* grads_coarse,
-                         const bnrf_param_grads* grads_fine, float* d_poses, void* workspace, size_t workspace_bytes,
-                         void* stream) {
+static int render_backward_impl(bnrf_ctx* ctx, const bnrf_render_seg* segs, int n_segs, const float* d_rgb_map, const float* d_rgb0,
+                                const void* saved, size_t saved_bytes, const bnrf_param_grads* grads_coarse,
+                                const bnrf_param_grads* grads_fine, float* const* d_poses, void* workspace, size_t workspace_bytes,
+                                void* stream) {
     if (!ctx) return BNRF_ERR_ARG;
-    if (!poses || !ray_idx || !K || !saved || !workspace || !d_poses || P <= 0 || R <= 0)
-        return fail(ctx, BNRF_ERR_ARG, "render_backward: bad argument");
+    if (!segs || n_segs <= 0 || n_segs > 4 || !saved || !workspace || !d_poses) return fail(ctx, BNRF_ERR_ARG, "render_backward: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     const bnrf_cfg& c = ctx->cfg;
-    const int64_t n = (int64_t)P * R;
+    int64_t n = 0;
+    for (int i = 0; i < n_segs; ++i) {
+        if (!segs[i].poses || !segs[i].ray_idx || !d_poses[i] || segs[i].P <= 0 || segs[i].R <= 0) return fail(ctx, BNRF_ERR_ARG, "render_backward: bad segment %d", i);
+        n += (int64_t)segs[i].P * segs[i].R;
+    }
     const bool fine = c.n_importance > 0;
     const int Sc = c.n_samples, Sf = c.n_samples + c.n_importance;
     const SavedLayout s = carve_saved(c, n, const_cast<void*>(saved));
@@ -727,10 +729,41 @@ int bnrf_render_backward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_i
         pe_ray_backward_kernel<<<grid, 32 * kWarps, 0, st>>>(acts.pe_f32, w.b.d_pe, z, n, S, w.g_o, w.g_d);
         BNRF_LAUNCH_CHECK(ctx);
     }
-    rays_backward_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(poses, ray_idx, P, R, H, W, K[0], K[4], K[2], K[5], remap,
-                                                                    c.ndc, w.g_o, w.g_d, w.g_v, w.g_dn, d_poses);
-    BNRF_LAUNCH_CHECK(ctx);
+    {
+        int64_t off = 0;
+        for (int i = 0; i < n_segs; ++i) {
+            const bnrf_render_seg& sg = segs[i];
+            const int64_t ns = (int64_t)sg.P * sg.R;
+            rays_backward_kernel<<<(unsigned)ceil_div(ns, 128), 128, 0, st>>>(sg.poses, sg.ray_idx, sg.P, sg.R, sg.H, sg.W, sg.K[0], sg.K[4], sg.K[2], sg.K[5],
+                                                                             sg.remap, c.ndc, w.g_o + 3 * off, w.g_d + 3 * off, w.g_v + 3 * off, w.g_dn + off,
+                                                                             d_poses[i]);
+            BNRF_LAUNCH_CHECK(ctx);
+            off += ns;
+        }
+    }
     return BNRF_OK;
+}
+
+int bnrf_render_backward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W,
+                         const float* K, const float* remap, const float* d_rgb_map, const float* d_rgb0,
+                         const void* saved, size_t saved_bytes, const bnrf_param_grads* grads_coarse,
+                         const bnrf_param_grads* grads_fine, float* d_poses, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+    if (!ctx) return BNRF_ERR_ARG;
+    if (!K || !d_poses) return fail(ctx, BNRF_ERR_ARG, "render_backward: bad argument");
+    bnrf_render_seg sg{};
+    sg.poses = poses; sg.ray_idx = ray_idx; sg.P = P; sg.R = R; sg.H = H; sg.W = W; sg.remap = remap;
+    memcpy(sg.K, K, sizeof(sg.K));
+    float* dp[1] = {d_poses};
+    return render_backward_impl(ctx, &sg, 1, d_rgb_map, d_rgb0, saved, saved_bytes, grads_coarse, grads_fine, dp, workspace, workspace_bytes, stream);
+}
+
+int bnrf_render_backward_multi(bnrf_ctx* ctx, const bnrf_render_seg* segs, int n_segs, const float* d_rgb_map, const float* d_rgb0,
+                               const void* saved, size_t saved_bytes, const bnrf_param_grads* grads_coarse,
+                               const bnrf_param_grads* grads_fine, float* const* d_poses, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+    return render_backward_impl(ctx, segs, n_segs, d_rgb_map, d_rgb0, saved, saved_bytes, grads_coarse, grads_fine, d_poses, workspace,
+                                workspace_bytes, stream);
 }
 
 }  // extern "C"

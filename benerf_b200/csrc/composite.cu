@@ -78,7 +78,7 @@ __global__ void composite_kernel(const float* __restrict__ raw, const float* __r
                 nz = noise[ray * S + s];
             } else {
                 uint32_t w[4];
-                Philox::draw(rng.seed, rng_offset(rng), (uint64_t)ray, (uint32_t)s, stream_id, w);
+                Philox::draw(rng.seed, rng_offset(rng), rng.ray_base + (uint64_t)ray, (uint32_t)s, stream_id, w);
                 nz = Philox::normal(w[0], w[1]);
             }
             const float dens = fmaxf(__fadd_rn(rr[s * (C + 1) + C], nz), 0.0f);     // relu(sigma_raw + noise)
@@ -180,7 +180,7 @@ __global__ void resample_kernel(const float* __restrict__ z_c, const float* __re
             u = u_in[ray * K + j];
         } else {
             uint32_t w[4];
-            Philox::draw(rng.seed, rng_offset(rng), (uint64_t)ray, (uint32_t)j, kStreamU, w);
+            Philox::draw(rng.seed, rng_offset(rng), rng.ray_base + (uint64_t)ray, (uint32_t)j, kStreamU, w);
             u = Philox::uniform(w[0]);
         }
         // searchsorted(cdf, u, right=True): first index with cdf[idx] > u

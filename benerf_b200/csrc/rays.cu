@@ -76,7 +76,7 @@ __global__ void stratified_kernel(const float* __restrict__ t_vals, const float*
         r = t_rand[e];
     } else {
         uint32_t w[4];
-        Philox::draw(rng.seed, rng_offset(rng), (uint64_t)(e / S), (uint32_t)s, kStreamTRand, w);
+        Philox::draw(rng.seed, rng_offset(rng), rng.ray_base + (uint64_t)(e / S), (uint32_t)s, kStreamTRand, w);
         r = Philox::uniform(w[0]);
     }
     z[e] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), r));

@@ -133,7 +133,7 @@ class Engine:
         return (C.c_float * 9)(*flat)
 
     def render(self, poses, ray_idx, H, W, K, remap=None, rng=None, seed=0, offset=0, want_sigma=True, want_depth=False, want_z=False,
-               saved=None, offset_dev=None):
+               saved=None, offset_dev=None, ray_base=0):
         """Graph.render (model/nerf.py:236-343).  rng: dict of the four draws (parity mode) or None (Philox).
         saved: uint8 device tensor of saved_bytes(N) bytes -> training mode (bnrf_render_forward_train)."""
         P, R = poses.shape[0], ray_idx.numel()
@@ -150,7 +150,7 @@ class Engine:
         z_vals = new(n, Sf) if want_z else None
         outs = _lib.Outputs(*[_ptr(ret.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0", "sigma")],
                             _ptr(depth), _ptr(z_vals))
-        r = _lib.Rng(None, None, None, None, None, int(seed), int(offset), _ptr(offset_dev, torch.int64, name="offset_dev"))
+        r = _lib.Rng(None, None, None, None, None, int(seed), int(offset), int(ray_base), _ptr(offset_dev, torch.int64, name="offset_dev"))
         if rng is not None:
             r.t_rand, r.noise_c = _ptr(rng["t_rand"], name="t_rand"), _ptr(rng["noise_c"], name="noise_c")
             if self.n_importance > 0:
@@ -172,6 +172,53 @@ class Engine:
         if want_z:
             ret["z_vals"] = z_vals
         return ret
+
+    def _segs(self, segs):
+        """segs: [(poses [P,3,4], ray_idx [R], H, W, K, remap or None), ...] -> (bnrf_render_seg array, total rays)."""
+        arr = (_lib.RenderSeg * len(segs))()
+        n = 0
+        for a, (poses, ray_idx, H, W, K, remap) in zip(arr, segs):
+            a.poses, a.ray_idx = _ptr(poses, name="poses").value, _ptr(ray_idx, torch.int64, name="ray_idx").value
+            a.P, a.R, a.H, a.W = poses.shape[0], ray_idx.numel(), int(H), int(W)
+            a.K = self._K(K)
+            a.remap = _ptr(remap, name="remap").value if remap is not None else None
+            n += a.P * a.R
+        return arr, n
+
+    def render_multi(self, segs, seed=0, offset=0, saved=None, offset_dev=None, want_sigma=False):
+        """Several Graph.render calls as ONE ray batch (bnrf_render_forward_multi): outputs cover the concatenated rays of the
+        segments (segment 0 first, each pose-major).  saved: uint8 device tensor of saved_bytes(N) bytes -> training mode."""
+        arr, n = self._segs(segs)
+        Sf = self.n_samples + self.n_importance
+        new = lambda *s: torch.empty(*s, device=self.device, dtype=torch.float32)
+        ret = {"rgb_map": new(n, self.channels), "disp_map": new(n), "acc_map": new(n)}
+        if self.n_importance > 0:
+            ret.update({"rgb0": new(n, self.channels), "disp0": new(n), "acc0": new(n)})
+            if want_sigma:
+                ret["sigma"] = new(n, Sf)
+        outs = _lib.Outputs(*[_ptr(ret.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0", "sigma")], None, None)
+        r = _lib.Rng(None, None, None, None, None, int(seed), int(offset), 0, _ptr(offset_dev, torch.int64, name="offset_dev"))
+        need = self.lib.bnrf_workspace_bytes(self._ctx, n)
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.empty(need, device=self.device, dtype=torch.uint8)
+        self._check(self.lib.bnrf_render_forward_multi(
+            self._ctx, arr, len(segs), C.byref(r), C.byref(outs), C.c_void_p(self._workspace.data_ptr()), self._workspace.numel(),
+            _ptr(saved, torch.uint8, name="saved"), saved.numel() if saved is not None else 0, _stream()), "bnrf_render_forward_multi")
+        return ret
+
+    def render_backward_multi(self, segs, saved, d_rgb_map, d_rgb0, grads_coarse, grads_fine, d_poses):
+        """bnrf_render_backward_multi: d_rgb_map / d_rgb0 over the concatenated rays; d_poses: one [P_i,3,4] tensor per segment."""
+        arr, n = self._segs(segs)
+        need = self.lib.bnrf_backward_workspace_bytes(self._ctx, n)
+        if getattr(self, "_bwd_workspace", None) is None or self._bwd_workspace.numel() < need:
+            self._bwd_workspace = torch.empty(need, device=self.device, dtype=torch.uint8)
+        as_table = lambda g: g if g is None or isinstance(g, _lib.ParamGrads) else self._grad_table(g)
+        gc, gf = as_table(grads_coarse), as_table(grads_fine)
+        dp = (C.c_void_p * len(segs))(*[_ptr(d, name="d_poses").value for d in d_poses])
+        self._check(self.lib.bnrf_render_backward_multi(
+            self._ctx, arr, len(segs), _ptr(d_rgb_map, name="d_rgb_map"), _ptr(d_rgb0, name="d_rgb0"), _ptr(saved, torch.uint8, name="saved"),
+            saved.numel(), C.byref(gc) if gc is not None else None, C.byref(gf) if gf is not None else None, dp,
+            C.c_void_p(self._bwd_workspace.data_ptr()), self._bwd_workspace.numel(), _stream()), "bnrf_render_backward_multi")
 
     # -- a16: backward ------------------------------------------------------------------------
     def saved_bytes(self, n_rays):
@@ -311,15 +358,24 @@ def loss_cfg(args):
                         float(getattr(args, "event_coeff_real", 2.0)), float(getattr(args, "rgb_coeff", 1.0)))
 
 
-def training_loss_fused(cfg, evt_fine, evt_coarse, events_accu, idx_evt, blur_fine, blur_coarse, blur_target, all_reduce=None):
+def training_loss_fused(cfg, evt_fine, evt_coarse, events_accu, idx_evt, blur_fine, blur_coarse, blur_target, all_reduce=None,
+                        out_like=None, split=None):
     """bnrf_training_loss (+ bnrf_training_loss_finish): the loss block of train.py:163-331 and its gradients w.r.t. the four
     renders in one or two launches.  all_reduce: callable summing a float64 device tensor over the ranks in place (the five batch
-    sums of the normalised event loss), or None.  Returns (loss_out float64 [5], (d_evt_fine, d_evt_coarse, d_blur_fine, d_blur_coarse))."""
+    sums of the normalised event loss), or None.  Returns (loss_out float64 [5], (d_evt_fine, d_evt_coarse, d_blur_fine, d_blur_coarse)) -- or, with out_like = (fine, coarse) [n, C]
+    batch tensors whose rows [0, split) are the event render and [split, n) the blur render, the two [n, C] gradient buffers."""
     lib = _lib.load()
     dev = evt_fine.device
     R_e, R_b = idx_evt.numel(), blur_target.shape[0]
     ws = torch.empty(lib.bnrf_training_loss_workspace_bytes(R_e) // 8 + 1, device=dev, dtype=torch.float64)
-    grads = tuple(torch.empty_like(t) for t in (evt_fine, evt_coarse, blur_fine, blur_coarse))
+    if out_like is not None:
+        # the event and blur renders are the two row ranges [0, split) / [split, n) of one batch (Engine.render_multi): their
+        # gradients are written into the matching halves of ONE [n, C] buffer per level, ready for render_backward_multi
+        full = (torch.empty_like(out_like[0]), torch.empty_like(out_like[1]))
+        grads = (full[0][:split], full[1][:split], full[0][split:], full[1][split:])
+    else:
+        full = None
+        grads = tuple(torch.empty_like(t) for t in (evt_fine, evt_coarse, blur_fine, blur_coarse))
     loss_out = torch.empty(5, device=dev, dtype=torch.float64)
     ev = events_accu.reshape(-1)
     _rc(lib.bnrf_training_loss(C.byref(cfg), _ptr(evt_fine, name="evt_fine"), _ptr(evt_coarse, name="evt_coarse"),
@@ -333,7 +389,7 @@ def training_loss_fused(cfg, evt_fine, evt_coarse, events_accu, idx_evt, blur_fi
         _rc(lib.bnrf_training_loss_finish(C.byref(cfg), _ptr(evt_fine), _ptr(evt_coarse), _ptr(ev, torch.float64),
                                           _ptr(idx_evt, torch.int64), R_e, R_b, _ptr(ws, torch.float64), _ptr(grads[0]), _ptr(grads[1]),
                                           _ptr(loss_out, torch.float64), _stream()), "bnrf_training_loss_finish")
-    return loss_out, grads
+    return loss_out, (grads if full is None else full)
 
 
 def _rc(rc, what):

@@ -29,10 +29,10 @@ class _RenderFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, call, poses, *params):
-        eng, ray_idx, H, W, K, remap, rng, seed, offset, n_fine = call
+        eng, ray_idx, H, W, K, remap, rng, seed, offset, n_fine, ray_base = call
         n = poses.shape[0] * ray_idx.numel()
         saved = torch.empty(eng.saved_bytes(n), device=eng.device, dtype=torch.uint8)
-        ret = eng.render(poses, ray_idx, H, W, K, remap=remap, rng=rng, seed=seed, offset=offset, saved=saved)
+        ret = eng.render(poses, ray_idx, H, W, K, remap=remap, rng=rng, seed=seed, offset=offset, saved=saved, ray_base=ray_base)
         keys = [k for k in _OUT_KEYS if k in ret]
         ctx.call, ctx.keys, ctx.saved_buf, ctx.poses = call, keys, saved, poses
         ctx.params = params
@@ -42,7 +42,7 @@ class _RenderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *gouts):
-        eng, ray_idx, H, W, K, remap, rng, seed, offset, n_fine = ctx.call
+        eng, ray_idx, H, W, K, remap, rng, seed, offset, n_fine, ray_base = ctx.call
         g = {k: (go.contiguous() if go is not None else None) for k, go in zip(ctx.keys, gouts)}
         # bnrf_render_backward ACCUMULATES into the gradient tables.  When every parameter already owns a gradient buffer
         # (benerf_b200.parallel.FlatGrads: p.grad are views of one flat fp32 buffer) the kernels add straight into p.grad
@@ -201,11 +201,12 @@ class Graph(nn.Module):
 
     # ------------------------------------------------------------------------------------
     def render(self, iter_step, poses, ray_idx, H, W, K, args, enable_crf: bool, sensor_type: str, remap,
-               near=0., far=1., training=False, rng=None):
+               near=0., far=1., training=False, rng=None, ray_base=0):
         """model/nerf.py:236-343.  Returns {'rgb_map','disp_map','acc_map'} (+ 'rgb0','disp0','acc0','sigma'
         when N_importance > 0), pose-major.  training/eval produce identical rays upstream and
         share one path here.  enable_crf / sensor_type are accepted and ignored exactly as upstream
-        (model/nerf.py:127-131).  rng (keyword-only extension): dict of the four draws for parity runs."""
+        (model/nerf.py:127-131).  Extensions (keyword-only): rng = dict of the four draws for parity runs; ray_base = index of this
+        render's first ray in a larger batch (its Philox draws then equal those of Engine.render_multi for the same rows)."""
         eng = self.engine(args)
         if (near, far) != (0., 1.):
             raise ValueError("Graph.render is only ever called with near=0, far=1 upstream (model/nerf.py:239)")
@@ -220,10 +221,11 @@ class Graph(nn.Module):
         nets = [self.nerf] + ([self.nerf_fine] if hasattr(self, "nerf_fine") else [])
         params = self._render_params(nets)
         if torch.is_grad_enabled() and (poses.requires_grad or any(p.requires_grad for p in params)):
-            call = (eng, ray_idx, H, W, K_np, remap_t, rng, self.seed(), self._render_calls, len(nets) > 1)
+            call = (eng, ray_idx, H, W, K_np, remap_t, rng, self.seed(), self._render_calls, len(nets) > 1, int(ray_base))
             outs = _RenderFn.apply(call, poses, *params)
             return dict(zip([k for k in _OUT_KEYS if len(nets) > 1 or k in ("rgb_map", "disp_map", "acc_map")], outs))
-        return eng.render(poses.detach(), ray_idx, H, W, K_np, remap=remap_t, rng=rng, seed=self.seed(), offset=self._render_calls)
+        return eng.render(poses.detach(), ray_idx, H, W, K_np, remap=remap_t, rng=rng, seed=self.seed(), offset=self._render_calls,
+                          ray_base=ray_base)
 
     @torch.no_grad()
     def render_video(self, iter_step, poses, H, W, K, args, remap, type):

@@ -142,25 +142,23 @@ class Trainer:
         poses_evt = eng.spline_poses(knots, None, t["ts_evt"], a.traj)
         poses_rgb = eng.spline_poses(knots, transform, t["ts_rgb"], a.traj)
         fine = len(self.nets) > 1
-        rets, saved = {}, {}
-        for i, (tag, poses, idx, hh, ww, kk) in enumerate((("evt", poses_evt, t["idx_evt"], H_ev, W_ev, K_event),
-                                                          ("rgb", poses_rgb, t["idx_rgb"], H, W, K))):
-            n = poses.shape[0] * idx.numel()
-            saved[tag] = self._buffer("saved_" + tag, eng.saved_bytes(n))
-            rets[tag] = eng.render(poses, idx, hh, ww, kk, remap=t["remap_" + tag], seed=seed, offset=i + 1, saved=saved[tag],
-                                   offset_dev=self.step_dev, want_sigma=False)
+        # the event pose pair and the N blur poses (model/nerf.py:217,227) as two segments of ONE ray batch: every stage of the
+        # render and of its backward pass runs once over all 2 R_e + P R_b rays
+        segs = [(poses_evt, t["idx_evt"], H_ev, W_ev, K_event, t["remap_evt"]), (poses_rgb, t["idx_rgb"], H, W, K, t["remap_rgb"])]
+        n_evt = poses_evt.shape[0] * t["idx_evt"].numel()
+        n = n_evt + poses_rgb.shape[0] * t["idx_rgb"].numel()
+        saved = self._buffer("saved", eng.saved_bytes(n))
+        ret = eng.render_multi(segs, seed=seed, offset=1, saved=saved, offset_dev=self.step_dev)
         mark("forward")
         coarse_key = "rgb0" if fine else "rgb_map"
-        loss_out, (d_ef, d_ec, d_bf, d_bc) = training_loss_fused(
-            loss_cfg(a), rets["evt"]["rgb_map"], rets["evt"][coarse_key], t["events_accu"], t["idx_evt"], rets["rgb"]["rgb_map"],
-            rets["rgb"][coarse_key], t["blur_target"], all_reduce=IF._rank_sum())
+        loss_out, (d_fine, d_coarse) = training_loss_fused(
+            loss_cfg(a), ret["rgb_map"][:n_evt], ret[coarse_key][:n_evt], t["events_accu"], t["idx_evt"], ret["rgb_map"][n_evt:],
+            ret[coarse_key][n_evt:], t["blur_target"], all_reduce=IF._rank_sum(), out_like=(ret["rgb_map"], ret[coarse_key]), split=n_evt)
         mark("loss")
         d_poses = torch.zeros(poses_evt.shape[0] + poses_rgb.shape[0], 3, 4, device=eng.device)
         d_pe, d_pr = d_poses[:poses_evt.shape[0]], d_poses[poses_evt.shape[0]:]
         gc, gf = grad_tabs[0], grad_tabs[1] if fine else None
-        eng.render_backward(poses_rgb, t["idx_rgb"], H, W, K, saved["rgb"], d_bf, d_bc if fine else None, gc, gf, d_pr, remap=t["remap_rgb"])
-        eng.render_backward(poses_evt, t["idx_evt"], H_ev, W_ev, K_event, saved["evt"], d_ef, d_ec if fine else None, gc, gf, d_pe,
-                            remap=t["remap_evt"])
+        eng.render_backward_multi(segs, saved, d_fine, d_coarse if fine else None, gc, gf, [d_pe, d_pr])
         gk, gt = g.evt_knot_pose_se3.params.weight.grad, g.transform.params.weight.grad.reshape(6)
         eng.spline_poses_backward(knots, transform, t["ts_rgb"], d_pr, a.traj, d_knots=gk, d_transform=gt)
         eng.spline_poses_backward(knots, None, t["ts_evt"], d_pe, a.traj, d_knots=gk)
@@ -218,10 +216,14 @@ class Trainer:
         mark(None)
         poses_evt = g.get_pose_evt(a, ts_evt)
         poses_rgb = g.get_pose_rgb(a, ts_rgb)
-        g._render_calls = 64 * self.global_step          # same Philox stream offsets as the direct step: 64 * global_step + call index
+        # same Philox draws as the direct step, which renders both pose sets as one batch: stream offset 64 * global_step + 1, the
+        # blur rays keyed behind the event rays
+        g._render_calls = 64 * self.global_step
         ret_evt = g.render(self.global_step, poses_evt, idx_evt, H_ev or H, W_ev or W, K_event, a, enable_crf=True, sensor_type="event",
                            remap=remap_evt, training=True)
-        ret_rgb = g.render(self.global_step, poses_rgb, idx_rgb, H, W, K, a, enable_crf=True, sensor_type="rgb", remap=remap_rgb, training=True)
+        g._render_calls = 64 * self.global_step
+        ret_rgb = g.render(self.global_step, poses_rgb, idx_rgb, H, W, K, a, enable_crf=True, sensor_type="rgb", remap=remap_rgb, training=True,
+                           ray_base=ret_evt["rgb_map"].shape[0])
         mark("forward")
         if getattr(a, "optimize_event_crf", False):                      # train.py:176-185
             ret_evt = {k: g.event_crf.forward(ret_evt[k]) for k in ("rgb_map", "rgb0")}

@@ -95,6 +95,8 @@ typedef struct {
      * depths lets the fine network be compared on identical samples.  NULL in production. */
     const float* z_fine;
     uint64_t seed, offset;
+    uint64_t ray_base;          /* added to the ray index that keys a draw: a render whose rays are rows [ray_base, ...) of a larger
+                                 * batch draws what bnrf_render_forward_multi draws for those rows */
     const uint64_t* offset_dev; /* NULL, or a device counter: the effective stream offset is offset + 64 * (*offset_dev).  A training
                                  * loop captured in a CUDA graph keeps its iteration count there (bnrf_step_advance), so that
                                  * replays draw fresh numbers although the launch arguments are frozen */
@@ -155,6 +157,22 @@ int bnrf_render_forward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_id
                         int H, int W, const float* K, const float* remap, const bnrf_rng* rng,
                         const bnrf_outputs* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* One Graph.render call as an argument block: several of them can be rendered as ONE ray batch (the rays of segment 0 first,
+ * each segment pose-major).  A training iteration renders the event pose pair and the N blur poses (model/nerf.py:217,227);
+ * as two segments of one batch every stage runs once over all their rays (half the launches, one partial tile instead of two). */
+typedef struct {
+    const float* poses;      /* device [P,3,4] */
+    const int64_t* ray_idx;  /* device [R] flat pixel indices */
+    int32_t P, R, H, W;
+    float K[9];              /* host, row-major intrinsics */
+    const float* remap;      /* device [H,W,2] or NULL */
+} bnrf_render_seg;
+
+/* bnrf_render_forward / bnrf_render_forward_train (saved != NULL) over the concatenated rays of n_segs <= 4 segments;
+ * outputs, workspace and saved are sized for N = sum P_i R_i rays. */
+int bnrf_render_forward_multi(bnrf_ctx* ctx, const bnrf_render_seg* segs, int n_segs, const bnrf_rng* rng, const bnrf_outputs* out,
+                              void* workspace, size_t workspace_bytes, void* saved, size_t saved_bytes, void* stream);
+
 /* -------------------------------------------------------------------------------------- */
 /* a16: training -- the part of loss.backward() (train.py:340) that runs through Graph.render */
 
@@ -186,6 +204,12 @@ int bnrf_render_backward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_i
                          const void* saved, size_t saved_bytes, const bnrf_param_grads* grads_coarse,
                          const bnrf_param_grads* grads_fine, float* d_poses, void* workspace,
                          size_t workspace_bytes, void* stream);
+/* bnrf_render_backward for a batch rendered by bnrf_render_forward_multi: d_rgb_map / d_rgb0 device [N,C] over the concatenated
+ * rays; d_poses[i]: device [P_i,3,4] of segment i (added into). */
+int bnrf_render_backward_multi(bnrf_ctx* ctx, const bnrf_render_seg* segs, int n_segs, const float* d_rgb_map, const float* d_rgb0,
+                               const void* saved, size_t saved_bytes, const bnrf_param_grads* grads_coarse,
+                               const bnrf_param_grads* grads_fine, float* const* d_poses, void* workspace, size_t workspace_bytes,
+                               void* stream);
 /* Backward of bnrf_spline_poses: adds d L / d knots (device [4,6]) and, when transform != NULL,
  * d L / d transform (device [6]) given d L / d poses (device [P,3,4]).  spline.py:247-331 under autograd. */
 int bnrf_spline_poses_backward(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts,
