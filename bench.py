@@ -134,6 +134,69 @@ def run_cpu_oracle(n_pixels, repeats=1):
     return rays / (best / repeats), rays, best / repeats
 
 
+def staged_reference():
+    """The unmodified reference staged by build() under baseline/_ref (tools/stage_reference.py), or None."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        from stage_reference import import_staged
+        return import_staged()
+    except Exception as e:                       # a missing third-party import on this box: fall back to the port, say why
+        print(f"staged reference not importable ({type(e).__name__}: {e}); using the oracle port", file=sys.stderr)
+        return None
+    finally:
+        sys.path.pop(0)
+
+
+_REF_STATE = {}
+
+
+def run_cpu_reference(ref, n_pixels, repeats=1):
+    """`repeats` steps of the workload through the REFERENCE's own code on the host CPU: model/optimize.py Model/Graph, get_pose_evt /
+    get_pose_rgb (spline.py), Graph.render x2 (model/nerf.py:236-343: rays, embedder, NeRF.forward coarse + sample_pdf + fine,
+    raw2output), then the blur mean (train.py:307-318) and the event log-difference with the reference's RGB2Gray /
+    rgb2brightlog.  Forward only, under no_grad, all host threads.  Returns (rays/s, rays per step, mean seconds per step)."""
+    if "graph" not in _REF_STATE:
+        torch.manual_seed(0)
+        args = ref_args()
+        args.max_iter, args.barf_c2f_start, args.barf_c2f_end = 80000, 0.1, 0.5
+        graph = ref.optimize.Model(args).build_network(args)
+        ref.helpers.init_nerf(graph.nerf)
+        ref.helpers.init_nerf(graph.nerf_fine)
+        _REF_STATE.update(graph=graph, args=args, gray=ref.img_utils.RGB2Gray())
+    graph, args, rgb2gray = _REF_STATE["graph"], _REF_STATE["args"], _REF_STATE["gray"]
+    g = torch.Generator().manual_seed(0)
+    idx_evt = torch.randint(0, H * W, (n_pixels,), generator=g)
+    idx_rgb = torch.randint(0, H * W, (n_pixels,), generator=g)
+    K = torch.tensor(K_MAT, dtype=torch.float32)
+    total = 0.0
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            p_evt = graph.get_pose_evt(args, torch.tensor(WINDOW, dtype=torch.float32))
+            p_rgb = graph.get_pose_rgb(args, torch.tensor(EXPOSURE, dtype=torch.float32))
+            r_evt = graph.render(0, p_evt, idx_evt, H, W, K, args, enable_crf=True, sensor_type="event", remap=None, training=True)
+            r_rgb = graph.render(0, p_rgb, idx_rgb, H, W, K, args, enable_crf=True, sensor_type="rgb", remap=None, training=True)
+            for lvl in ("rgb_map", "rgb0"):
+                blur = 0
+                for j in range(N_POSES):
+                    blur = blur + r_rgb[lvl][j * n_pixels:(j + 1) * n_pixels]
+                blur = blur / N_POSES
+                b1 = ref.math_utils.rgb2brightlog(rgb2gray(r_evt[lvl][:n_pixels]), args.dataset)
+                b2 = ref.math_utils.rgb2brightlog(rgb2gray(r_evt[lvl][n_pixels:]), args.dataset)
+                _ = b2 - b1
+            total += time.perf_counter() - t0
+    rays = (N_POSES + 2) * n_pixels
+    return rays / (total / repeats), rays, total / repeats
+
+
+def run_cpu_arm(n_pixels, repeats=1):
+    """The CPU arm of the bench: the staged reference when present (kind "reference"), else the oracle port (kind "port")."""
+    ref = staged_reference()
+    if ref is not None:
+        return run_cpu_reference(ref, n_pixels, repeats) + ("reference", "unmodified reference (baseline/_ref: model/nerf.py Graph.render, spline.py, run_nerf_helpers.py), torch CPU fp32")
+    return run_cpu_oracle(n_pixels, repeats) + ("port", "oracle/ (torch CPU fp32 restatement, pinned to the reference's outputs)")
+
+
 def run_cpu_oracle_train(n_evt, n_rgb):
     """Forward + backward of one training iteration (configs[2] shape, scaled down) on the host CPU with the oracle under
     torch autograd -- what train.py:160-340 costs per ray on the reference's CPU path.  Returns (rays/s, rays, seconds)."""
@@ -168,21 +231,22 @@ def bench_reference(opts):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     n_pixels = opts.cpu_pixels
-    run_cpu_oracle(max(8, n_pixels // 4))          # one untimed warm-up pass (thread pools, allocator)
+    for _ in range(max(1, min(opts.warmup, 2))):   # untimed warm-up passes (thread pools, allocator)
+        run_cpu_arm(max(8, n_pixels // 4))
     t = []
-    rays = 0
+    rays, kind, what = 0, "port", ""
     for _ in range(opts.steps):
-        rps, rays, dt = run_cpu_oracle(n_pixels)
+        rps, rays, dt, kind, what = run_cpu_arm(n_pixels)
         t.append(dt)
     ms = 1e3 * sum(t) / len(t)
     value = rays / (ms / 1e3)
-    sample = f"{n_pixels} pixels x ({N_POSES}+2) poses = {rays} rays per step, fp32 torch CPU"
+    sample = f"{n_pixels} pixels x ({N_POSES}+2) poses = {rays} rays per step (the GPU arm renders 65,536 pixels per step: same poses, samples and networks, bounded pixel count), {what}"
     print(json.dumps({
         "impl": "reference", "metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": opts.gpus, "steps": opts.steps,
         "warmup": opts.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(n_pixels, opts.gpus, note="bounded CPU sample of the same workload"),
-        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -460,12 +524,12 @@ def bench_ours(opts):
     cpu = None
     if rank == 0 and world == 1 and not opts.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        run_cpu_oracle(16)
+        run_cpu_arm(16)
         reps = 10
-        rps, rays, dt = run_cpu_oracle(opts.cpu_pixels, repeats=reps)
-        cpu = {"value": rps, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+        rps, rays, dt, kind, what = run_cpu_arm(opts.cpu_pixels, repeats=reps)
+        cpu = {"value": rps, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": kind,
                "sample": f"{reps} steps of {opts.cpu_pixels} pixels x 21 poses = {rays} rays, {dt:.2f} s per step ({reps * dt:.0f} s of CPU "
-                         "work), oracle/ (torch CPU fp32)"}
+                         f"work), {what}"}
     if cpu is not None and train is not None:
         run_cpu_oracle_train(8, 1)
         runs = [run_cpu_oracle_train(256, 27) for _ in range(5)]          # 1/4 of the configs[2] batch: 512 + 513 rays

@@ -88,6 +88,8 @@ PROTOTYPES = {
     "bnrf_training_loss_workspace_bytes": (_Z, [_L]),
     "bnrf_training_loss": (_I, [C.POINTER(LossCfg), _P, _P, _P, _P, _L, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P]),
     "bnrf_training_loss_finish": (_I, [C.POINTER(LossCfg), _P, _P, _P, _P, _L, _L, _P, _P, _P, _P, _P]),
+    "bnrf_crf_forward": (_I, [_I, _I, C.POINTER(_P), C.POINTER(_P), _P, _L, _P, _P]),
+    "bnrf_crf_backward": (_I, [_I, _I, C.POINTER(_P), C.POINTER(_P), _P, _P, _L, _P, C.POINTER(_P), C.POINTER(_P), _P]),
     "bnrf_adam_step": (_I, [_P, _P, _P, _P, _L, C.POINTER(AdamGroup), _I, _L, C.c_float, C.c_float, C.c_float, C.c_float, _I, _P]),
     "bnrf_adam_step_sched": (_I, [_P, _P, _P, _P, _L, C.POINTER(AdamSchedGroup), _I, _P, C.c_double, C.c_float, C.c_float, C.c_float, C.c_float, _I, _P]),
     "bnrf_step_advance": (_I, [_P, _P]),

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libbenerf_b200.so")
 SOURCES = ["api.cu", "pose.cu", "rays.cu", "composite.cu", "image_formation.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc2.cu", "mlp_tc3.cu",
-           "sgemm.cu", "gemm_tc.cu", "bwd_tiles.cu", "wgrad_pair.cu", "dgrad_chain.cu", "dgrad_chain2.cu", "backward.cu", "optim.cu", "probe_ts.cu", "loss.cu"]
+           "sgemm.cu", "gemm_tc.cu", "bwd_tiles.cu", "wgrad_pair.cu", "dgrad_chain.cu", "dgrad_chain2.cu", "backward.cu", "optim.cu", "probe_ts.cu", "loss.cu", "crf.cu"]
 NO_FMAD = {"pose.cu", "rays.cu"}
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

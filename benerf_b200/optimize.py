@@ -36,6 +36,8 @@ class Model(nerf.Model):
         parm_evt = torch.cat([torch.rand(1, 6) * 0.01 for _ in range(4)])
         g.evt_knot_pose_se3.params.weight.data = torch.nn.Parameter(parm_evt)
         g.transform.params.weight.data = torch.nn.Parameter(torch.zeros(1, 6))
+        g.rgb_crf.weights_biases_init()
+        g.event_crf.weights_biases_init()
         if torch.cuda.is_available():
             g.to("cuda")        # the reference runs with default tensor type cuda (train.py:472)
         return g

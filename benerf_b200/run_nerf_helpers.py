@@ -51,6 +51,8 @@ def render_video_test(iter_step, graph, render_poses, H, W, K, args, remap):
     rgbs, disps = [], []
     for pose in render_poses:
         ret = graph.render_video(iter_step, pose[None, :3, :4], H, W, K, args, remap, type="rgb")
+        if getattr(args, "optimize_rgb_crf", False):                     # run_nerf_helpers.py:125-126
+            ret["rgb_map"] = graph.rgb_crf.forward(ret["rgb_map"])
         rgbs.append(ret["rgb_map"].cpu().numpy())
         disps.append(ret["disp_map"].cpu().numpy())
     return np.stack(rgbs, 0), np.stack(disps, 0)
@@ -66,6 +68,8 @@ def render_image_test(iter_step, graph, render_poses, H, W, K, args, logdir, rem
     imgs, depth = [], []
     for j, pose in enumerate(render_poses):
         ret = graph.render_video(iter_step, pose[None, :3, :4], H, W, K, args, remap, type="rgb")
+        if getattr(args, "optimize_rgb_crf", False):                     # run_nerf_helpers.py:152-153
+            ret["rgb_map"] = graph.rgb_crf.forward(ret["rgb_map"])
         rgb8 = to8bit(ret["rgb_map"].cpu().numpy())
         _write_png(os.path.join(img_dir, dir[11:] + "{:03d}.png".format(j)), rgb8.squeeze())
         imgs.append(rgb8)

@@ -291,6 +291,20 @@ int bnrf_training_loss_finish(const bnrf_loss_cfg* cfg, const float* evt_fine, c
                               float* d_evt_coarse, double* loss_out, void* stream);
 
 /* -------------------------------------------------------------------------------------- */
+/* f4: camera-response tone mappers -- model/component.py:38-149 (ColorToneMapper / LuminanceToneMapper, input_type "Gray"),
+ * applied to the rendered tensors when args.optimize_rgb_crf / optimize_event_crf is set (train.py:176-192,
+ * run_nerf_helpers.py:125-126,152-153) */
+
+/* y[e] = sigmoid(L_{hidden+1}(relu(L_hidden(... relu(L_0(x[e])))))): L_0 = Linear(1, width), `hidden` x Linear(width, width),
+ * L_{hidden+1} = Linear(width, 1).  weights / biases: hidden + 2 device pointers in layer order, PyTorch (out, in) layout
+ * (the nn.Sequential's Linear modules).  width <= 256, hidden <= 4 (and hidden * width^2 floats must fit shared memory). */
+int bnrf_crf_forward(int width, int hidden, const float* const* weights, const float* const* biases, const float* x, int64_t n,
+                     float* y, void* stream);
+/* g = d loss / d y -> dx (written) and the parameter gradients (ADDED into d_weights / d_biases, same shapes as the parameters). */
+int bnrf_crf_backward(int width, int hidden, const float* const* weights, const float* const* biases, const float* x, const float* g,
+                      int64_t n, float* dx, float* const* d_weights, float* const* d_biases, void* stream);
+
+/* -------------------------------------------------------------------------------------- */
 /* f3: fused optimiser tail -- train.py:343-394 (optimizer.step() x3, learning-rate decay, zero_grad),
  * model/optimize.py:36-55 (torch.optim.Adam, default betas / eps, no weight decay) */
 

@@ -180,3 +180,32 @@ def test_fused_adam_matches_torch_adam():
         assert float(gbuf.abs().max()) == 0.0
         want = torch.cat([p.detach() for p in ref])
         assert float((flat - want).abs().max()) <= 2e-7 * float(want.abs().max()) + 1e-9, step
+
+
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_tone_mappers_match_reference_vectors(i):
+    """bnrf_crf_forward / bnrf_crf_backward through benerf_b200.component (same module tree and state-dict keys as
+    model/component.py) against the reference's outputs and autograd gradients: Color / Luminance, hidden 0 and 2."""
+    from benerf_b200 import component
+    f = load_golden("functions")
+    cls, hidden, width = ((component.ColorToneMapper, 0, 128), (component.LuminanceToneMapper, 0, 128), (component.ColorToneMapper, 2, 32))[i]
+    m = cls(hidden=hidden, width=width, input_type="Gray").to(DEV)
+    seq = m.mlp_gray if hasattr(m, "mlp_gray") else m.mlp_luminance
+    assert [k for k, _ in seq.named_parameters()] == [f"{2 * l}.{s}" for l in range(hidden + 2) for s in ("weight", "bias")]
+    with torch.no_grad():
+        for j, p in enumerate(seq.parameters()):
+            p.copy_(f[f"crf{i}_p{j}"])
+    x = f[f"crf{i}_x"].to(DEV).requires_grad_(True)
+    y = m.forward(x)
+    assert max_abs(y, f[f"crf{i}_y"]) < 1e-6
+    y.backward(f[f"crf{i}_gy"].to(DEV))
+
+    def rel(a, b):
+        return float((a.cpu().double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    assert rel(x.grad, f[f"crf{i}_dx"]) < 1e-5
+    for j, p in enumerate(seq.parameters()):
+        assert rel(p.grad, f[f"crf{i}_dp{j}"]) < 1e-5, j
+    with pytest.raises(NotImplementedError):
+        cls(input_type="RGB")
+    with pytest.raises(ValueError):
+        m.forward(torch.rand(4, 3, device=DEV))

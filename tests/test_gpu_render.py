@@ -118,8 +118,9 @@ def test_render_free_running_matches_reference(name, mode):
     case, gold, inp, rets, report = _run_case(name, mode, inject_z_fine=False)
     print("free-running", name, mode, _fmt(report))
     _check(report)
+    # measured (profiles/r02_parity_report.json): 2..18 flagged rays of 16..114 (<= 19 %); the bound is that + margin
     for tag in ("evt", "rgb"):
-        assert report[f"{tag}_flagged"] <= 0.4 * report[f"{tag}_rays"]
+        assert report[f"{tag}_flagged"] <= 0.25 * report[f"{tag}_rays"], report
 
 
 DARK = 0.1            # brightness below which d log(x)/dx > 10: the event tensor is > 10x as sensitive as the render itself
@@ -366,6 +367,66 @@ def test_full_bench_size_properties():
     blur = blur_mean(full["rgb_map"], P)
     want = full["rgb_map"].reshape(P, R, 3).double().mean(0)
     assert float((blur.double() - want).abs().max()) < 1e-6
+
+
+def test_bench_batch_sample_matches_oracle():
+    """Parity AT the size bench.py times (BASELINE.json configs[1] throughput shape: 65,536 pixels x 19 poses = 1,245,184 rays per
+    blur render): the four draws are injected for the whole batch, 216 of its pixels (4,104 rays, every pose) are re-rendered by
+    the CPU oracle on the very same draws, and the batch's rows for those rays must match --
+      coarse outputs (rgb0, acc0)         <= 1e-4 on every sampled ray off the last-sample kink
+      fine outputs, free-running          <= 1e-4 on the well-conditioned rays; rays whose inverse-CDF bins are ill-conditioned
+                                          (tests/test_oracle_conditioning.py) are counted and held to the gross-error bounds
+      fine outputs on the oracle's depths <= 1e-4 on EVERY sampled ray off the kink (the sample rendered alone with z_fine injected;
+                                          test_full_bench_size_properties ties rows of a sub-batch bit-exactly to the full batch)"""
+    from oracle import pose, resample
+    case = CASES["unreal_rgb"]
+    inp = make_inputs(case)
+    eng = make_engine(case, "tc")
+    eng.set_weights(0, to_dev(inp["coarse"])); eng.set_weights(1, to_dev(inp["fine"]))
+    R, P, n_s = 65536, 19, 216
+    g = torch.Generator(device=DEV).manual_seed(23)
+    idx = torch.randint(0, case.H * case.W, (R,), device=DEV, generator=g)
+    poses = pose.poses_from_knots(inp["knots"], inp["transform"], *case.exposure, P)
+    n = P * R
+    draws = {"t_rand": torch.rand(n, 64, device=DEV, generator=g), "noise_c": torch.randn(n, 64, device=DEV, generator=g),
+             "u": torch.rand(n, 64, device=DEV, generator=g), "noise_f": torch.randn(n, 128, device=DEV, generator=g)}
+    full = eng.render(poses.to(DEV).contiguous(), idx, case.H, case.W, case.K, rng=draws, want_z=True)
+    pick = torch.randperm(R, device=DEV, generator=g)[:n_s]
+    rows = (torch.arange(P, device=DEV)[:, None] * R + pick[None, :]).reshape(-1)          # pose-major rows of the sampled pixels
+    sub_draws = {k: v[rows].cpu() for k, v in draws.items()}
+    got = {k: v[rows].cpu() for k, v in full.items()}
+    with torch.no_grad():
+        want = orender.render(inp["coarse"], inp["fine"], poses, idx[pick].cpu(), case.H, case.W, case.K, sub_draws, return_intermediates=True)
+    ex = want["_extra"]
+    m = P * n_s
+    kink = orender.unstable_last_sample(ex["raw_coarse"], sub_draws["noise_c"], eps=1e-3) | \
+        orender.unstable_last_sample(ex["raw_fine"], sub_draws["noise_f"], eps=1e-3)
+    mass, _ = resample.conditioning(ex["z_coarse"], ex["weights_coarse"], sub_draws["u"])
+    flagged = (mass.min(-1)[0] < 2e-3) & ~kink
+    ok = ~kink & ~flagged
+
+    def err(k, sel):
+        e = (got[k] - want[k]).abs().reshape(m, -1).amax(-1)
+        return float(e[sel].max()) if sel.any() else 0.0
+    rep = {"rays": m, "kink": int(kink.sum()), "flagged": int(flagged.sum()), "rgb0": err("rgb0", ~kink), "acc0": err("acc0", ~kink),
+           "rgb_map": err("rgb_map", ok), "acc_map": err("acc_map", ok), "rgb_map_flagged": err("rgb_map", flagged),
+           "z_max_diff": float((got["z_vals"] - ex["z_fine"]).abs().max())}
+    # the sample alone, fine pass on the oracle's depths: every ray
+    d = to_dev(sub_draws)
+    d["z_fine"] = ex["z_fine"].to(DEV)
+    alone = eng.render(poses.to(DEV).contiguous(), idx[pick].contiguous(), case.H, case.W, case.K, rng=d)
+    for k in ("rgb_map", "acc_map", "sigma"):
+        e = (alone[k].cpu() - want[k]).abs().reshape(m, -1).amax(-1)
+        rep[k + "_identical_samples"] = float(e[~kink].max())
+    print("bench-batch sample", _fmt(rep))
+    assert rep["kink"] <= m // 50 and rep["flagged"] <= m // 4
+    for k in ("rgb0", "acc0", "rgb_map", "acc_map", "rgb_map_identical_samples", "acc_map_identical_samples", "sigma_identical_samples"):
+        assert rep[k] < TOL, (k, rep)
+    assert rep["rgb_map_flagged"] < LOOSE["rgb_map"], rep
+    import json, os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "parity_bench_batch_sample.json"), "w") as f:
+        json.dump(rep, f, indent=1)
 
 
 def test_image_formation_full_frame_properties():

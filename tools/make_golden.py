@@ -286,6 +286,25 @@ def run_functions(ref):
     ron, rdn = ref.helpers.ndc_rays(Hr, Wr, Kr[0][0], 1.0, ro, rd)
     out["remap_lut"], out["remap_idx"], out["remap_poses"] = remap, idx, poses2
     out["remap_rays_o"], out["remap_rays_d"], out["remap_rays_o_ndc"], out["remap_rays_d_ndc"] = ro, rd, ron, rdn
+    # f4: the tone mappers (model/component.py:38-149), forward and gradients; parameters perturbed away from the init so that
+    # every layer carries signal.  crf{i}: (class, hidden, width)
+    from model import component
+    for i, (cls, hidden, width) in enumerate(((component.ColorToneMapper, 0, 128), (component.LuminanceToneMapper, 0, 128),
+                                              (component.ColorToneMapper, 2, 32))):
+        torch.manual_seed(100 + i)
+        m = cls(hidden=hidden, width=width, input_type="Gray")
+        m.weights_biases_init()
+        seq = m.mlp_gray if hasattr(m, "mlp_gray") else m.mlp_luminance
+        with torch.no_grad():
+            for p in seq.parameters():
+                p.add_(torch.from_numpy((rng.standard_normal(tuple(p.shape)) * 0.3).astype(np.float32)))
+        x = torch.from_numpy(rng.random((96, 1)).astype(np.float32)).requires_grad_(True)
+        gy = torch.from_numpy(rng.standard_normal((96, 1)).astype(np.float32))
+        y = m.forward(x)
+        y.backward(gy)
+        out[f"crf{i}_x"], out[f"crf{i}_y"], out[f"crf{i}_gy"], out[f"crf{i}_dx"] = x.detach(), y.detach(), gy, x.grad
+        for j, p in enumerate(seq.parameters()):
+            out[f"crf{i}_p{j}"], out[f"crf{i}_dp{j}"] = p.detach().clone(), p.grad.clone()
     return {k: v.detach().cpu().numpy() for k, v in out.items()}
 
 
