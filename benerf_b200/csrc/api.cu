@@ -20,7 +20,7 @@ int fail(bnrf_ctx* ctx, int code, const char* fmt, ...) {
 // One launch repacks every tensor of a network (bnrf_set_weights runs after every optimiser step): a table of segments,
 // blockIdx.y = segment.  Transposes (in_f > 0): dst[(k_dst + k) * N + n] = src[n * in_f + k_src + k] for k < k_count,
 // n < out_f (PyTorch (out,in) -> k-major); plain copies (in_f == 0): dst[i] = src[i] for i < k_count.
-struct PackSeg { const float* src; float* dst; int out_f, in_f, k_src, k_dst, k_count, N; };
+struct PackSeg { const float* src; float* dst; int out_f, in_f, k_src, k_dst, k_count, N; const float* kscale; /* [k_count] per input channel, or NULL */ };
 struct PackTable { PackSeg seg[28]; int n; };
 __global__ void pack_all_kernel(const __grid_constant__ PackTable t) {
     const PackSeg& s = t.seg[blockIdx.y];
@@ -28,7 +28,8 @@ __global__ void pack_all_kernel(const __grid_constant__ PackTable t) {
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         if (s.in_f) {
             const int k = idx / s.out_f, n = idx % s.out_f;
-            s.dst[(size_t)(s.k_dst + k) * s.N + n] = s.src[(size_t)n * s.in_f + s.k_src + k];
+            const float v = s.src[(size_t)n * s.in_f + s.k_src + k];
+            s.dst[(size_t)(s.k_dst + k) * s.N + n] = s.kscale ? v * s.kscale[k] : v;
         } else {
             s.dst[idx] = s.src[idx];
         }
@@ -101,15 +102,18 @@ int pack_weights(bnrf_ctx* ctx, int n, const float* const* w, const float* const
     NetParams& np = ctx->net[n];
     const int C = ctx->cfg.channels;
     PackTable t{};
-    auto tr = [&](const float* W, int out_f, int in_f, int k_src, int k_dst, int k_count, int N, float* dst) {
-        t.seg[t.n++] = PackSeg{W, dst, out_f, in_f, k_src, k_dst, k_count, N};
+    auto tr = [&](const float* W, int out_f, int in_f, int k_src, int k_dst, int k_count, int N, float* dst, const float* kscale = nullptr) {
+        t.seg[t.n++] = PackSeg{W, dst, out_f, in_f, k_src, k_dst, k_count, N, kscale};
     };
-    auto cp = [&](const float* src, int cnt, float* dst) { t.seg[t.n++] = PackSeg{src, dst, 0, 0, 0, 0, cnt, 0}; };
+    auto cp = [&](const float* src, int cnt, float* dst) { t.seg[t.n++] = PackSeg{src, dst, 0, 0, 0, 0, cnt, 0, nullptr}; };
+    // BARF c2f (bnrf_set_encoding_weights): the encoding channels' weights scale the weight-matrix columns that read them
+    const float* sp = ctx->enc_scaled ? ctx->enc_scale : nullptr;
+    const float* sd = ctx->enc_scaled ? ctx->enc_scale + 64 : nullptr;
     // GEMM step s <- reference linear: 0-7 pts_linears, 8 feature_linear, 9 views_linears.0 (feature block)
-    tr(w[BNRF_L_PTS0], kWidth, kPtsCh, 0, 0, kPtsCh, kWidth, np.wt[0]);
+    tr(w[BNRF_L_PTS0], kWidth, kPtsCh, 0, 0, kPtsCh, kWidth, np.wt[0], sp);
     for (int l = 1; l < 8; ++l) {
         if (l == 5) {   // cat([input_pts, h]) -> [pe64 | h256]  (model/nerf.py:98)
-            tr(w[l], kWidth, kPtsCh + kWidth, 0, 0, kPtsCh, kWidth, np.wt[5]);
+            tr(w[l], kWidth, kPtsCh + kWidth, 0, 0, kPtsCh, kWidth, np.wt[5], sp);
             tr(w[l], kWidth, kPtsCh + kWidth, kPtsCh, kPtsChPad, kWidth, kWidth, np.wt[5]);
         } else {
             tr(w[l], kWidth, kWidth, 0, 0, kWidth, kWidth, np.wt[l]);
@@ -117,7 +121,7 @@ int pack_weights(bnrf_ctx* ctx, int n, const float* const* w, const float* const
     }
     tr(w[BNRF_L_FEATURE], kWidth, kWidth, 0, 0, kWidth, kWidth, np.wt[8]);
     tr(w[BNRF_L_VIEWS], kHalf, kWidth + kDirCh, 0, 0, kWidth, kHalf, np.wt[9]);       // cat([feature, dirs]) (model/nerf.py:103)
-    tr(w[BNRF_L_VIEWS], kHalf, kWidth + kDirCh, kWidth, 0, kDirCh, kHalf, np.w_dir);
+    tr(w[BNRF_L_VIEWS], kHalf, kWidth + kDirCh, kWidth, 0, kDirCh, kHalf, np.w_dir, sd);
     for (int l = 0; l < 8; ++l) cp(b[l], kWidth, np.bias[l]);
     cp(b[BNRF_L_FEATURE], kWidth, np.bias[8]);
     cp(b[BNRF_L_VIEWS], kHalf, np.bias[9]);
@@ -208,7 +212,8 @@ int bnrf_create(bnrf_ctx** out, int device, const bnrf_cfg* cfg) {
     int rc;
     for (int n = 0; n < 2; ++n)
         if ((rc = alloc_net(ctx, n)) != BNRF_OK) return bail(rc);
-    if (cudaMalloc(&ctx->t_vals, kMaxSamples * sizeof(float)) != cudaSuccess ||
+    if (cudaMalloc(&ctx->enc_scale, 96 * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&ctx->t_vals, kMaxSamples * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&ctx->tile_counter, 64 * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&ctx->err_flag, sizeof(unsigned int)) != cudaSuccess)
         return bail(fail(ctx, BNRF_ERR_CUDA, "cudaMalloc failed"));
@@ -230,7 +235,7 @@ void bnrf_destroy(bnrf_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (int n = 0; n < 2; ++n) free_net(ctx, n);
-    cudaFree(ctx->t_vals); cudaFree(ctx->tile_counter); cudaFree(ctx->err_flag);
+    cudaFree(ctx->t_vals); cudaFree(ctx->tile_counter); cudaFree(ctx->err_flag); cudaFree(ctx->enc_scale);
     if (ctx->prof_ev[0]) for (int i = 0; i < 2 * 512; ++i) cudaEventDestroy(ctx->prof_ev[i]);
     delete ctx;
 }
@@ -270,6 +275,21 @@ int bnrf_set_sample_grid(bnrf_ctx* ctx, const float* t_vals_host, int S, void* s
     if (!ctx || !t_vals_host || S != ctx->cfg.n_samples) return fail(ctx, BNRF_ERR_ARG, "set_sample_grid: S must equal cfg.n_samples");
     BNRF_CUDA(ctx, cudaMemcpyAsync(ctx->t_vals, t_vals_host, S * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
     BNRF_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));   // the host buffer is borrowed only for the call
+    return BNRF_OK;
+}
+
+int bnrf_set_encoding_weights(bnrf_ctx* ctx, const float* w_pts, const float* w_dir, void* stream) {
+    if (!ctx || (w_pts == nullptr) != (w_dir == nullptr)) return fail(ctx, BNRF_ERR_ARG, "set_encoding_weights: pass both weight vectors or neither");
+    float host[96];
+    for (int i = 0; i < 96; ++i) host[i] = 1.0f;
+    if (w_pts) {
+        memcpy(host, w_pts, kPtsCh * sizeof(float));
+        memcpy(host + 64, w_dir, kDirCh * sizeof(float));
+    }
+    BNRF_CUDA(ctx, cudaMemcpyAsync(ctx->enc_scale, host, sizeof(host), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    BNRF_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));   // the host buffer is borrowed only for the call
+    ctx->enc_scaled = w_pts != nullptr;
+    for (int n = 0; n < 2; ++n) ctx->net[n].ready = false;         // the packed matrices no longer match: bnrf_set_weights must follow
     return BNRF_OK;
 }
 

@@ -280,7 +280,7 @@ __global__ void views_feature_wgrad_kernel(const float* __restrict__ G, const fl
 // ------------------------------------------------------------------ view-direction branch
 // per ray: encoding of the unit view direction (27 values, padded to 32), d enc = dvb * W_dir^T, d view
 __global__ void viewdir_backward_kernel(const float* __restrict__ view, const float* __restrict__ dvb,
-                                        const float* __restrict__ w_dir /*[27][128]*/, int64_t n_rays,
+                                        const float* __restrict__ w_dir /*[27][128]*/, const float* __restrict__ enc_scale /*[27] or NULL*/, int64_t n_rays,
                                         float* __restrict__ pe_dir /*[N,32]*/, float* __restrict__ d_view /*[N,3] +=*/) {
     const int lane = threadIdx.x % 32;
     const int64_t ray = (int64_t)blockIdx.x * kWarps + threadIdx.x / 32;
@@ -313,6 +313,7 @@ __global__ void viewdir_backward_kernel(const float* __restrict__ view, const fl
         float e = 0.f;
 #pragma unroll
         for (int i = 0; i < kDirCh; ++i) if (lane == i) e = enc[i];
+        if (enc_scale && lane < kDirCh) e *= enc_scale[lane];     // BARF c2f: the weight gradient sees the weighted encoding
         pe_dir[ray * 32 + lane] = e;            // lanes 27..31 write the zero padding
     }
     if (lane < 3) {
@@ -582,8 +583,9 @@ static int mlp_backward(bnrf_ctx* ctx, int net, int64_t n, int S, const ActPtrs&
         j.a_tiles = dz; j.b_tiles = h; j.NB = kWidth; j.dW = dWl; j.ldw = ldw; j.col0 = col0; j.n_valid = kWidth; j.dB = dBl;
     };
     // the bias of layer 5 rides on its wide block when that runs on the pair kernel (bias off the tensor core), else on the narrow one
-    job(DZ(0), kWidth, acts.pe_tiles, kPtsChPad, dW[0], kPtsCh, 0, kPtsCh, dB[0]);
-    job(DZ(5), kWidth, acts.pe_tiles, kPtsChPad, dW[5], kPtsCh + kWidth, 0, kPtsCh, pair ? nullptr : dB[5]);
+    // (BARF c2f: the saved encoding is unweighted; the weight-gradient columns of its channels take the channel weights)
+    job(DZ(0), kWidth, acts.pe_tiles, kPtsChPad, dW[0], kPtsCh, 0, kPtsCh, dB[0])->col_scale = ctx->enc_scaled ? ctx->enc_scale : nullptr;
+    job(DZ(5), kWidth, acts.pe_tiles, kPtsChPad, dW[5], kPtsCh + kWidth, 0, kPtsCh, pair ? nullptr : dB[5])->col_scale = ctx->enc_scaled ? ctx->enc_scale : nullptr;
     for (int l = 1; l < 8; ++l) {
         if (l == 5) wide(DZ(5), H(4), dW[5], kPtsCh + kWidth, kPtsCh, pair ? dB[5] : nullptr);
         else wide(DZ(l), H(l - 1), dW[l], kWidth, 0, dB[l]);
@@ -718,7 +720,8 @@ static int render_backward_impl(bnrf_ctx* ctx, const bnrf_render_seg* segs, int 
         BNRF_LAUNCH_CHECK(ctx);
         if ((rc = mlp_backward(ctx, net, n, S, acts, w.b, pg->weights, pg->biases, st))) return rc;
         // view-direction block of views_linears.0 and d viewdirs
-        viewdir_backward_kernel<<<grid, 32 * kWarps, 0, st>>>(s.view, w.b.dvb, ctx->net[net].w_dir, n, w.b.pe_dir, w.g_v);
+        viewdir_backward_kernel<<<grid, 32 * kWarps, 0, st>>>(s.view, w.b.dvb, ctx->net[net].w_dir, ctx->enc_scaled ? ctx->enc_scale + 64 : nullptr, n,
+                                                              w.b.pe_dir, w.g_v);
         BNRF_LAUNCH_CHECK(ctx);
         {   // direction block of views_linears.0 and its bias (pe_dir is written by viewdir_backward_kernel above)
             const int64_t rpb = 128;

@@ -365,6 +365,10 @@ __global__ void __launch_bounds__(wg::THREADS, 1) tile_wgrad_kernel(const __grid
             for (int c0 = 0; c0 < jb.N; c0 += 32) {
                 float v[32];
                 tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)mh * 256u + (uint32_t)c0, v);
+                if (jb.col_scale) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= (c0 + j < jb.n_valid) ? __ldg(jb.col_scale + c0 + j) : 0.0f;
+                }
                 if (vec && c0 + 32 <= jb.n_valid) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)

@@ -60,6 +60,7 @@ struct WgradJob {
     const unsigned char* h_tiles; int N;        // bf16 tile matrix, width N = 64 | 256
     float* dW; int ldw; int col0; int n_valid;
     float* dB;                                  // nullable
+    const float* col_scale;                     // nullable: the partial of column n is multiplied by col_scale[n] (BARF c2f weights)
     const float* wrow; int wrow_stride; float* dWv; float* dBv;   // nullable (alpha_linear rides on the feature job)
     int cta0, ctas;                             // CTAs [cta0, cta0 + ctas) split the tiles of this job
 };

@@ -74,6 +74,8 @@ struct bnrf_ctx {
     bnrf_cfg cfg;
     bnrf::NetParams net[2];
     float* t_vals;            // device [n_samples] sampling grid (linspace(0,1,S) by default)
+    float* enc_scale;         // device [64 + 32]: BARF c2f weights of the 63 point / 27 direction encoding channels (1 when off)
+    bool enc_scaled;          // bnrf_set_encoding_weights is in effect
     int* tile_counter;        // device scratch for the persistent tile scheduler
     unsigned int* err_flag;   // device: set by kernels on watchdog timeout
     unsigned long long* trace; // device [sm_count][16] stall counters of the last MLP launch, or NULL (bnrf_debug_mlp_trace)

@@ -95,6 +95,17 @@ class Engine:
         """Force a repack at the next render: for parameter updates torch cannot see (bnrf_adam_step writes in place)."""
         self._weights_version = [None, None]
 
+    def set_encoding_weights(self, w_pts=None, w_dir=None):
+        """BARF c2f channel weights (bnrf_set_encoding_weights): w_pts [63], w_dir [27] host sequences, or None / None to switch the
+        weighting off.  The packed weights depend on them: the next sync_weights / set_weights repacks."""
+        if w_pts is None:
+            self._check(self.lib.bnrf_set_encoding_weights(self._ctx, None, None, _stream()), "bnrf_set_encoding_weights")
+        else:
+            a = (C.c_float * 63)(*[float(v) for v in w_pts])
+            b = (C.c_float * 27)(*[float(v) for v in w_dir])
+            self._check(self.lib.bnrf_set_encoding_weights(self._ctx, a, b, _stream()), "bnrf_set_encoding_weights")
+        self.invalidate_weights()
+
     def set_sample_grid(self, t_vals):
         t = torch.as_tensor(t_vals, dtype=torch.float32).cpu().contiguous()
         arr = (C.c_float * t.numel())(*t.tolist())

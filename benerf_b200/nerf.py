@@ -20,6 +20,20 @@ from ._lib import LINEAR_NAMES
 _OUT_KEYS = ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0", "sigma")
 
 
+def barf_c2f_channel_weights(iter_step, args):
+    """model/nerf.py:16-26 as per-channel factors of the 63-channel point and 27-channel direction encodings fed to the network
+    (cat([x, barf_c2f_weight(PE(x))]), model/nerf.py:75-88): ((63 floats), (27 floats)).  Upstream multiplies the [M, 6L] encoding
+    viewed as (-1, L) by the L ramp values, so channel e of the sin/cos part takes weight[e % L], and the raw input 1."""
+    out = []
+    for L in (args.multires, args.multires_views):
+        progress = iter_step / args.max_iter
+        alpha = (progress - args.barf_c2f_start) / (args.barf_c2f_end - args.barf_c2f_start) * L
+        k = torch.arange(L)
+        weight = (1 - (alpha - k).clamp_(min=0, max=1).mul_(np.pi).cos_()) / 2          # same float32 ops as upstream
+        out.append(tuple([1.0, 1.0, 1.0] + [float(weight[e % L]) for e in range(6 * L)]))
+    return tuple(out)
+
+
 class _RenderFn(torch.autograd.Function):
     """Graph.render under autograd: forward = bnrf_render_forward_train, backward = bnrf_render_backward.
 
@@ -116,9 +130,8 @@ class Graph(nn.Module):
     # ------------------------------------------------------------------------------------
     def engine(self, args):
         if self._engine is None:
-            if not getattr(args, "ndc", True) or not args.use_viewdirs or getattr(args, "use_barf_c2f", False):
-                raise ValueError("benerf_b200 covers the configuration every shipped config uses: ndc=True, "
-                                 "use_viewdirs=True, use_barf_c2f=False")
+            if not getattr(args, "ndc", True) or not args.use_viewdirs:
+                raise ValueError("benerf_b200 covers the configuration every shipped config uses: ndc=True, use_viewdirs=True")
             self._engine = Engine(n_samples=args.N_samples, n_importance=args.N_importance, channels=args.channels,
                                   mlp_mode=getattr(args, "mlp_mode", "tc"), gemm_mode=getattr(args, "gemm_mode", "tc"))
         return self._engine
@@ -140,7 +153,19 @@ class Graph(nn.Module):
             self._param_cache = (len(nets), ps)
         return self._param_cache[1]
 
-    def _sync(self, eng):
+    def _sync_barf(self, eng, iter_step, args):
+        w = barf_c2f_channel_weights(iter_step, args)
+        if w != getattr(self, "_barf_weights", None):
+            eng.set_encoding_weights(*w)
+            self._barf_weights = w
+
+    def _sync(self, eng, iter_step=0, args=None):
+        # BARF coarse-to-fine (args.use_barf_c2f, model/nerf.py:16-26,75-88): the per-channel encoding weights of this iter_step
+        # are folded into the packed weight matrices, so a change of the weights forces a repack
+        w = barf_c2f_channel_weights(iter_step, args) if args is not None and getattr(args, "use_barf_c2f", False) else None
+        if w != getattr(self, "_barf_weights", None):
+            eng.set_encoding_weights(*(w if w is not None else (None, None)))
+            self._barf_weights = w
         eng.sync_weights(0, self.nerf)
         if hasattr(self, "nerf_fine"):
             eng.sync_weights(1, self.nerf_fine)
@@ -210,7 +235,7 @@ class Graph(nn.Module):
         eng = self.engine(args)
         if (near, far) != (0., 1.):
             raise ValueError("Graph.render is only ever called with near=0, far=1 upstream (model/nerf.py:239)")
-        self._sync(eng)
+        self._sync(eng, iter_step, args)
         dev = eng.device
         poses = poses[:, :3, :4].to(device=dev, dtype=torch.float32).contiguous()
         ray_idx = torch.as_tensor(ray_idx).reshape(-1).to(device=dev, dtype=torch.int64).contiguous()

@@ -38,7 +38,8 @@ class Trainer:
         self.params = params
         self.crf = bool(getattr(args, "optimize_rgb_crf", False) or getattr(args, "optimize_event_crf", False))
         self.fused = bool(getattr(args, "fused_optimizer", True))
-        self.use_graph = self.fused and not self.crf and bool(getattr(args, "cuda_graph", True))
+        # BARF c2f changes the packed weights with iter_step on the host: such runs step eagerly
+        self.use_graph = self.fused and not self.crf and bool(getattr(args, "cuda_graph", True)) and not getattr(args, "use_barf_c2f", False)
         if self.fused:
             # parameters, like their gradients, become views of ONE flat buffer (same order), so that the optimiser tail is a
             # single launch (bnrf_adam_step_sched); state_dict / load_state_dict / init_nerf keep working on the views
@@ -134,6 +135,8 @@ class Trainer:
         mark = self._mark
         mark(None)
         weights, grad_tabs = self._tables(eng)
+        if getattr(a, "use_barf_c2f", False):
+            g._sync_barf(eng, self.global_step, a)
         for net, params in enumerate(weights):                           # the parameters changed (bnrf_adam_step_sched wrote them in place)
             eng.set_weights(net, params)
         knots = g.evt_knot_pose_se3.params.weight.data

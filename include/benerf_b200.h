@@ -173,6 +173,13 @@ typedef struct {
 int bnrf_render_forward_multi(bnrf_ctx* ctx, const bnrf_render_seg* segs, int n_segs, const bnrf_rng* rng, const bnrf_outputs* out,
                               void* workspace, size_t workspace_bytes, void* saved, size_t saved_bytes, void* stream);
 
+/* BARF coarse-to-fine weighting (args.use_barf_c2f, model/nerf.py:16-26,75-88): the network input is cat([x, w (.) PE(x)]) with
+ * per-channel weights w that depend on iter_step.  w_pts: host [63] (the first 3 = 1: the raw point), w_dir: host [27]; both NULL
+ * switch the weighting off.  A linear layer sees w (.) e as columns of its weight matrix scaled by w, so the weights are folded
+ * into the packed matrices at the next bnrf_set_weights (which the caller must issue: the pack depends on them) and the forward
+ * kernels run unchanged; the backward pass scales the affected weight-gradient columns by the same w. */
+int bnrf_set_encoding_weights(bnrf_ctx* ctx, const float* w_pts, const float* w_dir, void* stream);
+
 /* -------------------------------------------------------------------------------------- */
 /* a16: training -- the part of loss.backward() (train.py:340) that runs through Graph.render */
 

@@ -11,7 +11,7 @@ import math
 import torch
 import torch.nn.functional as F
 
-from .encode import positional_encoding
+from .encode import positional_encoding, encode
 
 D, WIDTH, SKIP = 8, 256, 4
 PTS_FREQS, DIR_FREQS = 10, 4
@@ -45,7 +45,7 @@ def xavier_params(channels=3, generator=None, bias_scale=0.0):
     return params
 
 
-def mlp_forward(params, pts, viewdirs):
+def mlp_forward(params, pts, viewdirs, barf=None):
     """pts [N,S,3], viewdirs [N,3] -> raw [N,S,C+1] = cat(rgb, sigma); no output activation.
 
     model/nerf.py:67-116: encode points and (per-sample broadcast) view
@@ -55,9 +55,9 @@ def mlp_forward(params, pts, viewdirs):
     """
     lin = lambda name, x: F.linear(x, params[name + ".weight"], params[name + ".bias"])
     flat = pts.reshape(-1, 3)
-    enc_p = positional_encoding(flat, PTS_FREQS)
+    enc_p = encode(flat, PTS_FREQS, barf)                 # barf = (progress, start, end): model/nerf.py:75-88
     dirs = viewdirs[:, None].expand(pts.shape).reshape(-1, 3)
-    enc_d = positional_encoding(dirs, DIR_FREQS)
+    enc_d = encode(dirs, DIR_FREQS, barf)
     h = enc_p
     for i in range(D):
         h = F.relu(lin(f"pts_linears.{i}", h))

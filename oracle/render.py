@@ -26,7 +26,7 @@ def draw_rng(n_rays, n_samples, n_importance, generator=None):
 
 def render(params_coarse, params_fine, poses, ray_idx, H, W, K, rng, *,
            n_samples=64, n_importance=64, channels=3, remap=None, ndc=True,
-           near=0.0, far=1.0, return_intermediates=False):
+           near=0.0, far=1.0, return_intermediates=False, barf=None):
     """poses [P,3,4], ray_idx [R] -> dict like Graph.render (pose-major, N = P*R rays).
 
     Keys: rgb_map, disp_map, acc_map (+ rgb0, disp0, acc0, sigma if n_importance>0).
@@ -37,14 +37,14 @@ def render(params_coarse, params_fine, poses, ray_idx, H, W, K, rng, *,
     o, d, view = _rays.ray_batch(poses, ray_idx, H, W, K, remap=remap, ndc=ndc)
     n = o.shape[0]
     z = _rays.stratified_depths(n, n_samples, rng["t_rand"], near, far)
-    raw = mlp_forward(params_coarse, _rays.sample_points(o, d, z), view)
+    raw = mlp_forward(params_coarse, _rays.sample_points(o, d, z), view, barf)
     c = composite(raw, z, d, rng["noise_c"], channels)
     out = {"rgb_map": c["rgb_map"], "disp_map": c["disp_map"], "acc_map": c["acc_map"]}
     extra = {"rays_o": o, "rays_d": d, "viewdirs": view, "z_coarse": z, "raw_coarse": raw,
              "weights_coarse": c["weights"], "depth0": c["depth_map"], "sigma0": c["sigma"]}
     if n_importance > 0:
         zf = fine_depths(z, c["weights"], rng["u"])
-        raw_f = mlp_forward(params_fine, _rays.sample_points(o, d, zf), view)
+        raw_f = mlp_forward(params_fine, _rays.sample_points(o, d, zf), view, barf)
         f = composite(raw_f, zf, d, rng["noise_f"], channels)
         out = {"rgb_map": f["rgb_map"], "disp_map": f["disp_map"], "acc_map": f["acc_map"],
                "rgb0": c["rgb_map"], "disp0": c["disp_map"], "acc0": c["acc_map"], "sigma": f["sigma"]}

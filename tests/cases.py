@@ -40,6 +40,7 @@ class Case:
     training: bool = True
     seed: int = 0
     n_events: int = 4000
+    barf_iter: int = -1     # >= 0: args.use_barf_c2f with iter_step = barf_iter of max_iter = 1000, start 0.1, end 0.5 (model/nerf.py:16-26)
 
     @property
     def K(self):
@@ -62,7 +63,16 @@ CASES = {c.name: c for c in [
     # gray + fine network, linear trajectory, larger camera motion, zero biases (init_nerf state)
     Case("gray_linear", "BeNeRF_Blender", 1, 400, 600, 541.850232, 300.0, 200.0, 5, 8, 8,
          traj="linear", knot_scale=0.2, transform_scale=0.05, bias_scale=0.0, seed=15),
+    # BARF coarse-to-fine weighting of the positional encodings, mid-schedule (frequencies 0..3 on, 4 partly, 5..9 off)
+    Case("barf_c2f", "BeNeRF_Unreal", 3, 480, 768, 548.409, 384.0, 240.0, 5, 6, 12, seed=16, barf_iter=270),
 ]}
+
+BARF_MAX_ITER, BARF_START, BARF_END = 1000, 0.1, 0.5
+
+
+def barf_of(case):
+    """(progress, start, end) of a BARF case for the oracle, else None."""
+    return (case.barf_iter / BARF_MAX_ITER, BARF_START, BARF_END) if case.barf_iter >= 0 else None
 
 
 def layer_shapes(channels):

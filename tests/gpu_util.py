@@ -18,6 +18,12 @@ def make_engine(case, mode):
     from benerf_b200.engine import Engine
     eng = Engine(n_samples=case.n_samples, n_importance=case.n_importance, channels=case.channels, mlp_mode=mode)
     eng.set_sample_grid(torch.linspace(0.0, 1.0, steps=case.n_samples))   # the oracle's own grid (see bnrf_set_sample_grid)
+    if case.barf_iter >= 0:                                                # BARF c2f case: channel weights of its iter_step
+        from argparse import Namespace
+        from benerf_b200.nerf import barf_c2f_channel_weights
+        from tests.cases import BARF_MAX_ITER, BARF_START, BARF_END
+        eng.set_encoding_weights(*barf_c2f_channel_weights(case.barf_iter, Namespace(
+            multires=10, multires_views=4, max_iter=BARF_MAX_ITER, barf_c2f_start=BARF_START, barf_c2f_end=BARF_END)))
     return eng
 
 

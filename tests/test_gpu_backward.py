@@ -22,10 +22,27 @@ pytestmark = pytest.mark.gpu
 
 
 def case_args(case):
+    from tests.cases import BARF_MAX_ITER, BARF_START, BARF_END
     return Namespace(dataset=case.dataset, channels=case.channels, N_samples=case.n_samples, N_importance=case.n_importance,
-                     multires=10, multires_views=4, i_embed=0, use_viewdirs=True, use_barf_c2f=False, ndc=True, traj=case.traj,
+                     multires=10, multires_views=4, i_embed=0, use_viewdirs=True, use_barf_c2f=case.barf_iter >= 0,
+                     max_iter=BARF_MAX_ITER, barf_c2f_start=BARF_START, barf_c2f_end=BARF_END, ndc=True, traj=case.traj,
                      num_interpolated_pose=case.n_poses, rgb_crf_net_hidden=0, rgb_crf_net_width=128, event_crf_net_hidden=0,
                      event_crf_net_width=128, chunk=4096, seed=0, event_threshold=case.event_threshold)
+
+
+def _record(key, report):
+    """Append a per-tensor gradient-error report to gpurun_out/gradient_parity.json (copied to profiles/ per round)."""
+    import json, os
+    os.makedirs("gpurun_out", exist_ok=True)
+    path = os.path.join("gpurun_out", "gradient_parity.json")
+    try:
+        with open(path) as f:
+            data = json.load(f)
+    except Exception:
+        data = {}
+    data[key] = {k: float(v) for k, v in report.items()}
+    with open(path, "w") as f:
+        json.dump(data, f, indent=1, sort_keys=True)
 
 
 def rel_err(got, want):
@@ -162,7 +179,7 @@ def _first_pixels(case, inp, n_px):
 
 
 @pytest.mark.parametrize("name,n_px", [("unreal_rgb", None), ("gray_linear", None), ("blender_gray_coarse", None),
-                                       ("unreal_rgb", 3), ("blender_gray_coarse", 5)])
+                                       ("unreal_rgb", 3), ("blender_gray_coarse", 5), ("barf_c2f", None)])
 def test_render_backward_matches_oracle_autograd(name, n_px):
     """One Graph.render under autograd with random cotangents on rgb_map / rgb0, identical samples injected.
     The n_px variants leave a partial last tile and an odd tile count (57 rays x 64 / 128 samples, 35 rays x 64)."""
@@ -175,8 +192,9 @@ def test_render_backward_matches_oracle_autograd(name, n_px):
     knots, transform, coarse, fine_p = _oracle_leaves(case, inp)
     poses_o = pose.poses_from_knots(knots, transform, *case.exposure, case.n_poses, case.traj)
     draws = dict(inp["rng_rgb"])
+    from tests.cases import barf_of
     want = orender.render(coarse, fine_p, poses_o, inp["idx_rgb"], case.H, case.W, case.K, draws, n_samples=case.n_samples,
-                          n_importance=case.n_importance, channels=case.channels, return_intermediates=True)
+                          n_importance=case.n_importance, channels=case.channels, return_intermediates=True, barf=barf_of(case))
     g = torch.Generator().manual_seed(3)
     cot = {k: torch.randn(want[k].shape, generator=g) for k in (("rgb_map", "rgb0") if fine else ("rgb_map",))}
     sum((want[k] * cot[k]).sum() for k in cot).backward()
@@ -184,8 +202,8 @@ def test_render_backward_matches_oracle_autograd(name, n_px):
         draws["z_fine"] = want["_extra"]["z_fine"].detach()
     poses = graph.get_pose_rgb(args, torch.tensor(case.exposure, dtype=torch.float32))
     assert poses.requires_grad
-    got = graph.render(0, poses, inp["idx_rgb"], case.H, case.W, case.K, args, enable_crf=True, sensor_type="rgb", remap=None,
-                       training=True, rng=to_dev(draws))
+    got = graph.render(max(case.barf_iter, 0), poses, inp["idx_rgb"], case.H, case.W, case.K, args, enable_crf=True, sensor_type="rgb",
+                       remap=None, training=True, rng=to_dev(draws))
     for k in cot:
         assert float((got[k].detach().cpu() - want[k].detach()).abs().max()) < 1e-4
     sum((got[k] * cot[k].to(DEV)).sum() for k in cot).backward()
@@ -200,11 +218,12 @@ def test_render_backward_matches_oracle_autograd(name, n_px):
     worst = max(report, key=report.get)
     print(f"{name}: worst relative gradient error {report[worst]:.2e} at {worst}; knots {report['knots']:.2e} transform {report['transform']:.2e}")
     tight = [k for k in report if "rgb_linear" in k or "alpha_linear" in k]
+    _record(f"render_backward[{name}-{n_px}]", report)
     assert max(report[k] for k in tight) < 2e-4, {k: report[k] for k in tight}
-    assert report[worst] < 1e-2, report
+    assert report[worst] < 5e-3, report            # behind ReLU masks: measured <= 2e-3 (mask flips, module docstring)
 
 
-@pytest.mark.parametrize("name,gemm_mode", [("unreal_rgb", "tc"), ("e2nerf_syn", "tc"), ("e2nerf_real", "tc"), ("gray_linear", "tc"),
+@pytest.mark.parametrize("name,gemm_mode", [("unreal_rgb", "tc"), ("e2nerf_syn", "tc"), ("e2nerf_real", "tc"), ("gray_linear", "tc"), ("barf_c2f", "tc"),
                                             ("unreal_rgb", "tc_linear"), ("gray_linear", "tc_linear"),
                                             ("unreal_rgb", "tc_chain1"), ("e2nerf_real", "tc_chain1"), ("gray_linear", "tc_chain1")])
 def test_training_iteration_gradients_match_reference(name, gemm_mode):
@@ -221,7 +240,7 @@ def test_training_iteration_gradients_match_reference(name, gemm_mode):
                                    ("rgb", graph.get_pose_rgb(args, torch.tensor(case.exposure, dtype=torch.float32)), inp["idx_rgb"], inp["rng_rgb"])):
         draws = dict(draws)
         draws["z_fine"] = gold[f"{tag}_z_f"]
-        rets[tag] = graph.render(0, poses, idx, case.H, case.W, case.K, args, enable_crf=True, sensor_type=tag, remap=None,
+        rets[tag] = graph.render(max(case.barf_iter, 0), poses, idx, case.H, case.W, case.K, args, enable_crf=True, sensor_type=tag, remap=None,
                                  training=True, rng=to_dev(draws))
     loss, parts = IF.training_loss(rets["evt"], rets["rgb"], gold["events_accu"].to(DEV), inp["idx_evt"].to(DEV),
                                    inp["blur_target"].to(DEV), args)
@@ -237,7 +256,8 @@ def test_training_iteration_gradients_match_reference(name, gemm_mode):
         report[f"norms_{lvl}"] = float(((norms - gold[f"grad_norms_{lvl}"]).abs() / gold[f"grad_norms_{lvl}"].clamp_min(1e-12)).max())
         report[f"samples_{lvl}"] = rel_err(samples, gold[f"grad_samples_{lvl}"])
     print(f"{name}: loss {float(loss):.6f} (ref {float(gold['loss']):.6f}) gradient errors vs reference {report}")
-    assert max(report.values()) < 1e-2, report
+    _record(f"training_iteration[{name}-{gemm_mode}]", report)
+    assert max(report.values()) < 5e-3, report
 
 
 def test_trainer_fused_tail_matches_torch_adam_tail():

@@ -10,7 +10,7 @@ import torch
 
 import oracle
 from oracle import pose, rays, encode, composite, resample, render, image_formation, events
-from tests.cases import CASES, make_inputs, load_golden
+from tests.cases import CASES, make_inputs, load_golden, barf_of
 
 TIGHT = dict(rtol=0, atol=2e-6)
 
@@ -98,7 +98,7 @@ def test_full_iteration_matches_reference(name):
                                    ("rgb", poses_rgb, inp["idx_rgb"], inp["rng_rgb"])):
         ret = render.render(inp["coarse"], inp["fine"], poses, idx, case.H, case.W, case.K, draws,
                             n_samples=case.n_samples, n_importance=case.n_importance,
-                            channels=case.channels, return_intermediates=True)
+                            channels=case.channels, return_intermediates=True, barf=barf_of(case))
         ex = ret.pop("_extra")
         rets[tag] = ret
         torch.testing.assert_close(ex["z_coarse"], gold[f"{tag}_z_c"], rtol=0, atol=0)

@@ -53,12 +53,13 @@ def import_reference():
 
 
 def ref_args(case):
+    from tests.cases import BARF_MAX_ITER, BARF_START, BARF_END
     return Namespace(dataset=case.dataset, channels=case.channels, N_samples=case.n_samples,
                      N_importance=case.n_importance, multires=10, multires_views=4, i_embed=0,
-                     use_viewdirs=True, use_barf_c2f=False, ndc=True, traj=case.traj,
+                     use_viewdirs=True, use_barf_c2f=case.barf_iter >= 0, ndc=True, traj=case.traj,
                      num_interpolated_pose=case.n_poses, rgb_crf_net_hidden=0, rgb_crf_net_width=128,
-                     event_crf_net_hidden=0, event_crf_net_width=128, chunk=4096, max_iter=80000,
-                     barf_c2f_start=0.1, barf_c2f_end=0.5)
+                     event_crf_net_hidden=0, event_crf_net_width=128, chunk=4096, max_iter=BARF_MAX_ITER,
+                     barf_c2f_start=BARF_START, barf_c2f_end=BARF_END)
 
 
 @contextlib.contextmanager
@@ -133,7 +134,7 @@ def run_case(ref, case):
     for tag, poses, idx, draws, sensor in (("evt", poses_evt, inp["idx_evt"], inp["rng_evt"], "event"),
                                            ("rgb", poses_rgb, inp["idx_rgb"], inp["rng_rgb"], "rgb")):
         with injected_rng(draws), record_calls(graph, out, tag):
-            ret = graph.render(0, poses, idx, case.H, case.W, K, args, enable_crf=True,
+            ret = graph.render(max(case.barf_iter, 0), poses, idx, case.H, case.W, K, args, enable_crf=True,
                                sensor_type=sensor, remap=None, training=case.training)
         rets[tag] = ret
         for k, v in ret.items():
