@@ -61,8 +61,13 @@ class _RenderFn(torch.autograd.Function):
         # bnrf_render_backward ACCUMULATES into the gradient tables.  When every parameter already owns a gradient buffer
         # (benerf_b200.parallel.FlatGrads: p.grad are views of one flat fp32 buffer) the kernels add straight into p.grad
         # and autograd is told there is nothing left to accumulate: no temporaries, no 48 add kernels per render.
-        direct = all(p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 and p.grad.device == eng.device
-                     for p in ctx.params)
+        if ctx.saved_buf is None:
+            raise RuntimeError("Graph.render's saved activations were released by the first backward pass (they are ~10 KB per "
+                               "sample); render again instead of backward(retain_graph=True)")
+        # direct accumulation only on request (parallel.FlatGrads sets _bnrf_direct_grad on the parameters it lays out): otherwise
+        # torch.autograd.grad(loss, params) would silently get no gradient while .grad is mutated
+        direct = all(getattr(p, "_bnrf_direct_grad", False) and p.grad is not None and p.grad.is_contiguous()
+                     and p.grad.dtype == torch.float32 and p.grad.device == eng.device for p in ctx.params)
         if direct:
             grads = [p.grad for p in ctx.params]
         else:
@@ -175,6 +180,7 @@ class Graph(nn.Module):
         """model/nerf.py:160-234: pick an event window, accumulate it, interpolate the two pose sets,
         render the event pair and the N-pose blur batch."""
         dev = self.engine(args).device
+        ev = self._device_events(events, dev, args)
         ts_all = events["ts"]
         if args.event_time_window:
             window_t = args.accumulate_time_length
@@ -184,10 +190,12 @@ class Graph(nn.Module):
             else:
                 low_t = np.random.randint((1 - window_t) // window_t) * window_t
                 upper_t = np.min((low_t + window_t, 1.0))
-            # events are time-sorted: the closed window [low, up] (Q16) is one contiguous slice
-            lo = int(np.searchsorted(ts_all, float(np.asarray(low_t).reshape(-1)[0]), side="left"))
-            hi = int(np.searchsorted(ts_all, float(np.asarray(upper_t).reshape(-1)[0]), side="right"))
+            # the reference masks low <= ts <= up over all events (order-independent, model/nerf.py:170-178); on time-sorted
+            # events -- checked once at upload, a sorted device copy is made otherwise -- that closed window (Q16) is one slice
+            lo = int(np.searchsorted(ev["ts_sorted"], float(np.asarray(low_t).reshape(-1)[0]), side="left"))
+            hi = int(np.searchsorted(ev["ts_sorted"], float(np.asarray(upper_t).reshape(-1)[0]), side="right"))
             events_ts = np.stack((low_t, upper_t)).reshape(2)
+            win = ev["sorted"]
         else:
             num = len(events["pol"])
             N_window = round(num * args.accumulate_time_length)
@@ -197,8 +205,8 @@ class Graph(nn.Module):
                 lo = np.random.randint((num - N_window) // N_window) * N_window
             hi = int(lo + N_window)
             events_ts = ts_all[np.array([lo, hi - 1])]
-        ev = self._device_events(events, dev, args)
-        events_accu = image_formation.accumulate_events(ev["x"][lo:hi], ev["y"][lo:hi], ev["pol"][lo:hi],
+            win = ev["given"]                           # an index window is a slice of the events in the order given (model/nerf.py:190-193)
+        events_accu = image_formation.accumulate_events(win["x"][lo:hi], win["y"][lo:hi], win["pol"][lo:hi],
                                                         args.event_height, args.event_width)
         spline_evt_poses = self.get_pose_evt(args, torch.tensor(events_ts, dtype=torch.float32))
         spline_rgb_poses = self.get_pose_rgb(args, torch.tensor(rgb_exp_ts, dtype=torch.float32))
@@ -211,17 +219,28 @@ class Graph(nn.Module):
         return ret_event, ret_rgb, ray_idx_event, ray_idx_rgb, events_accu
 
     def _device_events(self, events, dev, args):
-        """Keep the (sorted) event arrays resident on the device instead of masking + uploading the
-        window every iteration (model/nerf.py:162-199)."""
+        """Keep the event arrays resident on the device instead of masking + uploading the window every iteration
+        (model/nerf.py:162-199).  Returns {"given": arrays in the caller's order, "sorted": arrays in time order, "ts_sorted"}; for
+        time-sorted input (verified here, once per events object) the two are the same tensors."""
         key = id(events["ts"])
         if self._events_dev is None or self._events_dev[0] != key:
             pol = np.asarray(events["pol"], dtype=np.float32).copy()
             if args.dataset == "TUM_VIE":
                 pol[pol == 0] = -1                      # 0 = negative polarity in TUM-VIE (model/nerf.py:194-196)
-            self._events_dev = (key, {
-                "x": torch.as_tensor(np.asarray(events["x"]), dtype=torch.int32, device=dev),
-                "y": torch.as_tensor(np.asarray(events["y"]), dtype=torch.int32, device=dev),
-                "pol": torch.as_tensor(pol, device=dev)})
+            ts = np.asarray(events["ts"])
+
+            def upload(order=None):
+                pick = (lambda a: a) if order is None else (lambda a: a[order])
+                return {"x": torch.as_tensor(pick(np.asarray(events["x"])), dtype=torch.int32, device=dev),
+                        "y": torch.as_tensor(pick(np.asarray(events["y"])), dtype=torch.int32, device=dev),
+                        "pol": torch.as_tensor(pick(pol), device=dev)}
+            given = upload()
+            if ts.size < 2 or bool(np.all(ts[1:] >= ts[:-1])):
+                state = {"given": given, "sorted": given, "ts_sorted": ts}
+            else:
+                order = np.argsort(ts, kind="stable")
+                state = {"given": given, "sorted": upload(order), "ts_sorted": ts[order]}
+            self._events_dev = (key, state)
         return self._events_dev[1]
 
     # ------------------------------------------------------------------------------------

@@ -3,22 +3,7 @@ import torch
 
 from . import nerf
 from .component import ColorToneMapper, LuminanceToneMapper, ControlKnotLieAlgebra, TransformationLieAlgebra
-
-
-class _SplineFn(torch.autograd.Function):
-    """spline.cubic_spline_pose_unit_time / linear_pose_unit_time under autograd (bnrf_spline_poses[_backward])."""
-
-    @staticmethod
-    def forward(ctx, eng, traj, ts, knots, transform):
-        k = knots.detach().to(eng.device, torch.float32).contiguous()
-        t = transform.detach().reshape(6).to(eng.device, torch.float32).contiguous() if transform is not None else None
-        ctx.eng, ctx.traj, ctx.ts, ctx.k, ctx.t = eng, traj, ts, k, t
-        return eng.spline_poses(k, t, ts, traj)
-
-    @staticmethod
-    def backward(ctx, d_poses):
-        d_knots, d_transform = ctx.eng.spline_poses_backward(ctx.k, ctx.t, ctx.ts, d_poses.contiguous(), ctx.traj)
-        return None, None, None, d_knots, (d_transform.reshape(1, 6) if d_transform is not None else None)
+from .spline import SplineFn
 
 
 class Model(nerf.Model):
@@ -63,7 +48,7 @@ class Graph(nerf.Graph):
         ts = torch.linspace(float(ts2[0]), float(ts2[1]), num, device=eng.device)
         if args.traj not in ("linear", "spline"):
             raise ValueError(args.traj)
-        return _SplineFn.apply(eng, args.traj, ts, self.evt_knot_pose_se3.params.weight,
+        return SplineFn.apply(eng, args.traj, ts, self.evt_knot_pose_se3.params.weight,
                                self.transform.params.weight if with_transform else None)
 
     def get_pose_evt(self, args, events_ts, seg_num=None):

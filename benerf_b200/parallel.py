@@ -56,13 +56,18 @@ class FlatGrads:
     single all-reduce with no packing copies."""
 
     def __init__(self, params):
-        self.params = [p for p in params if p.requires_grad]
+        self.params = list(params)
+        if not all(p.requires_grad for p in self.params):
+            # the flat layout is shared with the optimiser's parameter / moment buffers (train.Trainer): dropping a frozen tensor
+            # would shift every later offset
+            raise ValueError("FlatGrads lays out ALL given parameters; freeze an optimiser through its flag, not with requires_grad=False")
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
+            p._bnrf_direct_grad = True          # Graph.render's backward may add straight into p.grad (nerf._RenderFn.backward)
             off += p.numel()
 
     def zero(self):

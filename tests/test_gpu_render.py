@@ -314,6 +314,41 @@ def test_graph_forward_windows_events_and_renders_both_batches(time_window, rand
     assert float(graph.evt_knot_pose_se3.params.weight.grad.abs().sum()) > 0 and float(graph.transform.params.weight.grad.abs().sum()) > 0
 
 
+@pytest.mark.parametrize("time_window", [True, False])
+def test_graph_forward_accepts_unsorted_events(time_window):
+    """The reference selects a time window with a mask over ALL events (model/nerf.py:170-178), so it does not care about their
+    order; an index window is a slice in the order given (190-193).  Graph.forward must give the reference's accumulation for
+    shuffled events too (it sorts a device copy once when the timestamps are not monotone)."""
+    import numpy as np
+    from tests.test_gpu_backward import case_args
+    from benerf_b200 import optimize, run_nerf_helpers as rh
+    case = CASES["e2nerf_syn"]
+    inp = make_inputs(case)
+    args = case_args(case)
+    args.event_time_window, args.random_sampling_window, args.accumulate_time_length = time_window, True, 0.1
+    args.event_height, args.event_width, args.sampling_event_rays, args.sampling_rgb_rays = case.H, case.W, 16, 38
+    graph = optimize.Model(args).build_network(args)
+    rh.init_nerf(graph.nerf); rh.init_nerf(graph.nerf_fine)
+    graph.to(DEV)
+    perm = np.random.default_rng(3).permutation(len(inp["events"]["ts"]))
+    ev = {k: np.asarray(v)[perm] for k, v in inp["events"].items()}
+    assert not np.all(ev["ts"][1:] >= ev["ts"][:-1])
+    np.random.seed(7)
+    with torch.no_grad():
+        _, _, _, _, accu = graph.forward(0, ev, case.exposure, case.H, case.W, case.K, case.K, args, None, None)
+    np.random.seed(7)
+    if time_window:
+        low = np.random.rand(1) * (1 - 0.1); up = low + 0.1
+        sel = np.where((low <= ev["ts"]) * (ev["ts"] <= up))
+    else:
+        num = len(ev["pol"]); nw = round(num * 0.1)
+        lo = np.random.randint(num - nw)
+        sel = (np.arange(lo, lo + nw),)
+    want = np.zeros((case.H, case.W))
+    np.add.at(want, (ev["y"][sel], ev["x"][sel]), ev["pol"][sel])
+    assert np.array_equal(accu.cpu().numpy(), want) and np.abs(want).sum() > 0
+
+
 def test_full_bench_size_properties():
     """Size-independent properties at the FULL size bench.py times (BASELINE.json configs[1] throughput shape: 65,536 pixels x
     19 poses = 1,245,184 rays, 64 + 128 samples), where the oracle cannot follow:
