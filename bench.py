@@ -423,7 +423,7 @@ def bench_ours(opts):
     graph.to(dev)
     eng = graph.engine(args)
     if opts.mode == "train":                 # development aid: only the training-step measurement
-        t = bench_train_step(opts, dev, world, rank, steps=opts.steps, warmup=opts.warmup, config=opts.train_config)
+        t = bench_train_step(opts, dev, world, rank, steps=opts.steps, warmup=opts.warmup, config=opts.train_config, scaling=opts.train_scaling)
         if rank == 0:
             print(json.dumps(t))
         if world > 1:
@@ -583,6 +583,7 @@ def main():
     ap.add_argument("--mlp-mode", default="tc", choices=["tc", "tc2", "tc1", "simt"])
     ap.add_argument("--mode", default="render", choices=["render", "train"], help="train: print only the training-step line")
     ap.add_argument("--train-config", default="e2nerf_synthetic", choices=["e2nerf_synthetic", "e2nerf_real"])
+    ap.add_argument("--train-scaling", default="weak", choices=["weak", "strong"], help="--mode train: per-GPU batch fixed, or one batch split")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-step", action="store_true", help="skip the extra training-step measurement")
     opts = ap.parse_args()

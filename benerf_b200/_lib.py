@@ -63,8 +63,11 @@ PROTOTYPES = {
     "bnrf_last_error": (C.c_char_p, [_P]),
     "bnrf_set_weights": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_P), _P]),
     "bnrf_set_encoding_weights": (_I, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), _P]),
+    "bnrf_set_weights_pair": (_I, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P]),
     "bnrf_set_sample_grid": (_I, [_P, C.POINTER(C.c_float), _I, _P]),
     "bnrf_spline_poses": (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
+    "bnrf_spline_poses_pair": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "bnrf_spline_poses_pair_backward": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "bnrf_workspace_bytes": (_Z, [_P, _L]),
     "bnrf_render_forward": (_I, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(C.c_float), _P, C.POINTER(Rng), C.POINTER(Outputs), _P, _Z, _P]),
     "bnrf_saved_bytes": (_Z, [_P, _L]),

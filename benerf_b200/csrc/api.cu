@@ -20,34 +20,53 @@ int fail(bnrf_ctx* ctx, int code, const char* fmt, ...) {
 // One launch repacks every tensor of a network (bnrf_set_weights runs after every optimiser step): a table of segments,
 // blockIdx.y = segment.  Transposes (in_f > 0): dst[(k_dst + k) * N + n] = src[n * in_f + k_src + k] for k < k_count,
 // n < out_f (PyTorch (out,in) -> k-major); plain copies (in_f == 0): dst[i] = src[i] for i < k_count.
-struct PackSeg { const float* src; float* dst; int out_f, in_f, k_src, k_dst, k_count, N; const float* kscale; /* [k_count] per input channel, or NULL */ };
-struct PackTable { PackSeg seg[28]; int n; };
+// amax (nullable): max |value written| is folded into *amax (as uint bits) -- the per-GEMM-step maxima from which the fp16
+// pre-scale of the tensor-core weight stream is derived, gathered while the matrix is transposed anyway.
+struct PackSeg { const float* src; float* dst; int out_f, in_f, k_src, k_dst, k_count, N; const float* kscale; /* [k_count] per input channel, or NULL */
+                 unsigned int* amax; };
+struct PackTable { PackSeg seg[56]; int n; };
 __global__ void pack_all_kernel(const __grid_constant__ PackTable t) {
     const PackSeg& s = t.seg[blockIdx.y];
     const int total = s.in_f ? s.k_count * s.out_f : s.k_count;
+    float m = 0.0f;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         if (s.in_f) {
             const int k = idx / s.out_f, n = idx % s.out_f;
-            const float v = s.src[(size_t)n * s.in_f + s.k_src + k];
-            s.dst[(size_t)(s.k_dst + k) * s.N + n] = s.kscale ? v * s.kscale[k] : v;
+            float v = s.src[(size_t)n * s.in_f + s.k_src + k];
+            if (s.kscale) v *= s.kscale[k];
+            s.dst[(size_t)(s.k_dst + k) * s.N + n] = v;
+            m = fmaxf(m, fabsf(v));
         } else {
             s.dst[idx] = s.src[idx];
         }
+    }
+    if (s.amax) {
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x % 32 == 0 && m > 0.0f) atomicMax(s.amax, __float_as_uint(m));
     }
 }
 
 // wt9m[k][j] = sum_f wt8[k][f] * wt9[f][j];  bias9m[j] = b_views[j] + sum_f b_feature[f] * wt9[f][j]   (block k, thread j;
 // block 256 computes the bias)
-__global__ void merge_views_kernel(const float* __restrict__ wt8 /*[256 k][256 f]*/, const float* __restrict__ wt9 /*[256 f][128 j]*/,
-                                   const float* __restrict__ b_feature, const float* __restrict__ b_views,
-                                   float* __restrict__ wt9m, float* __restrict__ bias9m) {
+struct MergeViews { const float *wt8, *wt9, *b_feature, *b_views; float *wt9m, *bias9m; unsigned int* amax; /* slot 10, nullable */ };
+struct MergeViewsPair { MergeViews net[2]; };
+__global__ void merge_views_kernel(const __grid_constant__ MergeViewsPair p) {      // blockIdx.y = network
+    const MergeViews& m = p.net[blockIdx.y];
     const int k = blockIdx.x, j = threadIdx.x;
-    const float* a = (k < kWidth) ? wt8 + (size_t)k * kWidth : b_feature;
+    const float* a = (k < kWidth) ? m.wt8 + (size_t)k * kWidth : m.b_feature;
     float acc = 0.f;
 #pragma unroll 8
-    for (int f = 0; f < kWidth; ++f) acc = fmaf(a[f], wt9[(size_t)f * kHalf + j], acc);
-    if (k < kWidth) wt9m[(size_t)k * kHalf + j] = acc;
-    else bias9m[j] = b_views[j] + acc;
+    for (int f = 0; f < kWidth; ++f) acc = fmaf(a[f], m.wt9[(size_t)f * kHalf + j], acc);
+    if (k < kWidth) {
+        m.wt9m[(size_t)k * kHalf + j] = acc;
+        if (m.amax) {
+            float v = fabsf(acc);
+            for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if (j % 32 == 0 && v > 0.0f) atomicMax(m.amax, __float_as_uint(v));
+        }
+    } else {
+        m.bias9m[j] = m.b_views[j] + acc;
+    }
 }
 
 int pack_tc_stream(bnrf_ctx*, int net, cudaStream_t);   // mlp_tc.cu
@@ -98,30 +117,30 @@ void free_net(bnrf_ctx* ctx, int n) {
     memset(&np, 0, sizeof(np));
 }
 
-int pack_weights(bnrf_ctx* ctx, int n, const float* const* w, const float* const* b, cudaStream_t st) {
+// Segments of one network.  fused: the per-step maxima are gathered here (absmax slots 0..9) instead of by absmax_kernel.
+static void pack_segments(bnrf_ctx* ctx, int n, const float* const* w, const float* const* b, PackTable& t, bool fused) {
     NetParams& np = ctx->net[n];
     const int C = ctx->cfg.channels;
-    PackTable t{};
-    auto tr = [&](const float* W, int out_f, int in_f, int k_src, int k_dst, int k_count, int N, float* dst, const float* kscale = nullptr) {
-        t.seg[t.n++] = PackSeg{W, dst, out_f, in_f, k_src, k_dst, k_count, N, kscale};
+    auto tr = [&](const float* W, int out_f, int in_f, int k_src, int k_dst, int k_count, int N, float* dst, int slot, const float* kscale = nullptr) {
+        t.seg[t.n++] = PackSeg{W, dst, out_f, in_f, k_src, k_dst, k_count, N, kscale, (fused && slot >= 0) ? np.absmax + slot : nullptr};
     };
-    auto cp = [&](const float* src, int cnt, float* dst) { t.seg[t.n++] = PackSeg{src, dst, 0, 0, 0, 0, cnt, 0, nullptr}; };
+    auto cp = [&](const float* src, int cnt, float* dst) { t.seg[t.n++] = PackSeg{src, dst, 0, 0, 0, 0, cnt, 0, nullptr, nullptr}; };
     // BARF c2f (bnrf_set_encoding_weights): the encoding channels' weights scale the weight-matrix columns that read them
     const float* sp = ctx->enc_scaled ? ctx->enc_scale : nullptr;
     const float* sd = ctx->enc_scaled ? ctx->enc_scale + 64 : nullptr;
     // GEMM step s <- reference linear: 0-7 pts_linears, 8 feature_linear, 9 views_linears.0 (feature block)
-    tr(w[BNRF_L_PTS0], kWidth, kPtsCh, 0, 0, kPtsCh, kWidth, np.wt[0], sp);
+    tr(w[BNRF_L_PTS0], kWidth, kPtsCh, 0, 0, kPtsCh, kWidth, np.wt[0], 0, sp);
     for (int l = 1; l < 8; ++l) {
         if (l == 5) {   // cat([input_pts, h]) -> [pe64 | h256]  (model/nerf.py:98)
-            tr(w[l], kWidth, kPtsCh + kWidth, 0, 0, kPtsCh, kWidth, np.wt[5], sp);
-            tr(w[l], kWidth, kPtsCh + kWidth, kPtsCh, kPtsChPad, kWidth, kWidth, np.wt[5]);
+            tr(w[l], kWidth, kPtsCh + kWidth, 0, 0, kPtsCh, kWidth, np.wt[5], 5, sp);
+            tr(w[l], kWidth, kPtsCh + kWidth, kPtsCh, kPtsChPad, kWidth, kWidth, np.wt[5], 5);
         } else {
-            tr(w[l], kWidth, kWidth, 0, 0, kWidth, kWidth, np.wt[l]);
+            tr(w[l], kWidth, kWidth, 0, 0, kWidth, kWidth, np.wt[l], l);
         }
     }
-    tr(w[BNRF_L_FEATURE], kWidth, kWidth, 0, 0, kWidth, kWidth, np.wt[8]);
-    tr(w[BNRF_L_VIEWS], kHalf, kWidth + kDirCh, 0, 0, kWidth, kHalf, np.wt[9]);       // cat([feature, dirs]) (model/nerf.py:103)
-    tr(w[BNRF_L_VIEWS], kHalf, kWidth + kDirCh, kWidth, 0, kDirCh, kHalf, np.w_dir, sd);
+    tr(w[BNRF_L_FEATURE], kWidth, kWidth, 0, 0, kWidth, kWidth, np.wt[8], 8);
+    tr(w[BNRF_L_VIEWS], kHalf, kWidth + kDirCh, 0, 0, kWidth, kHalf, np.wt[9], 9);       // cat([feature, dirs]) (model/nerf.py:103)
+    tr(w[BNRF_L_VIEWS], kHalf, kWidth + kDirCh, kWidth, 0, kDirCh, kHalf, np.w_dir, -1, sd);
     for (int l = 0; l < 8; ++l) cp(b[l], kWidth, np.bias[l]);
     cp(b[BNRF_L_FEATURE], kWidth, np.bias[8]);
     cp(b[BNRF_L_VIEWS], kHalf, np.bias[9]);
@@ -129,14 +148,56 @@ int pack_weights(bnrf_ctx* ctx, int n, const float* const* w, const float* const
     cp(b[BNRF_L_ALPHA], 1, np.b_alpha);
     cp(w[BNRF_L_RGB], C * kHalf, np.w_rgb);
     cp(b[BNRF_L_RGB], C, np.b_rgb);
+}
+
+static MergeViews merge_args(NetParams& np, bool fused) {
+    return MergeViews{np.wt[8], np.wt[9], np.bias[8], np.bias[9], np.wt9m, np.bias9m, fused ? np.absmax + 10 : nullptr};
+}
+
+int pack_weights(bnrf_ctx* ctx, int n, const float* const* w, const float* const* b, cudaStream_t st) {
+    NetParams& np = ctx->net[n];
+    PackTable t{};
+    pack_segments(ctx, n, w, b, t, false);
     pack_all_kernel<<<dim3(16, t.n), 256, 0, st>>>(t);
     BNRF_LAUNCH_CHECK(ctx);
-    merge_views_kernel<<<kWidth + 1, kHalf, 0, st>>>(np.wt[8], np.wt[9], np.bias[8], np.bias[9], np.wt9m, np.bias9m);
+    MergeViewsPair mv{};
+    mv.net[0] = merge_args(np, false);
+    merge_views_kernel<<<dim3(kWidth + 1, 1), kHalf, 0, st>>>(mv);
     BNRF_LAUNCH_CHECK(ctx);
     int rc = pack_tc_stream(ctx, n, st);
     if (rc != BNRF_OK) return rc;
     np.ready = true;
     np.dg_dirty = true;
+    return BNRF_OK;
+}
+
+// Both networks of a Graph repacked together (the training loop does this after every optimiser step): 4 launches instead of 12 --
+// transpose + per-step maxima, merged view step + its maximum, tensor-core stream (the pre-scale is derived from the maxima inside
+// the packing kernel), and, for a training context, the dgrad chain's transposed stream.
+int pack_weights_pair(bnrf_ctx* ctx, const float* const* w0, const float* const* b0, const float* const* w1, const float* const* b1,
+                      cudaStream_t st) {
+    if (ctx->cfg.mlp_mode != BNRF_MLP_TC_FP16X2) {           // the other kernels keep the per-network pipeline
+        int rc = pack_weights(ctx, 0, w0, b0, st);
+        return rc ? rc : pack_weights(ctx, 1, w1, b1, st);
+    }
+    PackTable t{};
+    for (int n = 0; n < 2; ++n) {
+        BNRF_CUDA(ctx, cudaMemsetAsync(ctx->net[n].absmax, 0, 16 * sizeof(unsigned int), st));
+        pack_segments(ctx, n, n ? w1 : w0, n ? b1 : b0, t, true);
+    }
+    pack_all_kernel<<<dim3(16, t.n), 256, 0, st>>>(t);
+    BNRF_LAUNCH_CHECK(ctx);
+    MergeViewsPair mv{};
+    for (int n = 0; n < 2; ++n) mv.net[n] = merge_args(ctx->net[n], true);
+    merge_views_kernel<<<dim3(kWidth + 1, 2), kHalf, 0, st>>>(mv);
+    BNRF_LAUNCH_CHECK(ctx);
+    int rc = pack_tc3_stream_pair(ctx, st);
+    if (rc != BNRF_OK) return rc;
+    for (int n = 0; n < 2; ++n) { ctx->net[n].ready = true; ctx->net[n].dg_dirty = true; }
+    if (ctx->cfg.gemm_mode == BNRF_GEMM_TC) {                // training contexts: the dgrad chain's operand stream, both networks
+        if ((rc = pack_dgrad_chain_pair_stream_both(ctx, st))) return rc;
+        for (int n = 0; n < 2; ++n) ctx->net[n].dg_dirty = false;
+    }
     return BNRF_OK;
 }
 
@@ -300,16 +361,36 @@ int bnrf_set_weights(bnrf_ctx* ctx, int net, const float* const* weights, const 
     return pack_weights(ctx, net, weights, biases, (cudaStream_t)stream);
 }
 
+int bnrf_set_weights_pair(bnrf_ctx* ctx, const float* const* w_coarse, const float* const* b_coarse, const float* const* w_fine,
+                          const float* const* b_fine, void* stream) {
+    if (!ctx || !w_coarse || !b_coarse || !w_fine || !b_fine) return fail(ctx, BNRF_ERR_ARG, "set_weights_pair: bad argument");
+    for (int i = 0; i < BNRF_NUM_LINEARS; ++i)
+        if (!w_coarse[i] || !b_coarse[i] || !w_fine[i] || !b_fine[i]) return fail(ctx, BNRF_ERR_ARG, "set_weights_pair: linear %d is null", i);
+    return pack_weights_pair(ctx, w_coarse, b_coarse, w_fine, b_fine, (cudaStream_t)stream);
+}
+
 int bnrf_spline_poses(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts, int P, int traj,
                       float* poses_out, void* stream) {
     if (!ctx) return BNRF_ERR_ARG;
-    return launch_spline(ctx, knots, transform, ts, P, traj, poses_out, (cudaStream_t)stream);
+    return launch_spline(ctx, knots, transform, ts, P, 0, traj, poses_out, (cudaStream_t)stream);
+}
+
+int bnrf_spline_poses_pair(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts, int P, int n_plain, int traj,
+                           float* poses_out, void* stream) {
+    if (!ctx) return BNRF_ERR_ARG;
+    return launch_spline(ctx, knots, transform, ts, P, n_plain, traj, poses_out, (cudaStream_t)stream);
+}
+
+int bnrf_spline_poses_pair_backward(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts, int P, int n_plain,
+                                    int traj, const float* d_poses, float* d_knots, float* d_transform, void* stream) {
+    if (!ctx) return BNRF_ERR_ARG;
+    return launch_spline_backward(ctx, knots, transform, ts, P, n_plain, traj, d_poses, d_knots, d_transform, (cudaStream_t)stream);
 }
 
 int bnrf_spline_poses_backward(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts, int P, int traj,
                                const float* d_poses, float* d_knots, float* d_transform, void* stream) {
     if (!ctx) return BNRF_ERR_ARG;
-    return launch_spline_backward(ctx, knots, transform, ts, P, traj, d_poses, d_knots, d_transform, (cudaStream_t)stream);
+    return launch_spline_backward(ctx, knots, transform, ts, P, 0, traj, d_poses, d_knots, d_transform, (cudaStream_t)stream);
 }
 
 size_t bnrf_workspace_bytes(const bnrf_ctx* ctx, int64_t n_rays) {

@@ -150,9 +150,9 @@ __device__ inline uint64_t rng_offset(const bnrf_rng& r) { return r.offset + (r.
 enum : uint32_t { kStreamTRand = 1, kStreamNoiseC = 2, kStreamU = 3, kStreamNoiseF = 4 };
 
 // ---- launchers implemented in the individual .cu files ---------------------------------
-int launch_spline(bnrf_ctx*, const float* knots, const float* transform, const float* ts, int P, int traj,
+int launch_spline(bnrf_ctx*, const float* knots, const float* transform, const float* ts, int P, int n_plain, int traj,
                   float* poses, cudaStream_t);
-int launch_spline_backward(bnrf_ctx*, const float* knots, const float* transform, const float* ts, int P, int traj,
+int launch_spline_backward(bnrf_ctx*, const float* knots, const float* transform, const float* ts, int P, int n_plain, int traj,
                            const float* d_poses, float* d_knots, float* d_transform, cudaStream_t);
 int launch_rays(bnrf_ctx*, const float* poses, const int64_t* ray_idx, int P, int R, int H, int W, const float* K,
                 const float* remap, float* o, float* d, float* view, cudaStream_t);
@@ -176,6 +176,8 @@ int pack_tc2_stream(bnrf_ctx*, int net, const float* const* table_dev, const flo
 int launch_mlp_tc2(bnrf_ctx*, int net, const float* o, const float* d, const float* vb, const float* z,
                    int64_t n, int S, float* raw, const ActPtrs* acts /*NULL unless training*/, cudaStream_t);
 size_t tc3_stream_halfs();
+int pack_tc3_stream_pair(bnrf_ctx*, cudaStream_t);                  // both networks, pre-scale derived from NetParams::absmax in the kernel
+int pack_dgrad_chain_pair_stream_both(bnrf_ctx*, cudaStream_t);    // both networks in one launch
 int pack_tc3_stream(bnrf_ctx*, int net, const float* const* table_dev, const float* scale_dev, cudaStream_t);
 int launch_mlp_tc3(bnrf_ctx*, int net, const float* o, const float* d, const float* vb, const float* z,
                    int64_t n, int S, float* raw, const ActPtrs* acts /*NULL unless training*/, cudaStream_t);

@@ -362,8 +362,11 @@ dgrad_chain_pair_kernel(const unsigned char* __restrict__ stream, const unsigned
 }
 
 // rank r's stage (pass p, K-block kb, hi/lo): element (n, k) of its [N/2 x 64] SW128 tile <- wt[slot][(k0 + r*N/2 + n) * K + kb*64 + k]
-__global__ void pack_chain_pair_stream_kernel(const float* const* __restrict__ wt, unsigned char* __restrict__ stream) {
-    const int p = blockIdx.y, rank = blockIdx.z;
+struct ChainPackNets { const float* const* wt[2]; unsigned char* stream[2]; };
+__global__ void pack_chain_pair_stream_kernel(const __grid_constant__ ChainPackNets nets) {       // blockIdx.z = 2 * network + rank
+    const float* const* __restrict__ wt = nets.wt[blockIdx.z >> 1];
+    unsigned char* __restrict__ stream = nets.stream[blockIdx.z >> 1];
+    const int p = blockIdx.y, rank = blockIdx.z & 1;
     const PassInfo pi = pass_info(p);
     const int i = blockIdx.x;
     if (i >= pass_stages(p)) return;
@@ -386,7 +389,17 @@ size_t dgrad_chain_pair_stream_bytes() { return 2 * dgp::rank_stream_bytes(); }
 
 int pack_dgrad_chain_pair_stream(bnrf_ctx* ctx, int net, cudaStream_t st) {
     NetParams& np = ctx->net[net];
-    dgp::pack_chain_pair_stream_kernel<<<dim3(8, dgp::NUM_PASSES, 2), 256, 0, st>>>(np.wt_table, np.dgp_stream);
+    dgp::ChainPackNets nets{};
+    nets.wt[0] = np.wt_table; nets.stream[0] = np.dgp_stream;
+    dgp::pack_chain_pair_stream_kernel<<<dim3(8, dgp::NUM_PASSES, 2), 256, 0, st>>>(nets);
+    BNRF_LAUNCH_CHECK(ctx);
+    return BNRF_OK;
+}
+
+int pack_dgrad_chain_pair_stream_both(bnrf_ctx* ctx, cudaStream_t st) {
+    dgp::ChainPackNets nets{};
+    for (int n = 0; n < 2; ++n) { nets.wt[n] = ctx->net[n].wt_table; nets.stream[n] = ctx->net[n].dgp_stream; }
+    dgp::pack_chain_pair_stream_kernel<<<dim3(8, dgp::NUM_PASSES, 4), 256, 0, st>>>(nets);
     BNRF_LAUNCH_CHECK(ctx);
     return BNRF_OK;
 }

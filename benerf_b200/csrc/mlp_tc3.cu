@@ -566,6 +566,50 @@ mlp_tc3_kernel(const __grid_constant__ Schedule sched, TcParams p, const float* 
 // two CTAs' B rows along N, so rank r holds features [128 r, 128 r + 128) of a FULL group, [128 h + 64 r, + 64) of N-half h,
 // and [64 r, 64 r + 64) of the 128-wide view layer.
 struct PackTable3 { uint32_t off[2 * MAX_GROUPS]; };
+
+// 2^s with max|W| * 2^s in [1024, 2048) (the fp16 pre-scale of a GEMM step's weights, cf. tc::scale_kernel)
+__device__ inline float prescale_from_absmax(unsigned int bits, float* inv) {
+    const float m = __uint_as_float(bits);
+    int s = 0;
+    if (m > 0.0f && isfinite(m)) s = 10 - ilogbf(m);
+    s = max(-24, min(24, s));
+    *inv = exp2f((float)-s);
+    return exp2f((float)s);
+}
+
+struct PackNet3 { const float* const* wt; const unsigned int* absmax; float* scale; float* inv_scale; __half* stream; };
+struct PackNets3 { PackNet3 net[2]; };
+// pack_stream3_kernel for both networks (blockIdx.z), deriving each step's pre-scale from the maxima pack_all_kernel /
+// merge_views_kernel gathered; block (0, 0, net) also publishes scale / inv_scale for the MLP kernel's epilogue.
+__global__ void pack_stream3_pair_kernel(const __grid_constant__ Schedule sched, const __grid_constant__ PackTable3 tab, size_t rank_bytes,
+                                         const __grid_constant__ PackNets3 nets) {
+    const PackNet3& pn = nets.net[blockIdx.z];
+    const int i = blockIdx.x, rank = blockIdx.y;
+    if (i == 0 && rank == 0 && threadIdx.x < 11) {
+        float inv;
+        pn.scale[threadIdx.x] = prescale_from_absmax(pn.absmax[threadIdx.x], &inv);
+        pn.inv_scale[threadIdx.x] = inv;
+    }
+    const GroupDesc gd = sched.g[i >> 1];
+    const int lo = i & 1;
+    const bool view = gd.t == NUM_STEPS - 1;
+    const int ti = view ? 10 : gd.t;
+    const float* w = pn.wt[ti];
+    float inv;
+    const float sc = prescale_from_absmax(pn.absmax[ti], &inv);
+    const int N = view ? 128 : 256;
+    const int k0 = gd.kb < 0 ? 0 : (gd.t == 5 ? kPtsChPad : 0) + 64 * gd.kb;
+    const int nrows = (int)(group_stage_bytes(gd) / 128u);
+    const int n0 = view ? 64 * rank : (gd.kind == G_FULL ? 128 * rank : 128 * (gd.kind - G_H0) + 64 * rank);
+    unsigned char* dst = reinterpret_cast<unsigned char*>(pn.stream) + (size_t)rank * rank_bytes + tab.off[i];
+    for (int e = threadIdx.x; e < nrows * 64; e += blockDim.x) {
+        const int k = e / nrows, n = e % nrows;
+        const float v = w[(size_t)(k0 + k) * N + n0 + n] * sc;
+        const __half hi = __float2half_rn(v);
+        const __half out = lo ? __float2half_rn(v - __half2float(hi)) : hi;
+        *reinterpret_cast<__half*>(dst + sw128_offset(n, k)) = out;
+    }
+}
 __global__ void pack_stream3_kernel(const __grid_constant__ Schedule sched, const __grid_constant__ PackTable3 tab, size_t rank_bytes,
                                     const float* const* __restrict__ wt, const float* __restrict__ scale, __half* __restrict__ stream) {
     const int i = blockIdx.x, rank = blockIdx.y;
@@ -617,6 +661,23 @@ int pack_tc3_stream(bnrf_ctx* ctx, int net, const float* const* table_dev, const
     for (int g = 0; g < sc.n; ++g)
         for (int i = 0; i < 2; ++i) { tab.off[2 * g + i] = off; off += group_stage_bytes(sc.g[g]); }
     pack_stream3_kernel<<<dim3(2 * sc.n, 2), 256, 0, st>>>(sc, tab, schedule_stream_bytes(sc), table_dev, scale_dev, np.tc3_stream);
+    BNRF_LAUNCH_CHECK(ctx);
+    return BNRF_OK;
+}
+
+int pack_tc3_stream_pair(bnrf_ctx* ctx, cudaStream_t st) {
+    using namespace tc3;
+    const Schedule& sc = tc3_schedule();
+    PackTable3 tab{};
+    uint32_t off = 0;
+    for (int g = 0; g < sc.n; ++g)
+        for (int i = 0; i < 2; ++i) { tab.off[2 * g + i] = off; off += group_stage_bytes(sc.g[g]); }
+    PackNets3 nets{};
+    for (int n = 0; n < 2; ++n) {
+        NetParams& np = ctx->net[n];
+        nets.net[n] = PackNet3{np.wt_table, np.absmax, np.scale, np.tc_scale, np.tc3_stream};
+    }
+    pack_stream3_pair_kernel<<<dim3(2 * sc.n, 2, 2), 256, 0, st>>>(sc, tab, schedule_stream_bytes(sc), nets);
     BNRF_LAUNCH_CHECK(ctx);
     return BNRF_OK;
 }

@@ -185,10 +185,12 @@ __device__ void interpolate_pose(const T* knots, float time, int traj, T* P) {
     quat_to_pose(q, t, P);
 }
 
+// poses p < n_plain interpolate the knots as they are (event camera), the others knots + transform (RGB camera)
 __global__ void spline_kernel(const float* __restrict__ knots, const float* __restrict__ transform,
-                              const float* __restrict__ ts, int P, int traj, float* __restrict__ poses) {
+                              const float* __restrict__ ts, int P, int n_plain, int traj, float* __restrict__ poses) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
+    if (p < n_plain) transform = nullptr;
     float k[24];
 #pragma unroll
     for (int i = 0; i < 24; ++i) k[i] = knots[i] + (transform ? transform[i % 6] : 0.0f);   // optimize.py:86-89
@@ -206,10 +208,11 @@ __global__ void spline_kernel(const float* __restrict__ knots, const float* __re
 // pose p along knot element j.  The RGB knots are knots + transform (optimize.py:86-89), so the transform's
 // gradient is the sum of the four knots' gradients element-wise.
 __global__ void spline_backward_kernel(const float* __restrict__ knots, const float* __restrict__ transform,
-                                       const float* __restrict__ ts, int P, int traj, const float* __restrict__ d_poses,
+                                       const float* __restrict__ ts, int P, int n_plain, int traj, const float* __restrict__ d_poses,
                                        float* __restrict__ d_knots, float* __restrict__ d_transform) {
     const int p = blockIdx.x, j = threadIdx.x;
     if (p >= P || j >= 24) return;
+    if (p < n_plain) transform = nullptr;
     Dual k[24];
     for (int i = 0; i < 24; ++i) k[i] = Dual(knots[i] + (transform ? transform[i % 6] : 0.0f), i == j ? 1.0f : 0.0f);
     Dual out[12];
@@ -221,18 +224,19 @@ __global__ void spline_backward_kernel(const float* __restrict__ knots, const fl
     if (transform && d_transform) atomicAdd(d_transform + (j % 6), g);
 }
 
-int launch_spline_backward(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts, int P, int traj,
+int launch_spline_backward(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts, int P, int n_plain, int traj,
                            const float* d_poses, float* d_knots, float* d_transform, cudaStream_t st) {
-    if (!knots || !ts || !d_poses || !d_knots || P <= 0 || (traj != 0 && traj != 1)) return fail(ctx, BNRF_ERR_ARG, "spline_backward: bad argument");
-    spline_backward_kernel<<<P, 32, 0, st>>>(knots, transform, ts, P, traj, d_poses, d_knots, d_transform);
+    if (!knots || !ts || !d_poses || !d_knots || P <= 0 || n_plain < 0 || n_plain > P || (traj != 0 && traj != 1))
+        return fail(ctx, BNRF_ERR_ARG, "spline_backward: bad argument");
+    spline_backward_kernel<<<P, 32, 0, st>>>(knots, transform, ts, P, n_plain, traj, d_poses, d_knots, d_transform);
     BNRF_LAUNCH_CHECK(ctx);
     return BNRF_OK;
 }
 
-int launch_spline(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts, int P, int traj,
+int launch_spline(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts, int P, int n_plain, int traj,
                   float* poses, cudaStream_t st) {
-    if (!knots || !ts || !poses || P <= 0 || (traj != 0 && traj != 1)) return fail(ctx, BNRF_ERR_ARG, "spline_poses: bad argument");
-    spline_kernel<<<(P + 63) / 64, 64, 0, st>>>(knots, transform, ts, P, traj, poses);
+    if (!knots || !ts || !poses || P <= 0 || n_plain < 0 || n_plain > P || (traj != 0 && traj != 1)) return fail(ctx, BNRF_ERR_ARG, "spline_poses: bad argument");
+    spline_kernel<<<(P + 63) / 64, 64, 0, st>>>(knots, transform, ts, P, n_plain, traj, poses);
     BNRF_LAUNCH_CHECK(ctx);
     return BNRF_OK;
 }

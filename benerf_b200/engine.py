@@ -79,6 +79,21 @@ class Engine:
             bs[i] = _ptr(b, device=self.device, name=name + ".bias")
         self._check(self.lib.bnrf_set_weights(self._ctx, int(net), ws, bs, _stream()), "bnrf_set_weights")
 
+    def _weight_tables(self, params):
+        ws, bs, keep = (C.c_void_p * 12)(), (C.c_void_p * 12)(), []
+        for i, name in enumerate(_lib.LINEAR_NAMES):
+            w, b = params[name + ".weight"].detach(), params[name + ".bias"].detach()
+            keep += [w, b]
+            ws[i] = _ptr(w, device=self.device, name=name + ".weight")
+            bs[i] = _ptr(b, device=self.device, name=name + ".bias")
+        return ws, bs, keep
+
+    def set_weights_pair(self, params_coarse, params_fine):
+        """Both networks in one repack (bnrf_set_weights_pair)."""
+        wc, bc, k0 = self._weight_tables(params_coarse)
+        wf, bf, k1 = self._weight_tables(params_fine)
+        self._check(self.lib.bnrf_set_weights_pair(self._ctx, wc, bc, wf, bf, _stream()), "bnrf_set_weights_pair")
+
     def sync_weights(self, net, module):
         """Repack only when an optimiser step (or load_state_dict) touched the module's parameters."""
         cache = self.__dict__.setdefault("_sync_params", {})
@@ -137,6 +152,19 @@ class Engine:
         self._check(self.lib.bnrf_spline_poses(self._ctx, _ptr(knots, name="knots"), _ptr(transform, name="transform"),
                                                _ptr(ts, name="ts"), P, TRAJ[traj], _ptr(out), _stream()), "bnrf_spline_poses")
         return out
+
+    def spline_poses_pair(self, knots, transform, ts, n_plain, traj="spline"):
+        """Event poses (first n_plain timestamps, knots only) and RGB poses (the rest, knots + transform) in one launch."""
+        P = ts.numel()
+        out = torch.empty(P, 3, 4, device=self.device, dtype=torch.float32)
+        self._check(self.lib.bnrf_spline_poses_pair(self._ctx, _ptr(knots, name="knots"), _ptr(transform, name="transform"), _ptr(ts, name="ts"),
+                                                    P, int(n_plain), TRAJ[traj], _ptr(out), _stream()), "bnrf_spline_poses_pair")
+        return out
+
+    def spline_poses_pair_backward(self, knots, transform, ts, n_plain, d_poses, d_knots, d_transform, traj="spline"):
+        self._check(self.lib.bnrf_spline_poses_pair_backward(
+            self._ctx, _ptr(knots, name="knots"), _ptr(transform, name="transform"), _ptr(ts, name="ts"), ts.numel(), int(n_plain), TRAJ[traj],
+            _ptr(d_poses, name="d_poses"), _ptr(d_knots), _ptr(d_transform), _stream()), "bnrf_spline_poses_pair_backward")
 
     # -- a3-a10 -----------------------------------------------------------------------------
     def _K(self, K):

@@ -73,8 +73,9 @@ class Trainer:
         a = self.args
         dev = self.flat_params.device
         use_remap = a.dataset == "TUM_VIE"
+        ts_e, ts_r = self._linspace(ts_evt, 2), self._linspace(ts_rgb, a.num_interpolated_pose)
         inputs = {"events_accu": events_accu, "idx_evt": idx_evt, "idx_rgb": idx_rgb, "blur_target": blur_target,
-                  "ts_evt": self._linspace(ts_evt, 2), "ts_rgb": self._linspace(ts_rgb, a.num_interpolated_pose),
+                  "ts": torch.cat([ts_e.to(ts_r.device), ts_r]),                        # the 2 event timestamps first, then the exposure's
                   "remap_evt": remap_evt if use_remap else None, "remap_rgb": remap_rgb if use_remap else None}
         consts = (int(H), int(W), int(H_ev), int(W_ev), _as_tuple(K), _as_tuple(K_event))
         if self.use_graph and self.phase_ms is None:
@@ -137,13 +138,16 @@ class Trainer:
         weights, grad_tabs = self._tables(eng)
         if getattr(a, "use_barf_c2f", False):
             g._sync_barf(eng, self.global_step, a)
-        for net, params in enumerate(weights):                           # the parameters changed (bnrf_adam_step_sched wrote them in place)
-            eng.set_weights(net, params)
+        if len(weights) == 2:                                            # the parameters changed (bnrf_adam_step_sched wrote them in place)
+            eng.set_weights_pair(weights[0], weights[1])
+        else:
+            eng.set_weights(0, weights[0])
         knots = g.evt_knot_pose_se3.params.weight.data
         transform = g.transform.params.weight.data.reshape(6)
         seed = g.seed()
-        poses_evt = eng.spline_poses(knots, None, t["ts_evt"], a.traj)
-        poses_rgb = eng.spline_poses(knots, transform, t["ts_rgb"], a.traj)
+        n_pe = 2                                                                       # get_pose_evt: window start / end (model/optimize.py:58-82)
+        poses = eng.spline_poses_pair(knots, transform, t["ts"], n_pe, a.traj)         # get_pose_evt + get_pose_rgb, one launch
+        poses_evt, poses_rgb = poses[:n_pe], poses[n_pe:]
         fine = len(self.nets) > 1
         # the event pose pair and the N blur poses (model/nerf.py:217,227) as two segments of ONE ray batch: every stage of the
         # render and of its backward pass runs once over all 2 R_e + P R_b rays
@@ -163,8 +167,7 @@ class Trainer:
         gc, gf = grad_tabs[0], grad_tabs[1] if fine else None
         eng.render_backward_multi(segs, saved, d_fine, d_coarse if fine else None, gc, gf, [d_pe, d_pr])
         gk, gt = g.evt_knot_pose_se3.params.weight.grad, g.transform.params.weight.grad.reshape(6)
-        eng.spline_poses_backward(knots, transform, t["ts_rgb"], d_pr, a.traj, d_knots=gk, d_transform=gt)
-        eng.spline_poses_backward(knots, None, t["ts_evt"], d_pe, a.traj, d_knots=gk)
+        eng.spline_poses_pair_backward(knots, transform, t["ts"], n_pe, d_poses, gk, gt, a.traj)
         mark("backward")
         self.flat.all_reduce_sum()                                       # the single exchange of the step
         mark("all_reduce")

@@ -129,6 +129,10 @@ const char* bnrf_last_error(const bnrf_ctx* ctx);   /* ctx may be NULL: last cre
  * Call after every optimiser step.  Replaces the nn.Linear reads of model/nerf.py:93-112. */
 int bnrf_set_weights(bnrf_ctx* ctx, int net, const float* const* weights /*[12] device*/,
                      const float* const* biases /*[12] device*/, void* stream);
+/* bnrf_set_weights for both networks of a Graph at once (what a training loop does after every optimiser step): the repack runs
+ * as 4 launches over both networks instead of 6 per network. */
+int bnrf_set_weights_pair(bnrf_ctx* ctx, const float* const* w_coarse, const float* const* b_coarse, const float* const* w_fine,
+                          const float* const* b_fine, void* stream);
 
 /* Override the coarse sampling grid t_vals (host float[S], S == cfg.n_samples).  Default is
  * torch.linspace(0, 1, S) as the reference's CUDA device evaluates it (model/nerf.py:297); the
@@ -144,6 +148,13 @@ int bnrf_set_sample_grid(bnrf_ctx* ctx, const float* t_vals_host, int S, void* s
  * traj 0 = cubic B-spline, 1 = linear between knots 0 and 3; poses_out device [P,3,4]. */
 int bnrf_spline_poses(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts,
                       int P, int traj, float* poses_out, void* stream);
+/* get_pose_evt and get_pose_rgb of one iteration (model/nerf.py:208,211) in one launch: poses [0, n_plain) interpolate the knots as
+ * they are (event camera, model/optimize.py:58-82), poses [n_plain, P) the knots + transform (RGB camera, :84-111).  The backward
+ * call ADDS into d_knots [4,6] and d_transform [6] (the latter from the poses >= n_plain only). */
+int bnrf_spline_poses_pair(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts, int P, int n_plain, int traj,
+                           float* poses_out, void* stream);
+int bnrf_spline_poses_pair_backward(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts, int P, int n_plain,
+                                    int traj, const float* d_poses, float* d_knots, float* d_transform, void* stream);
 
 /* -------------------------------------------------------------------------------------- */
 /* a3-a10: Graph.render -- model/nerf.py:236-343                                            */
