@@ -481,7 +481,7 @@ int launch_mlp_tc(bnrf_ctx* ctx, int net, const float* o, const float* d, const 
 // Uses the same swizzle, descriptor, MMA and TMEM-load helpers as the MLP kernel so that the
 // layout conventions can be validated in isolation (tests/test_gpu_probe.py).
 __global__ void __launch_bounds__(128, 1)
-umma_probe_kernel(const __half* __restrict__ A, const __half* __restrict__ B, int N, uint32_t lbo_field, float* __restrict__ D) {
+umma_probe_kernel(const __half* __restrict__ A, const __half* __restrict__ B, int N, uint32_t lbo_field, uint32_t fmt_bits, float* __restrict__ D) {
     using namespace tc;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -502,7 +502,7 @@ umma_probe_kernel(const __half* __restrict__ A, const __half* __restrict__ B, in
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     if (threadIdx.x == 0) {
-        const uint32_t idesc = make_idesc(128, N);
+        const uint32_t idesc = make_idesc(128, N) | fmt_bits;      // fmt_bits: bit 7 = A is bf16, bit 10 = B is bf16
         for (int kk = 0; kk < 4; ++kk)
             tc_mma_f16(tmem, make_desc(base + kk * 32, lbo_field), make_desc(base + KBLOCK_BYTES + kk * 32, lbo_field), idesc, kk > 0);
         tc_commit(smem_u32(&done_bar));
@@ -530,6 +530,16 @@ extern "C" int bnrf_debug_umma_probe(const void* A_half, const void* B_half, int
     if (!A_half || !B_half || !D || N < 16 || N > 256 || N % 16) return BNRF_ERR_ARG;
     const size_t smem = tc::KBLOCK_BYTES + 32768 + 1024;
     if (cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return BNRF_ERR_CUDA;
-    umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __half*)A_half, (const __half*)B_half, N, (uint32_t)lbo_field, D);
+    umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __half*)A_half, (const __half*)B_half, N, (uint32_t)lbo_field, 0u, D);
+    return cudaGetLastError() == cudaSuccess ? BNRF_OK : BNRF_ERR_CUDA;
+}
+
+extern "C" int bnrf_debug_umma_probe_fmt(const void* A16, const void* B16, int N, int a_bf16, int b_bf16, float* D, void* stream) {
+    using namespace bnrf;
+    if (!A16 || !B16 || !D || N < 16 || N > 256 || N % 16) return BNRF_ERR_ARG;
+    const size_t smem = tc::KBLOCK_BYTES + 32768 + 1024;
+    if (cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return BNRF_ERR_CUDA;
+    const uint32_t fmt = (a_bf16 ? 1u << 7 : 0u) | (b_bf16 ? 1u << 10 : 0u);
+    umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __half*)A16, (const __half*)B16, N, 0u, fmt, D);
     return cudaGetLastError() == cudaSuccess ? BNRF_OK : BNRF_ERR_CUDA;
 }

@@ -401,27 +401,22 @@ mlp_tc3_kernel(const __grid_constant__ Schedule sched, TcParams p, const float* 
                                 // AFTER the hand-off (the next layer's MMAs may already run on this chunk): the same 32 activations as
                                 // bf16 hi / lo + ReLU mask bits into the staging slot of their 64-column block, in the tile-matrix layout
                                 // (bwd_tiles.cuh); slot kb of layer t is block number sg + kb
+                                // (the empty asm keeps the compiler from starting the conversions below before the hand-off and carrying
+                                // their results across it in spilled registers)
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) { asm volatile("" : "+f"(v[j])); }
                                 const int kb = kh >> 1;
                                 const uint32_t blk = sg + (uint32_t)kb, slot = blk % NSLOT;
                                 timed_wait(bar(L::BAR_ST_EMPTY + slot), ((blk / NSLOT) & 1u) ^ 1u, 10, w_st);
                                 unsigned char* s0 = sm + L::OFF_ST + slot * SLOT_BYTES;
 #pragma unroll
                                 for (int c8 = 0; c8 < 4; ++c8) {
-                                    // rebuilt from the packed fp16 hi + lo (the value to 2^-22) rather than kept live across the hand-off:
-                                    // 32 more registers would spill, and a spill is an L2 round trip (the shared-memory carve-out leaves no L1)
-                                    float w8[8];
                                     uint32_t bits = 0;
 #pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&va[4 * c8 + e]));
-                                        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&vb[4 * c8 + e]));
-                                        w8[2 * e] = a.x + c.x; w8[2 * e + 1] = a.y + c.y;
-                                        bits |= ((va[4 * c8 + e] & 0x0000ffffu) ? 1u : 0u) << (2 * e);         // post-ReLU: h > 0 <=> hi half != 0
-                                        bits |= ((va[4 * c8 + e] & 0xffff0000u) ? 1u : 0u) << (2 * e + 1);
-                                    }
+                                    for (int e = 0; e < 8; ++e) bits |= (v[8 * c8 + e] > 0.0f ? 1u : 0u) << e;
                                     const uint32_t off = sw128_offset(r, (kh & 1) * 32 + c8 * 8);
                                     uint4 hi, lo;
-                                    bwt::split8_bf16_pub(w8, hi, lo);
+                                    bwt::split8_bf16_pub(v + 8 * c8, hi, lo);
                                     *reinterpret_cast<uint4*>(s0 + off) = hi;
                                     *reinterpret_cast<uint4*>(s0 + KBLOCK_BYTES + off) = lo;
                                     s0[2 * KBLOCK_BYTES + (off >> 4)] = (unsigned char)bits;

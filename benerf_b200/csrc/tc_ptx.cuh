@@ -241,6 +241,9 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
                  : "memory");
 }
+// Register rebalancing between warp roles: every warp of an aligned group of four must execute the same instruction.
+template <uint32_t N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <uint32_t N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem desc]; A: lane = row, one 32-bit column = two consecutive K elements (K = 16 -> 8 columns)
 __device__ __forceinline__ void tc_mma_pair_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {

@@ -375,6 +375,9 @@ int bnrf_profile_read(bnrf_ctx* ctx, double* mlp_ms, int64_t* mlp_timed, double*
  * swizzle, UMMA descriptors, tcgen05.mma and tcgen05.ld helpers as the MLP kernel.  A, B device
  * fp16 row-major; D device fp32 [128,N]; lbo_field = raw 14-bit leading-byte-offset field. */
 int bnrf_debug_umma_probe(const void* A_half, const void* B_half, int N, int lbo_field, float* D, void* stream);
+/* Same with the element formats of the instruction descriptor chosen per operand (a_bf16 / b_bf16: 0 = fp16, 1 = bf16):
+ * the weight-gradient kernel multiplies fp16 activation tiles with bf16 gradient tiles in one kind::f16 MMA. */
+int bnrf_debug_umma_probe_fmt(const void* A16, const void* B16, int N, int a_bf16, int b_bf16, float* D, void* stream);
 
 /* Bring-up probe (tests only) of the ".ts" MMA form on a CTA pair: D[256,N] = A[256,64] * B[N,64]^T with the A operand in
  * tensor memory (written with tcgen05.st at column a_col, lane = row, one 32-bit column = two consecutive K elements) and

@@ -23,6 +23,24 @@ def test_umma_probe_matches_integer_gemm(N):
     assert torch.equal(D, want), f"max abs diff {(D - want).abs().max().item()}"
 
 
+@pytest.mark.parametrize("a_bf16, b_bf16", [(0, 1), (1, 0), (1, 1)])
+def test_umma_probe_mixed_operand_formats(a_bf16, b_bf16):
+    """kind::f16 takes the A and B element formats independently: fp16 activations x bf16 gradients in one MMA (wgrad_pair.cu).
+    Values are chosen so that reading an operand in the wrong format gives a different product."""
+    from benerf_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(7 + a_bf16 * 2 + b_bf16)
+    A = (torch.randint(-8, 9, (128, 64), generator=g).float() * 0.375).to(torch.bfloat16 if a_bf16 else torch.float16).cuda()
+    B = (torch.randint(-8, 9, (128, 64), generator=g).float() * 1.25).to(torch.bfloat16 if b_bf16 else torch.float16).cuda()
+    D = torch.full((128, 128), float("nan"), device="cuda")
+    rc = lib.bnrf_debug_umma_probe_fmt(C.c_void_p(A.data_ptr()), C.c_void_p(B.data_ptr()), 128, a_bf16, b_bf16,
+                                       C.c_void_p(D.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    want = A.float() @ B.float().t()
+    assert torch.equal(D, want), f"max abs diff {(D - want).abs().max().item()}"
+
+
 @pytest.mark.parametrize("N,a_col", [(256, 256), (128, 128), (128, 480), (256, 288)])
 def test_umma_ts_probe_a_operand_in_tensor_memory(N, a_col):
     """tcgen05.mma cta_group::2 with A read from TMEM (tcgen05.st: lane = row, 32-bit column = 2 consecutive K elements)
