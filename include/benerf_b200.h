@@ -376,7 +376,8 @@ int bnrf_profile_read(bnrf_ctx* ctx, double* mlp_ms, int64_t* mlp_timed, double*
  * fp16 row-major; D device fp32 [128,N]; lbo_field = raw 14-bit leading-byte-offset field. */
 int bnrf_debug_umma_probe(const void* A_half, const void* B_half, int N, int lbo_field, float* D, void* stream);
 /* Same with the element formats of the instruction descriptor chosen per operand (a_bf16 / b_bf16: 0 = fp16, 1 = bf16):
- * the weight-gradient kernel multiplies fp16 activation tiles with bf16 gradient tiles in one kind::f16 MMA. */
+ * only equal formats multiply correctly on B200, which is why the forward pass re-splits its activations as bf16 for the
+ * weight-gradient kernel (tests/test_gpu_probe.py). */
 int bnrf_debug_umma_probe_fmt(const void* A16, const void* B16, int N, int a_bf16, int b_bf16, float* D, void* stream);
 
 /* Bring-up probe (tests only) of the ".ts" MMA form on a CTA pair: D[256,N] = A[256,64] * B[N,64]^T with the A operand in
