@@ -294,14 +294,32 @@ def bench_image_formation_stress(dev, steps=5, warmup=3):
         ms = timed(lambda: IF.event_logdiff(ev_in, B, "BeNeRF_Unreal"))
         nbytes = 4 * R * (3 * (B + 1) + B)
         out["event_logdiff"] = {"ms": ms, "bytes": nbytes, "achieved_gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / hbm_peak}
-        E = 10_000_000
+        # event scatter: E = 1e7 time-sorted events into 256 bins x [1080, 1920] float64 (4.2 GB of images) in ONE launch.  The
+        # 120 MB of one event set would stay in the 126 MB L2 across repeats, so every pass reads a different one of SETS sets
+        # (480 MB): the input side comes from HBM, and so do the read-modify-writes into the bin images.
+        E, SETS = 10_000_000, 4
         g = torch.Generator(device=dev).manual_seed(0)
-        x = torch.randint(0, 1920, (E,), device=dev, generator=g, dtype=torch.int32)
-        y = torch.randint(0, 1080, (E,), device=dev, generator=g, dtype=torch.int32)
-        pol = (torch.randint(0, 2, (E,), device=dev, generator=g) * 2 - 1).float()
-        img = torch.zeros(1080, 1920, device=dev, dtype=torch.float64)
-        ms = timed(lambda: IF.accumulate_events(x, y, pol, 1080, 1920, out=img))
-        out["event_scatter"] = {"ms": ms, "events": E, "events_per_s": E / ms * 1e3, "read_gbs": 12 * E / ms / 1e6}
+        sets = []
+        for _ in range(SETS):
+            sets.append((torch.randint(0, 1920, (E,), device=dev, generator=g, dtype=torch.int32),
+                         torch.randint(0, 1080, (E,), device=dev, generator=g, dtype=torch.int32),
+                         (torch.randint(0, 2, (E,), device=dev, generator=g) * 2 - 1).float()))
+        bounds = torch.linspace(0, E, B + 1, device=dev).round().to(torch.int64)
+        img = torch.zeros(B, 1080, 1920, device=dev, dtype=torch.float64)
+        turn = [0]
+
+        def scatter():
+            x, y, pol = sets[turn[0] % SETS]
+            turn[0] += 1
+            IF.accumulate_events_binned(x, y, pol, bounds, 1080, 1920, out=img)
+
+        ms = timed(scatter)
+        total = float(img.sum())                                  # every pass adds sum(pol) of its set: a checksum of all passes
+        want = sum(float(sets[i % SETS][2].sum()) for i in range(turn[0]))
+        out["event_scatter"] = {"ms": ms, "events": E, "bins": B, "events_per_s": E / ms * 1e3, "input_read_gbs": 12 * E / ms / 1e6,
+                                "atomic_sector_gbs": 2 * 32 * E / ms / 1e6, "input_sets": SETS, "checksum_ok": total == want,
+                                "note": "inputs rotate over 4 sets (480 MB > L2); one 32 B sector read + written per event"}
+        del img, sets
     out["peak_gbs"], out["peak_source"] = hbm_peak, src
     out["workload"] = "1920x1080, 51 blur poses, 257 frames -> 256 event bins, 1e7 events (BASELINE.json configs[4], per GPU)"
     del frames

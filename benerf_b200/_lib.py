@@ -89,6 +89,7 @@ PROTOTYPES = {
     "bnrf_blur_mean_backward": (_I, [_P, _I, _L, _I, _P, _P]),
     "bnrf_event_logdiff_backward": (_I, [_P, _P, _I, _L, _I, _I, _P, _P]),
     "bnrf_accumulate_events": (_I, [_P, _P, _P, _L, _I, _I, _P, _P]),
+    "bnrf_accumulate_events_binned": (_I, [_P, _P, _P, _L, _P, _I, _I, _I, _P, _P]),
     "bnrf_training_loss_workspace_bytes": (_Z, [_L]),
     "bnrf_training_loss": (_I, [C.POINTER(LossCfg), _P, _P, _P, _P, _L, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P]),
     "bnrf_training_loss_finish": (_I, [C.POINTER(LossCfg), _P, _P, _P, _P, _L, _L, _P, _P, _P, _P, _P]),

@@ -142,6 +142,27 @@ __global__ void accumulate_events_kernel(const int32_t* __restrict__ x, const in
     }
 }
 
+// The same for `bins` consecutive windows of one time-sorted event array: window b = events [bounds[b], bounds[b + 1]) goes to
+// image b.  One launch; each thread finds the window of its event by binary search over the (shared-memory) boundaries.
+__global__ void accumulate_events_binned_kernel(const int32_t* __restrict__ x, const int32_t* __restrict__ y, const float* __restrict__ pol,
+                                                const int64_t* __restrict__ bounds, int bins, int H, int W, double* __restrict__ out) {
+    extern __shared__ int64_t s_bounds[];
+    for (int i = threadIdx.x; i <= bins; i += blockDim.x) s_bounds[i] = bounds[i];
+    __syncthreads();
+    const int64_t first = s_bounds[0], last = s_bounds[bins];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t image = (int64_t)H * W;
+    for (int64_t e = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < last; e += stride) {
+        int lo = 0, hi = bins;                         // largest b with s_bounds[b] <= e (empty windows are skipped by the search)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_bounds[mid] <= e) lo = mid; else hi = mid;
+        }
+        const int xi = x[e], yi = y[e];
+        if (xi >= 0 && xi < W && yi >= 0 && yi < H) atomicAdd(out + (int64_t)lo * image + (int64_t)yi * W + xi, (double)pol[e]);
+    }
+}
+
 static inline unsigned stream_grid(int64_t work, int threads) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -192,5 +213,14 @@ extern "C" int bnrf_accumulate_events(const int32_t* x, const int32_t* y, const 
     if (E == 0) return BNRF_OK;
     if (!x || !y || !pol || !out || E < 0 || H <= 0 || W <= 0) return BNRF_ERR_ARG;
     accumulate_events_kernel<<<stream_grid(E, 256), 256, 0, (cudaStream_t)stream>>>(x, y, pol, E, H, W, out);
+    return cudaGetLastError() == cudaSuccess ? BNRF_OK : BNRF_ERR_CUDA;
+}
+
+extern "C" int bnrf_accumulate_events_binned(const int32_t* x, const int32_t* y, const float* pol, int64_t E, const int64_t* bounds,
+                                             int bins, int H, int W, double* out, void* stream) {
+    if (bins == 0 || E == 0) return BNRF_OK;
+    if (!x || !y || !pol || !bounds || !out || E < 0 || bins < 0 || bins > 4096 || H <= 0 || W <= 0) return BNRF_ERR_ARG;
+    accumulate_events_binned_kernel<<<stream_grid(E, 256), 256, (size_t)(bins + 1) * sizeof(int64_t), (cudaStream_t)stream>>>(
+        x, y, pol, bounds, bins, H, W, out);
     return cudaGetLastError() == cudaSuccess ? BNRF_OK : BNRF_ERR_CUDA;
 }

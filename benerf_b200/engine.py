@@ -513,3 +513,24 @@ def accumulate_events(x, y, pol, H, W, out=None):
     _rc(lib.bnrf_accumulate_events(_ptr(x, torch.int32, name="x"), _ptr(y, torch.int32, name="y"), _ptr(pol, name="pol"),
                                    x.numel(), int(H), int(W), _ptr(out, torch.float64), _stream()), "bnrf_accumulate_events")
     return out
+
+
+def accumulate_events_binned(x, y, pol, bounds, H, W, out=None):
+    """`len(bounds) - 1` consecutive windows of a time-sorted event array in one launch: events [bounds[b], bounds[b+1]) ->
+    float64 image b of out [bins, H, W] (each window as utils/event_utils.py:247-259; the bins of get_pose_evt(..., seg_num),
+    model/optimize.py:58-71).  bounds: int64, non-decreasing, within [0, len(x)] (e.g. torch.searchsorted(ts, bin_edges))."""
+    lib = _lib.load()
+    bounds = torch.as_tensor(bounds).to(device=x.device, dtype=torch.int64).contiguous()
+    bins = bounds.numel() - 1
+    if bins < 0:
+        raise ValueError("bounds needs at least one entry")
+    if bins > 0 and (bool((bounds[1:] < bounds[:-1]).any()) or int(bounds[0]) < 0 or int(bounds[-1]) > x.numel()):
+        raise ValueError("bounds must be non-decreasing and within [0, number of events]")
+    if out is None:
+        out = torch.zeros(bins, H, W, device=x.device, dtype=torch.float64)
+    elif tuple(out.shape) != (bins, int(H), int(W)):
+        raise ValueError(f"out must have shape ({bins}, {H}, {W})")
+    _rc(lib.bnrf_accumulate_events_binned(_ptr(x, torch.int32, name="x"), _ptr(y, torch.int32, name="y"), _ptr(pol, name="pol"),
+                                          x.numel(), _ptr(bounds, torch.int64, name="bounds"), bins, int(H), int(W),
+                                          _ptr(out, torch.float64), _stream()), "bnrf_accumulate_events_binned")
+    return out

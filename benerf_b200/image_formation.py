@@ -6,7 +6,7 @@ rendered tensors -- is bnrf_training_loss (csrc/loss.cu), one launch (two for th
 """
 import torch
 
-from .engine import (blur_mean, event_logdiff, accumulate_events, LOG_MODE, loss_cfg, training_loss_fused)  # noqa: F401
+from .engine import (blur_mean, event_logdiff, accumulate_events, accumulate_events_binned, LOG_MODE, loss_cfg, training_loss_fused)  # noqa: F401
 
 PART_KEYS = ("event_rgb_map", "event_rgb0", "blur_rgb_map", "blur_rgb0")
 

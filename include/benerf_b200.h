@@ -273,6 +273,12 @@ int bnrf_event_logdiff_backward(const float* rgb /*device [B+1,R,C]*/, const flo
  * x, y device int32 [E]; pol device float [E]; out device double [H,W], NOT cleared here. */
 int bnrf_accumulate_events(const int32_t* x, const int32_t* y, const float* pol, int64_t E,
                            int H, int W, double* out, void* stream);
+/* The same for `bins` consecutive windows of one time-sorted event array in one launch (the 256 event bins of
+ * get_pose_evt(..., seg_num = 257), model/optimize.py:58-71, each accumulated as utils/event_utils.py:247-259 would):
+ * window b = events [bounds[b], bounds[b+1]) is added to image b.  bounds device int64 [bins+1], non-decreasing, within
+ * [0, E]; out device double [bins,H,W], NOT cleared here.  bins <= 4096. */
+int bnrf_accumulate_events_binned(const int32_t* x, const int32_t* y, const float* pol, int64_t E, const int64_t* bounds,
+                                  int bins, int H, int W, double* out, void* stream);
 
 /* -------------------------------------------------------------------------------------- */
 /* a14, a15: the loss block of one iteration, forward + gradients w.r.t. the rendered tensors -- train.py:163-177 (event pair,
@@ -376,8 +382,8 @@ int bnrf_profile_read(bnrf_ctx* ctx, double* mlp_ms, int64_t* mlp_timed, double*
  * fp16 row-major; D device fp32 [128,N]; lbo_field = raw 14-bit leading-byte-offset field. */
 int bnrf_debug_umma_probe(const void* A_half, const void* B_half, int N, int lbo_field, float* D, void* stream);
 /* Same with the element formats of the instruction descriptor chosen per operand (a_bf16 / b_bf16: 0 = fp16, 1 = bf16):
- * only equal formats multiply correctly on B200, which is why the forward pass re-splits its activations as bf16 for the
- * weight-gradient kernel (tests/test_gpu_probe.py). */
+ * only equal formats are executable on B200 (a mixed pair ends the launch with "illegal instruction" and poisons the CUDA
+ * context), which is why the forward pass re-splits its activations as bf16 for the weight-gradient kernel. */
 int bnrf_debug_umma_probe_fmt(const void* A16, const void* B16, int N, int a_bf16, int b_bf16, float* D, void* stream);
 
 /* Bring-up probe (tests only) of the ".ts" MMA form on a CTA pair: D[256,N] = A[256,64] * B[N,64]^T with the A operand in

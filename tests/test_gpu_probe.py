@@ -23,14 +23,13 @@ def test_umma_probe_matches_integer_gemm(N):
     assert torch.equal(D, want), f"max abs diff {(D - want).abs().max().item()}"
 
 
-_MIXED = pytest.mark.xfail(strict=False, reason="measured on B200: kind::f16 with different A / B element formats gives wrong products")
-
-
-@pytest.mark.parametrize("a_bf16, b_bf16", [pytest.param(0, 1, marks=_MIXED), pytest.param(1, 0, marks=_MIXED), (1, 1)])
+@pytest.mark.parametrize("a_bf16, b_bf16", [(1, 1)])
 def test_umma_probe_operand_formats(a_bf16, b_bf16):
-    """bf16 x bf16 (the backward kernels) through the same helpers; and the reason the forward pass cannot hand its packed fp16
-    activations to the weight-gradient kernel as they are: fp16 activations x bf16 gradients in one kind::f16 MMA do not multiply
-    correctly, although the instruction descriptor has one format field per operand (the mixed cases are expected failures).
+    """bf16 x bf16 (the backward kernels) through the same helpers as the fp16 probe.  The entry point takes one format per
+    operand because the instruction descriptor does; but fp16 x bf16 in one kind::f16 MMA is not executable on B200 -- the
+    launch ends with "an illegal instruction was encountered" and takes the CUDA context with it, so the mixed cases cannot
+    be kept here even as expected failures.  (That is why the forward pass re-splits its activations as bf16 for the
+    weight-gradient kernel instead of handing over its packed fp16 words.)
     Values are chosen so that reading an operand in the wrong format gives a different product."""
     from benerf_b200 import _lib
     lib = _lib.load()

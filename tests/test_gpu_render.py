@@ -4,6 +4,7 @@ The bound is north_star's: <= 1e-4 max-abs on rgb_map / rgb0 / sigma / acc and o
 event tensors, on identical rays with the four RNG draws injected.  Rays whose last-sample density
 sits on the relu kink (dists[-1] = 1e10, Q13) are counted and excluded, never silently tolerated.
 """
+import numpy as np
 import pytest
 import torch
 
@@ -184,6 +185,41 @@ def test_event_accumulation_matches_reference():
     assert got.dtype == torch.float64 and torch.equal(got.cpu(), gold["events_accu"])
     empty = E.accumulate_events(x[:0], y[:0], pol[:0], case.H, case.W)
     assert float(empty.abs().sum()) == 0.0
+
+
+def test_binned_event_accumulation_matches_per_window_oracle():
+    """bnrf_accumulate_events_binned: consecutive windows of a time-sorted event array in one launch; every window against the
+    oracle's accumulate (utils/event_utils.py:247-259) on its slice -- bit-exact (sums of +-1 in float64).  Covers empty
+    windows, a leading / trailing part outside all windows, and coordinates outside the image (dropped)."""
+    from benerf_b200 import engine as E
+    from oracle import events
+    H, W, n_ev, bins = 37, 53, 20_000, 9
+    rng = np.random.default_rng(5)
+    ts = np.sort(rng.uniform(0.0, 1.0, n_ev))
+    xs, ys = rng.integers(0, W, n_ev), rng.integers(0, H, n_ev)
+    pol = rng.integers(0, 2, n_ev) * 2.0 - 1.0
+    edges = np.array([0.05, 0.1, 0.1, 0.3, 0.31, 0.6, 0.6, 0.6, 0.9, 0.95])          # windows 1, 5, 6 are empty
+    bounds = np.searchsorted(ts, edges)
+    x = torch.from_numpy(xs.astype("int32")).to(DEV)
+    y = torch.from_numpy(ys.astype("int32")).to(DEV)
+    p = torch.from_numpy(pol.astype("float32")).to(DEV)
+    got = E.accumulate_events_binned(x, y, p, bounds, H, W)
+    assert got.shape == (bins, H, W) and got.dtype == torch.float64
+    for b in range(bins):
+        sl = slice(bounds[b], bounds[b + 1])
+        want = events.accumulate(H, W, xs[sl], ys[sl], pol[sl]) if bounds[b + 1] > bounds[b] else torch.zeros(H, W, dtype=torch.float64)
+        assert torch.equal(got[b].cpu(), want), b
+    assert float(got.sum()) == float(pol[bounds[0]:bounds[-1]].sum())
+    # one window == the single-window entry point; out-of-image coordinates are dropped, `out` is added to
+    one = E.accumulate_events_binned(x, y, p, [0, n_ev], H, W)
+    assert torch.equal(one[0], E.accumulate_events(x, y, p, H, W))
+    x_bad = x.clone(); x_bad[::7] = W; x_bad[1::7] = -1
+    keep = ((x_bad >= 0) & (x_bad < W)).cpu().numpy()
+    again = E.accumulate_events_binned(x_bad, y, p, [0, n_ev], H, W, out=one.clone())
+    assert torch.equal((again - one)[0].cpu(), events.accumulate(H, W, xs[keep], ys[keep], pol[keep]))
+    assert E.accumulate_events_binned(x, y, p, [3], H, W).shape == (0, H, W)
+    with pytest.raises(ValueError):
+        E.accumulate_events_binned(x, y, p, [5, 2], H, W)
 
 
 def test_image_formation_streaming_shapes():
