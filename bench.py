@@ -60,12 +60,13 @@ def peaks():
 
 def ncu_traffic(flop_per_launch):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r01_mlp_tc2_ncu_bench.json, written by tools/ncu_key_metrics.py), scaled by algorithmic work to this run's
+    (profiles/r02_mlp_tc3_ncu_bench.json, written by tools/r02_profiles.py from tools/gpu_r02_final.sh), scaled by algorithmic work to this run's
     average launch (the kernel's traffic is proportional to its rows); None when no capture is committed."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_mlp_tc2_ncu_bench.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_mlp_tc3_ncu_bench.json")) as f:
             cap = json.load(f)
         return {"bytes_per_launch": cap["dram_bytes"] * flop_per_launch / cap["algorithmic_flop"],
+                "over_algorithmic_bytes": cap["dram_bytes"] / cap["algorithmic_bytes"],
                 "source": "ncu --set full, %s, scaled from a launch of %.3g algorithmic FLOP" % (cap["kernel"], cap["algorithmic_flop"])}
     except Exception:
         return None
@@ -414,8 +415,10 @@ def bench_train_step(opts, dev, world, rank, steps=5, warmup=3, config="e2nerf_s
             "mem_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 1),
             "optimizer_tail": "fused (bnrf_adam_step_sched)" if args.fused_optimizer else "torch.optim.Adam x3",
             "cuda_graph": trainer._cg is not None,
-            "backward": "tcgen05 dgrad chain on CTA pairs + one wgrad launch per network on bf16 hi/lo tile matrices (dgrad_chain2.cu, "
-                        "bwd_tiles.cu), 3 MMAs per product, fp32 accumulate"}
+            "backward": "fused loss + analytic render gradients (loss.cu), heads_fused_kernel, tcgen05 dgrad chain on CTA pairs with the last "
+                        "K-block issued in N-halves (dgrad_chain2.cu), weight gradients of the eight 256-wide layers + view layer on CTA "
+                        "pairs (wgrad_pair.cu) and of the two encoded-point blocks on single CTAs (bwd_tiles.cu); bf16 hi/lo tile matrices, "
+                        "3 MMAs per product, fp32 accumulate; whole step replayed as one CUDA graph"}
 
 
 # ----------------------------------------------------------------------------------------------
