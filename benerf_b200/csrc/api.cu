@@ -203,7 +203,7 @@ int pack_weights_pair(bnrf_ctx* ctx, const float* const* w0, const float* const*
 
 // Workspace carve-up for bnrf_render_forward (all regions 256-byte aligned).
 struct Workspace {
-    float *o, *d, *view, *vb, *z_c, *z_f, *raw, *w_c;
+    float *o, *d, *view, *vb, *vb_f, *z_c, *z_f, *raw, *w_c;
     size_t bytes;
 };
 static Workspace carve(const bnrf_cfg& c, int64_t n, void* base) {
@@ -217,6 +217,7 @@ static Workspace carve(const bnrf_cfg& c, int64_t n, void* base) {
     const int Sc = c.n_samples, Sf = c.n_samples + c.n_importance, Smax = Sf;
     w.o = take(n * 3); w.d = take(n * 3); w.view = take(n * 3);
     w.vb = take(n * kHalf);
+    w.vb_f = take(c.n_importance > 0 ? n * kHalf : 0);
     w.z_c = take(n * Sc);
     w.z_f = take(c.n_importance > 0 ? n * Sf : 0);
     w.raw = take(n * Smax * (c.channels + 1));
@@ -427,16 +428,8 @@ static int render_impl(bnrf_ctx* ctx, const bnrf_render_seg* segs, int n_segs, c
     const bool fine = c.n_importance > 0;
     const int Sc = c.n_samples, Sf = c.n_samples + c.n_importance;
     int rc;
-    {
-        int64_t off = 0;                    // segments are laid out one after the other, each pose-major
-        for (int i = 0; i < n_segs; ++i) {
-            const bnrf_render_seg& sg = segs[i];
-            if ((rc = launch_rays(ctx, sg.poses, sg.ray_idx, sg.P, sg.R, sg.H, sg.W, sg.K, sg.remap, w.o + 3 * off, w.d + 3 * off, w.view + 3 * off, st))) return rc;
-            off += (int64_t)sg.P * sg.R;
-        }
-    }
-    if ((rc = launch_stratified(ctx, r.t_rand, &r, n, Sc, w.z_c, st))) return rc;
-    if ((rc = launch_viewbias(ctx, 0, w.view, n, w.vb, st))) return rc;
+    // rays of all segments (laid out one after the other, each pose-major), view bias of both networks, stratified depths
+    if ((rc = launch_ray_setup(ctx, segs, n_segs, &r, Sc, w.o, w.d, w.view, w.vb, fine ? w.vb_f : nullptr, saved ? s.pe_dir : nullptr, w.z_c, st))) return rc;
     if ((rc = run_mlp(ctx, 0, w.o, w.d, w.vb, w.z_c, n, Sc, raw_c, saved ? &s.acts_c : nullptr, st))) return rc;
     // coarse composite: outputs go to rgb0/disp0/acc0 when a fine pass follows (model/nerf.py:319-343)
     float* sigma_c_out = saved ? sig_c : (fine ? nullptr : out->sigma);
@@ -454,8 +447,7 @@ static int render_impl(bnrf_ctx* ctx, const bnrf_render_seg* segs, int n_segs, c
         return rc;
     }
     if (out->z_vals) BNRF_CUDA(ctx, cudaMemcpyAsync(out->z_vals, w.z_f, (size_t)n * Sf * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if ((rc = launch_viewbias(ctx, 1, w.view, n, w.vb, st))) return rc;
-    if ((rc = run_mlp(ctx, 1, w.o, w.d, w.vb, w.z_f, n, Sf, raw_f, saved ? &s.acts_f : nullptr, st))) return rc;
+    if ((rc = run_mlp(ctx, 1, w.o, w.d, w.vb_f, w.z_f, n, Sf, raw_f, saved ? &s.acts_f : nullptr, st))) return rc;
     if ((rc = launch_composite(ctx, raw_f, w.z_f, w.d, r.noise_f, &r, kStreamNoiseF, n, Sf, out->rgb_map, out->disp_map,
                                out->acc_map, nullptr, out->depth_map, saved ? sig_f : out->sigma, st))) return rc;
     if (saved && out->sigma) BNRF_CUDA(ctx, cudaMemcpyAsync(out->sigma, sig_f, (size_t)n * Sf * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -233,11 +233,13 @@ __global__ void __launch_bounds__(256) heads_fused_kernel(const float* __restric
 
 // ------------------------------------------------------------------ views_linears.0: direction block and bias
 // dW[j][256 + i] += sum_rays dvb[ray][j] * enc[ray][i] (i < 27),  dB[j] += sum_rays dvb[ray][j]; blockIdx.x = i (27 = bias)
-__global__ void viewdir_wgrad_kernel(const float* __restrict__ dvb, const float* __restrict__ pe_dir /*[N,32]*/, int64_t n_rays,
-                                     int64_t rays_per_block, float* __restrict__ dW /*[128, 283]*/, float* __restrict__ dB) {
-    const int j = threadIdx.x, i = blockIdx.x;
-    const int64_t r0 = (int64_t)blockIdx.y * rays_per_block;
-    const int64_t r1 = (r0 + rays_per_block < n_rays) ? r0 + rays_per_block : n_rays;
+// (role of net_tail_kernel: 128 threads = the 128 outputs j)
+__device__ __forceinline__ void viewdir_wgrad_block(unsigned vblock, const float* __restrict__ dvb, const float* __restrict__ pe_dir /*[N,32]*/,
+                                                    int64_t n_rays, float* __restrict__ dW /*[128, 283]*/, float* __restrict__ dB) {
+    constexpr int64_t kRaysPerBlock = 128;
+    const int j = threadIdx.x, i = (int)(vblock % (kDirCh + 1));
+    const int64_t r0 = (int64_t)(vblock / (kDirCh + 1)) * kRaysPerBlock;
+    const int64_t r1 = (r0 + kRaysPerBlock < n_rays) ? r0 + kRaysPerBlock : n_rays;
     float acc = 0.f;
 #pragma unroll 4
     for (int64_t ray = r0; ray < r1; ++ray) acc = fmaf(dvb[ray * kHalf + j], i < kDirCh ? pe_dir[ray * 32 + i] : 1.0f, acc);
@@ -252,19 +254,20 @@ __global__ void viewdir_wgrad_kernel(const float* __restrict__ dvb, const float*
 //   dW_f[f][k]     += sum_j W_v[j][f] G[j][k]                     (blocks 128..383: f, thread k)
 //   dB_f[f]        += sum_j W_v[j][f] s[j]
 // wt8[k][f] = W_f[f][k], wt9[f][j] = W_v[j][f] (the k-major copies of the weight cache).
-__global__ void views_feature_wgrad_kernel(const float* __restrict__ G, const float* __restrict__ s, const float* __restrict__ wt8,
-                                           const float* __restrict__ wt9, const float* __restrict__ b_f,
-                                           float* __restrict__ dW_views /*[128, 283]*/, float* __restrict__ dW_f /*[256, 256]*/,
-                                           float* __restrict__ dB_f) {
-    const int t = threadIdx.x;
-    if (blockIdx.x < kHalf) {
-        const int j = blockIdx.x, f = t;
+__device__ __forceinline__ void views_feature_wgrad_block(unsigned vblock, const float* __restrict__ G, const float* __restrict__ s,
+                                                          const float* __restrict__ wt8, const float* __restrict__ wt9,
+                                                          const float* __restrict__ b_f, float* __restrict__ dW_views /*[128, 283]*/,
+                                                          float* __restrict__ dW_f /*[256, 256]*/, float* __restrict__ dB_f) {
+    const int t = (int)(vblock & 1u) * 128 + threadIdx.x;        // two 128-thread blocks per output row
+    vblock >>= 1;
+    if (vblock < kHalf) {
+        const int j = (int)vblock, f = t;
         float acc = s[j] * b_f[f];
 #pragma unroll 8
         for (int k = 0; k < kWidth; ++k) acc = fmaf(G[j * kWidth + k], wt8[(size_t)k * kWidth + f], acc);
         dW_views[(size_t)j * (kWidth + kDirCh) + f] += acc;
     } else {
-        const int f = blockIdx.x - kHalf, k = t;
+        const int f = (int)vblock - kHalf, k = t;
         float acc = 0.f, bs = 0.f;
 #pragma unroll 8
         for (int j = 0; j < kHalf; ++j) {
@@ -279,12 +282,8 @@ __global__ void views_feature_wgrad_kernel(const float* __restrict__ G, const fl
 
 // ------------------------------------------------------------------ view-direction branch
 // per ray: encoding of the unit view direction (27 values, padded to 32), d enc = dvb * W_dir^T, d view
-__global__ void viewdir_backward_kernel(const float* __restrict__ view, const float* __restrict__ dvb,
-                                        const float* __restrict__ w_dir /*[27][128]*/, const float* __restrict__ enc_scale /*[27] or NULL*/, int64_t n_rays,
-                                        float* __restrict__ pe_dir /*[N,32]*/, float* __restrict__ d_view /*[N,3] +=*/) {
-    const int lane = threadIdx.x % 32;
-    const int64_t ray = (int64_t)blockIdx.x * kWarps + threadIdx.x / 32;
-    if (ray >= n_rays) return;
+__device__ __forceinline__ void viewdir_backward_ray(int64_t ray, int lane, const float* __restrict__ view, const float* __restrict__ dvb,
+                                                     const float* __restrict__ w_dir /*[27][128]*/, float* __restrict__ d_view /*[N,3] +=*/) {
     const float v[3] = {view[ray * 3], view[ray * 3 + 1], view[ray * 3 + 2]};
     float enc[kDirCh];
 #pragma unroll
@@ -309,13 +308,6 @@ __global__ void viewdir_backward_kernel(const float* __restrict__ view, const fl
         for (int q = 0; q < 4; ++q) a = fmaf(g4[q], w_dir[i * kHalf + lane + 32 * q], a);
         denc[i] = wsumf(a);
     }
-    if (lane < 32) {
-        float e = 0.f;
-#pragma unroll
-        for (int i = 0; i < kDirCh; ++i) if (lane == i) e = enc[i];
-        if (enc_scale && lane < kDirCh) e *= enc_scale[lane];     // BARF c2f: the weight gradient sees the weighted encoding
-        pe_dir[ray * 32 + lane] = e;            // lanes 27..31 write the zero padding
-    }
     if (lane < 3) {
         float dv = 0.f;
 #pragma unroll
@@ -334,12 +326,8 @@ __global__ void viewdir_backward_kernel(const float* __restrict__ view, const fl
 
 // ------------------------------------------------------------------ point encoding + pts = o + d*z
 // per ray: d_o += sum_s d_pts, d_d += sum_s z * d_pts with d_pts from d_pe through the saved sin/cos
-__global__ void pe_ray_backward_kernel(const float* __restrict__ pe, const float* __restrict__ d_pe,
-                                       const float* __restrict__ z, int64_t n_rays, int S,
-                                       float* __restrict__ d_o, float* __restrict__ d_d) {
-    const int lane = threadIdx.x % 32;
-    const int64_t ray = (int64_t)blockIdx.x * kWarps + threadIdx.x / 32;
-    if (ray >= n_rays) return;
+__device__ __forceinline__ void pe_ray_backward_ray(int64_t ray, int lane, const float* __restrict__ pe, const float* __restrict__ d_pe,
+                                                    const float* __restrict__ z, int S, float* __restrict__ d_o, float* __restrict__ d_d) {
     float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};
     for (int s = lane; s < S; s += 32) {
         const int64_t row = ray * S + s;
@@ -371,21 +359,61 @@ __global__ void pe_ray_backward_kernel(const float* __restrict__ pe, const float
     }
 }
 
+// ------------------------------------------------------------------ what follows the tensor-core kernels of one network, in one launch
+// Four independent pieces of work, told apart by block index (128 threads each; the first needs ~140 registers, three blocks per SM):
+// the encoded-point gradients of a ray's samples summed into d o / d d (4 rays per block), the view-direction branch (4 rays per
+// block), the direction block of views_linears.0 with its bias, and feature_linear + the feature block of views_linears.0 from
+// the contraction G.
+struct NetTail {
+    const float* pe; const float* d_pe; const float* z; int S; float* g_o; float* g_d;          // A
+    const float* view; const float* dvb; const float* w_dir; float* g_v;                       // B
+    const float* pe_dir; float* dW_views; float* dB_views;                                     // C
+    const float* G; const float* s; const float* wt8; const float* wt9; const float* b_f; float* dW_f; float* dB_f;   // D
+    int64_t n;
+    unsigned nA, nB, nC;
+};
+__global__ void __launch_bounds__(128) net_tail_kernel(const __grid_constant__ NetTail a) {
+    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+    unsigned b = blockIdx.x;
+    if (b < a.nA) {
+        const int64_t ray = (int64_t)b * 4 + warp;
+        if (ray < a.n) pe_ray_backward_ray(ray, lane, a.pe, a.d_pe, a.z, a.S, a.g_o, a.g_d);
+        return;
+    }
+    b -= a.nA;
+    if (b < a.nB) {
+        const int64_t ray = (int64_t)b * 4 + warp;
+        if (ray < a.n) viewdir_backward_ray(ray, lane, a.view, a.dvb, a.w_dir, a.g_v);
+        return;
+    }
+    b -= a.nB;
+    if (b < a.nC) { viewdir_wgrad_block(b, a.dvb, a.pe_dir, a.n, a.dW_views, a.dB_views); return; }
+    views_feature_wgrad_block(b - a.nC, a.G, a.s, a.wt8, a.wt9, a.b_f, a.dW_views, a.dW_f, a.dB_f);
+}
+
 // ------------------------------------------------------------------ rays: ndc, viewdirs, R*dir, origin -> d poses
-__global__ void rays_backward_kernel(const float* __restrict__ poses, const int64_t* __restrict__ ray_idx, int P, int R,
-                                     int H, int W, float fx, float fy, float cx, float cy, const float* __restrict__ remap,
-                                     int ndc, const float* __restrict__ g_o_in, const float* __restrict__ g_d_in,
-                                     const float* __restrict__ g_v_in, const float* __restrict__ g_dn_in,
-                                     float* __restrict__ d_poses /*[P,12] +=*/) {
+struct RaysBwdSeg { const float* poses; const int64_t* ray_idx; const float* remap; float* d_poses; int R, H, W; float fx, fy, cx, cy; int64_t off; };
+struct RaysBwd { RaysBwdSeg seg[4]; int n_segs, ndc; int64_t n; const float *g_o, *g_d, *g_v, *g_dn; };
+__global__ void rays_backward_kernel(const __grid_constant__ RaysBwd a) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = n < (int64_t)P * R;
-    int p = 0;
+    const bool live = n < a.n;
+    float* dst = nullptr;                       // this ray's pose gradient, [12] +=
     float gp[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) gp[i] = 0.f;
     if (live) {
-        p = (int)(n / R);
-        const int64_t pix = ray_idx[n % R];
+        int si = 0;
+#pragma unroll
+        for (int i = 1; i < 4; ++i) if (i < a.n_segs && n >= a.seg[i].off) si = i;
+        const RaysBwdSeg& sg = a.seg[si];
+        const float* poses = sg.poses; const float* remap = sg.remap;
+        const int R = sg.R, H = sg.H, W = sg.W, ndc = a.ndc;
+        const float fx = sg.fx, fy = sg.fy, cx = sg.cx, cy = sg.cy;
+        const float *g_o_in = a.g_o, *g_d_in = a.g_d, *g_v_in = a.g_v, *g_dn_in = a.g_dn;
+        const int64_t nl = n - sg.off;
+        const int p = (int)(nl / R);
+        dst = sg.d_poses + (size_t)p * 12;
+        const int64_t pix = sg.ray_idx[nl % R];
         float fi = (float)(pix % W), fj = (float)(pix / W);
         if (remap) { fi = remap[2 * pix]; fj = remap[2 * pix + 1]; }
         const float* c2w = poses + (size_t)p * 12;
@@ -445,19 +473,20 @@ __global__ void rays_backward_kernel(const float* __restrict__ poses, const int6
             gp[r * 4 + 3] = go[r];
         }
     }
-    // warp-level reduction when the whole warp works on one pose (the common case in pose-major order)
-    const int p0 = __shfl_sync(0xffffffffu, p, 0);
-    const bool uniform = __all_sync(0xffffffffu, !live || p == p0);
+    // warp-level reduction when the whole warp works on one pose (the common case in pose-major order); lane 0 is live whenever
+    // any lane is
+    float* dst0 = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst), 0));
+    const bool uniform = __all_sync(0xffffffffu, !live || dst == dst0);
     const bool any_live = __any_sync(0xffffffffu, live);
     if (uniform) {
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
             const float s = wsumf(gp[i]);
-            if ((threadIdx.x % 32) == 0 && any_live) atomicAdd(d_poses + (size_t)p0 * 12 + i, s);
+            if ((threadIdx.x % 32) == 0 && any_live) atomicAdd(dst0 + i, s);
         }
     } else if (live) {
 #pragma unroll
-        for (int i = 0; i < 12; ++i) atomicAdd(d_poses + (size_t)p * 12 + i, gp[i]);
+        for (int i = 0; i < 12; ++i) atomicAdd(dst + i, gp[i]);
     }
 }
 
@@ -603,10 +632,7 @@ static int mlp_backward(bnrf_ctx* ctx, int net, int64_t n, int S, const ActPtrs&
         j->wrow = w.d_raw + C; j->wrow_stride = C + 1; j->dWv = dW[BNRF_L_ALPHA]; j->dBv = dB[BNRF_L_ALPHA];
     }
     if ((rc = bwt::launch_tile_wgrad(ctx, p, st))) return rc;
-    views_feature_wgrad_kernel<<<kHalf + kWidth, kWidth, 0, st>>>(w.g_views, w.s_views, np.wt[8], np.wt[9], np.bias[8], dW[BNRF_L_VIEWS],
-                                                                  dW[BNRF_L_FEATURE], dB[BNRF_L_FEATURE]);
-    BNRF_LAUNCH_CHECK(ctx);
-    return BNRF_OK;
+    return BNRF_OK;        // net_tail_kernel (render_backward_impl) turns g_views / s_views into the feature_linear / views_linears.0 gradients
 }
 
 // ------------------------------------------------------------------ saved-tensor and workspace carve-ups
@@ -631,7 +657,7 @@ SavedLayout carve_saved(const bnrf_cfg& c, int64_t n, void* base) {
         a.mask_bits = reinterpret_cast<unsigned char*>(take_bytes(8 * (size_t)a.t_alloc * 4096));
         return a;
     };
-    s.o = take(n * 3); s.d = take(n * 3); s.view = take(n * 3);
+    s.o = take(n * 3); s.d = take(n * 3); s.view = take(n * 3); s.pe_dir = take(n * 32);
     s.z_c = take(n * Sc); s.raw_c = take(n * Sc * (c.channels + 1)); s.sig_c = take(n * Sc);
     s.acts_c = acts(n * Sc);
     s.z_f = take(fine ? n * Sf : 0); s.raw_f = take(fine ? n * Sf * (c.channels + 1) : 0); s.sig_f = take(fine ? n * Sf : 0);
@@ -657,7 +683,7 @@ static BwdWorkspace carve_bwd(const bnrf_cfg& c, int64_t n, void* base) {
     w.b.g_views = take(kHalf * kWidth + kHalf); w.b.s_views = w.b.g_views + kHalf * kWidth;
     w.b.dz9_tiles = reinterpret_cast<unsigned char*>(take_bytes((size_t)w.b.tiles * bwt::tile_bytes(kHalf)));
     w.b.d_pe = take(rows * kPtsChPad); w.b.dz9 = nullptr;
-    w.b.dvb = take(n * kHalf); w.b.pe_dir = take(n * 32);
+    w.b.dvb = take(n * kHalf); w.b.pe_dir = nullptr;          // the encoded view directions come with the saved tensors
     w.g_o = take(n * 3); w.g_d = take(n * 3); w.g_v = take(n * 3); w.g_dn = take(n);
     w.bytes = off;
     return w;
@@ -702,10 +728,8 @@ static int render_backward_impl(bnrf_ctx* ctx, const bnrf_render_seg* segs, int 
     const float* g_fine = fine ? d_rgb_map : nullptr;
     const float* g_coarse = fine ? d_rgb0 : d_rgb_map;
     if ((g_fine && !grads_fine) || (g_coarse && !grads_coarse)) return fail(ctx, BNRF_ERR_ARG, "render_backward: gradient tables missing");
-    BNRF_CUDA(ctx, cudaMemsetAsync(w.g_o, 0, (size_t)n * 3 * sizeof(float), st));
-    BNRF_CUDA(ctx, cudaMemsetAsync(w.g_d, 0, (size_t)n * 3 * sizeof(float), st));
-    BNRF_CUDA(ctx, cudaMemsetAsync(w.g_v, 0, (size_t)n * 3 * sizeof(float), st));
-    BNRF_CUDA(ctx, cudaMemsetAsync(w.g_dn, 0, (size_t)n * sizeof(float), st));
+    // the four per-ray gradient accumulators are carved one after the other (carve_bwd): one memset node
+    BNRF_CUDA(ctx, cudaMemsetAsync(w.g_o, 0, (size_t)(reinterpret_cast<char*>(w.g_dn + n) - reinterpret_cast<char*>(w.g_o)), st));
     int rc;
     for (int net = 1; net >= 0; --net) {
         const float* g = net ? g_fine : g_coarse;
@@ -719,30 +743,30 @@ static int render_backward_impl(bnrf_ctx* ctx, const bnrf_render_seg* segs, int 
         else composite_backward_kernel<1><<<grid, 32 * kWarps, 0, st>>>(raw, z, sig, s.d, g, n, S, w.b.d_raw, w.g_dn);
         BNRF_LAUNCH_CHECK(ctx);
         if ((rc = mlp_backward(ctx, net, n, S, acts, w.b, pg->weights, pg->biases, st))) return rc;
-        // view-direction block of views_linears.0 and d viewdirs
-        viewdir_backward_kernel<<<grid, 32 * kWarps, 0, st>>>(s.view, w.b.dvb, ctx->net[net].w_dir, ctx->enc_scaled ? ctx->enc_scale + 64 : nullptr, n,
-                                                              w.b.pe_dir, w.g_v);
-        BNRF_LAUNCH_CHECK(ctx);
-        {   // direction block of views_linears.0 and its bias (pe_dir is written by viewdir_backward_kernel above)
-            const int64_t rpb = 128;
-            viewdir_wgrad_kernel<<<dim3(kDirCh + 1, (unsigned)ceil_div(n, rpb)), kHalf, 0, st>>>(
-                w.b.dvb, w.b.pe_dir, n, rpb, pg->weights[BNRF_L_VIEWS], pg->biases[BNRF_L_VIEWS]);
+        {   // everything after the tensor-core kernels of this network, one launch
+            const NetParams& np = ctx->net[net];
+            NetTail t{};
+            t.pe = acts.pe_f32; t.d_pe = w.b.d_pe; t.z = z; t.S = S; t.g_o = w.g_o; t.g_d = w.g_d;
+            t.view = s.view; t.dvb = w.b.dvb; t.w_dir = np.w_dir; t.g_v = w.g_v;
+            t.pe_dir = s.pe_dir; t.dW_views = pg->weights[BNRF_L_VIEWS]; t.dB_views = pg->biases[BNRF_L_VIEWS];
+            t.G = w.b.g_views; t.s = w.b.s_views; t.wt8 = np.wt[8]; t.wt9 = np.wt[9]; t.b_f = np.bias[8];
+            t.dW_f = pg->weights[BNRF_L_FEATURE]; t.dB_f = pg->biases[BNRF_L_FEATURE];
+            t.n = n; t.nA = t.nB = (unsigned)ceil_div(n, 4); t.nC = (unsigned)((kDirCh + 1) * ceil_div(n, 128));
+            net_tail_kernel<<<t.nA + t.nB + t.nC + 2 * (kHalf + kWidth), 128, 0, st>>>(t);
             BNRF_LAUNCH_CHECK(ctx);
         }
-        pe_ray_backward_kernel<<<grid, 32 * kWarps, 0, st>>>(acts.pe_f32, w.b.d_pe, z, n, S, w.g_o, w.g_d);
-        BNRF_LAUNCH_CHECK(ctx);
     }
     {
+        RaysBwd a{};
         int64_t off = 0;
         for (int i = 0; i < n_segs; ++i) {
             const bnrf_render_seg& sg = segs[i];
-            const int64_t ns = (int64_t)sg.P * sg.R;
-            rays_backward_kernel<<<(unsigned)ceil_div(ns, 128), 128, 0, st>>>(sg.poses, sg.ray_idx, sg.P, sg.R, sg.H, sg.W, sg.K[0], sg.K[4], sg.K[2], sg.K[5],
-                                                                             sg.remap, c.ndc, w.g_o + 3 * off, w.g_d + 3 * off, w.g_v + 3 * off, w.g_dn + off,
-                                                                             d_poses[i]);
-            BNRF_LAUNCH_CHECK(ctx);
-            off += ns;
+            a.seg[i] = RaysBwdSeg{sg.poses, sg.ray_idx, sg.remap, d_poses[i], sg.R, sg.H, sg.W, sg.K[0], sg.K[4], sg.K[2], sg.K[5], off};
+            off += (int64_t)sg.P * sg.R;
         }
+        a.n_segs = n_segs; a.ndc = c.ndc; a.n = off; a.g_o = w.g_o; a.g_d = w.g_d; a.g_v = w.g_v; a.g_dn = w.g_dn;
+        rays_backward_kernel<<<(unsigned)ceil_div(off, 128), 128, 0, st>>>(a);
+        BNRF_LAUNCH_CHECK(ctx);
     }
     return BNRF_OK;
 }

@@ -158,6 +158,11 @@ int launch_rays(bnrf_ctx*, const float* poses, const int64_t* ray_idx, int P, in
                 const float* remap, float* o, float* d, float* view, cudaStream_t);
 int launch_stratified(bnrf_ctx*, const float* t_rand, const bnrf_rng* rng, int64_t n, int S, float* z, cudaStream_t);
 int launch_viewbias(bnrf_ctx*, int net, const float* view, int64_t n, float* vb, cudaStream_t);
+// rays + view directions of all segments, per-ray view bias of both networks, encoded view directions (pe_dir, training) and the
+// stratified depths in one launch (rays.cu)
+struct RaySetupSeg { const float* poses; const int64_t* ray_idx; const float* remap; int R, H, W; float fx, fy, cx, cy; int64_t off; };
+int launch_ray_setup(bnrf_ctx*, const bnrf_render_seg* segs, int n_segs, const bnrf_rng* rng, int S, float* o, float* d, float* view,
+                     float* vb_c, float* vb_f, float* pe_dir, float* z, cudaStream_t);
 int launch_mlp_simt(bnrf_ctx*, int net, const float* o, const float* d, const float* vb, const float* z,
                     int64_t n, int S, float* raw, cudaStream_t);
 int launch_mlp_tc(bnrf_ctx*, int net, const float* o, const float* d, const float* vb, const float* z,
@@ -187,6 +192,7 @@ inline bool mlp_mode_is_pair(int mode) { return mode == BNRF_MLP_TC_FP16X2 || mo
 // Tensors the forward pass keeps for the backward pass (bnrf_render_forward_train), carved from the caller's buffer.
 struct SavedLayout {
     float *o, *d, *view;            // [N,3] NDC origin / direction, pre-NDC unit view direction
+    float* pe_dir;                  // [N,32] encoded view direction (27 channels, BARF-weighted, zero padded)
     float *z_c, *raw_c, *sig_c;     // [N,S_c], [N,S_c,C+1], [N,S_c] relu(raw_sigma + noise)
     float *z_f, *raw_f, *sig_f;     // fine network
     ActPtrs acts_c, acts_f;

@@ -35,8 +35,9 @@ __global__ void adam_step_kernel(float* __restrict__ p, float* __restrict__ g, f
 struct AdamSched { bnrf_adam_sched_group g[8]; int n; };
 
 __global__ void adam_step_sched_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
-                                       const __grid_constant__ AdamSched groups, const uint64_t* __restrict__ step_dev, double decay_steps,
-                                       float beta1, float beta2, float eps, float grad_scale, int zero_grads) {
+                                       const __grid_constant__ AdamSched groups, uint64_t* __restrict__ step_dev, double decay_steps,
+                                       float beta1, float beta2, float eps, float grad_scale, int zero_grads,
+                                       unsigned int* __restrict__ blocks_done) {
     __shared__ float s_lr[8];
     __shared__ float s_bc1, s_bc2_sqrt;
     if (threadIdx.x < groups.n) {
@@ -67,6 +68,12 @@ __global__ void adam_step_sched_kernel(float* __restrict__ p, float* __restrict_
         }
         if (zero_grads) g[i] = 0.0f;
     }
+    if (blocks_done) {
+        // global_step += 1 inside this launch: every block has read the counter before the barrier above, so the last block to
+        // get here may advance it (atomicInc wraps the arrival count back to zero for the next launch)
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicInc(blocks_done, gridDim.x - 1) == gridDim.x - 1) *step_dev += 1;
+    }
 }
 
 __global__ void step_advance_kernel(uint64_t* step_dev) { *step_dev += 1; }
@@ -93,8 +100,9 @@ extern "C" int bnrf_adam_step(float* params, float* grads, float* exp_avg, float
 }
 
 extern "C" int bnrf_adam_step_sched(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
-                                    const bnrf_adam_sched_group* groups, int n_groups, const uint64_t* step_dev, double decay_steps,
-                                    float beta1, float beta2, float eps, float grad_scale, int zero_grads, void* stream) {
+                                    const bnrf_adam_sched_group* groups, int n_groups, uint64_t* step_dev, double decay_steps,
+                                    float beta1, float beta2, float eps, float grad_scale, int zero_grads, uint64_t* advance_scratch,
+                                    void* stream) {
     if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || !groups || n_groups <= 0 || n_groups > 8 || !step_dev || decay_steps <= 0) return BNRF_ERR_ARG;
     AdamSched gs{};
     gs.n = n_groups;
@@ -104,7 +112,8 @@ extern "C" int bnrf_adam_step_sched(float* params, float* grads, float* exp_avg,
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t want = (n + 255) / 256, cap = (int64_t)sms * 8;
     adam_step_sched_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
-        params, grads, exp_avg, exp_avg_sq, n, gs, step_dev, decay_steps, beta1, beta2, eps, grad_scale, zero_grads);
+        params, grads, exp_avg, exp_avg_sq, n, gs, step_dev, decay_steps, beta1, beta2, eps, grad_scale, zero_grads,
+        reinterpret_cast<unsigned int*>(advance_scratch));
     return cudaGetLastError() == cudaSuccess ? BNRF_OK : BNRF_ERR_CUDA;
 }
 

@@ -374,15 +374,18 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, groups, step, betas=(0.9, 0.99
 
 
 def adam_step_sched(params, grads, exp_avg, exp_avg_sq, groups, step_dev, decay_steps, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0,
-                    zero_grads=True):
-    """bnrf_adam_step_sched: groups [(begin, end, lr0, decay_rate, active), ...]; step_dev: int64 device scalar = global_step."""
+                    zero_grads=True, advance_scratch=None):
+    """bnrf_adam_step_sched: groups [(begin, end, lr0, decay_rate, active), ...]; step_dev: int64 device scalar = global_step.
+    advance_scratch: an int64 device scalar (zero-initialised, owned by the caller): the launch also increments step_dev."""
     lib = _lib.load()
     arr = (_lib.AdamSchedGroup * len(groups))(*[_lib.AdamSchedGroup(int(b), int(e), float(lr0), float(rate), int(bool(a)))
                                                 for b, e, lr0, rate, a in groups])
     _rc(lib.bnrf_adam_step_sched(_ptr(params, name="params"), _ptr(grads, name="grads"), _ptr(exp_avg, name="exp_avg"),
                                  _ptr(exp_avg_sq, name="exp_avg_sq"), params.numel(), arr, len(groups),
                                  _ptr(step_dev, torch.int64, name="step_dev"), float(decay_steps), float(betas[0]), float(betas[1]),
-                                 float(eps), float(grad_scale), int(bool(zero_grads)), _stream()), "bnrf_adam_step_sched")
+                                 float(eps), float(grad_scale), int(bool(zero_grads)),
+                                 _ptr(advance_scratch, torch.int64, name="advance_scratch") if advance_scratch is not None else None,
+                                 _stream()), "bnrf_adam_step_sched")
 
 
 def step_advance(step_dev):

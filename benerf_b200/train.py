@@ -18,7 +18,7 @@ Two executions of the same arithmetic:
 import torch
 
 from . import image_formation as IF
-from .engine import adam_step_sched, step_advance, loss_cfg, training_loss_fused
+from .engine import adam_step_sched, loss_cfg, training_loss_fused
 from .parallel import FlatGrads, world, rank
 from ._lib import LINEAR_NAMES
 
@@ -51,6 +51,7 @@ class Trainer:
             self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.flat_params), torch.zeros_like(self.flat_params)
             self.group_ranges = [(0, n_nerf), (n_nerf, n_nerf + 24), (n_nerf + 24, n_nerf + 30)]      # nerf(s), knots [4,6], transform [1,6]
             self.step_dev = torch.zeros(1, device=self.flat_params.device, dtype=torch.int64)        # train.py's global_step, on the device
+            self.step_scratch = torch.zeros(1, device=self.flat_params.device, dtype=torch.int64)    # block arrival count of the Adam launch
         self.flat = FlatGrads(params)
         self.base_lr = [[grp["lr"] for grp in o.param_groups] for o in self.optims]
         self.global_step = 0
@@ -175,8 +176,8 @@ class Trainer:
         rates = self._rates()
         groups = [(b, e, self.base_lr[k][0], rates[k], flags[k]) for k, (b, e) in enumerate(self.group_ranges)]
         adam_step_sched(self.flat_params, self.flat.flat, self.exp_avg, self.exp_avg_sq, groups, self.step_dev,
-                        getattr(a, "lrate_decay", 200) * 1000, grad_scale=1.0 / world(), zero_grads=True)
-        step_advance(self.step_dev)                                      # global_step += 1
+                        getattr(a, "lrate_decay", 200) * 1000, grad_scale=1.0 / world(), zero_grads=True,
+                        advance_scratch=self.step_scratch)               # ... and global_step += 1
         eng.invalidate_weights()                                         # for Graph.render callers outside this step (evaluation)
         mark("optimizer")
         return loss_out
@@ -197,8 +198,10 @@ class Trainer:
         cg = torch.cuda.CUDAGraph()
         with torch.cuda.graph(cg, capture_error_mode="thread_local"):
             out = self._step_direct(static, consts)
-        # library kernels + torch's own nodes: the d_poses fill and the NCCL all-reduce(s) of the gradient buffer / batch norms
-        self.launches_per_step = eng.launch_count() - before + 1 + (world() > 1) * (1 + (self.args.event_threshold <= 0))
+        # kernels launched through the context + the ones that do not go through it: the loss (two stages when the event loss is the
+        # normalised one), Adam, torch's fill of d_poses, and the NCCL all-reduce(s) of the gradient buffer / batch norms
+        normalised = self.args.event_threshold <= 0
+        self.launches_per_step = eng.launch_count() - before + (2 if normalised else 1) + 1 + 1 + (world() > 1) * (1 + normalised)
         self._cg = (cg, sig, static, out, {k: None for k in static})
         return self._replay(inputs)
 
@@ -251,8 +254,8 @@ class Trainer:
             rates = self._rates()
             groups = [(b, e, self.base_lr[k][0], rates[k], flags[k]) for k, (b, e) in enumerate(self.group_ranges)]
             adam_step_sched(self.flat_params, self.flat.flat, self.exp_avg, self.exp_avg_sq, groups, self.step_dev,
-                            getattr(a, "lrate_decay", 200) * 1000, grad_scale=1.0 / world(), zero_grads=True)
-            step_advance(self.step_dev)
+                            getattr(a, "lrate_decay", 200) * 1000, grad_scale=1.0 / world(), zero_grads=True,
+                            advance_scratch=self.step_scratch)
             g.engine(a).invalidate_weights()                             # in-place update torch's version counters do not see
         else:
             self.flat.all_reduce_mean()

@@ -357,10 +357,13 @@ typedef struct {
  * argument.  step_dev: device counter holding train.py's global_step (0-based) of THIS iteration; the kernel derives the
  * 1-based Adam step count (bias corrections) and each group's learning rate of train.py:355-394 from it on the device:
  * lr = lr0 for the first iteration, lr0 * decay_rate ** ((global_step - 1) / decay_steps) afterwards (the reference updates the
- * rate AFTER optimizer.step(), with the not yet incremented global_step). */
+ * rate AFTER optimizer.step(), with the not yet incremented global_step).
+ * advance_scratch: NULL, or one device word, zero before the first call and otherwise left alone: the launch then also does
+ * train.py's `global_step += 1` (*step_dev += 1, by the last thread block to finish), saving the bnrf_step_advance launch. */
 int bnrf_adam_step_sched(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
-                         const bnrf_adam_sched_group* groups, int n_groups, const uint64_t* step_dev, double decay_steps,
-                         float beta1, float beta2, float eps, float grad_scale, int zero_grads, void* stream);
+                         const bnrf_adam_sched_group* groups, int n_groups, uint64_t* step_dev, double decay_steps,
+                         float beta1, float beta2, float eps, float grad_scale, int zero_grads, uint64_t* advance_scratch,
+                         void* stream);
 /* *step_dev += 1 (train.py: global_step += 1), enqueued as the last node of the captured iteration. */
 int bnrf_step_advance(uint64_t* step_dev, void* stream);
 
