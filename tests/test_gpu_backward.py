@@ -425,3 +425,82 @@ def test_trainer_state_dict_round_trips_adam_moments():
     pa = torch.cat([p.detach().reshape(-1) for p in graph_a.parameters()])
     pb = torch.cat([p.detach().reshape(-1) for p in graph_b.parameters()])
     assert float((pa - pb).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("dataset,channels,threshold", [("BeNeRF_Unreal", 3, 0.1), ("E2NeRF_Real", 3, -1.0), ("BeNeRF_Blender", 1, 0.2)])
+@pytest.mark.parametrize("flags", [(True, True), (True, False), (False, True)])
+def test_fused_training_loss_matches_oracle_loss_and_autograd(dataset, channels, threshold, flags):
+    """bnrf_training_loss (csrc/loss.cu): the loss block of train.py:163-337 -- target gather, log-intensity difference, the
+    thresholded (synthetic) or L2-normalised (real) event loss, blur mean, rgb loss -- and its ANALYTIC gradients w.r.t. the four
+    rendered tensors, against the oracle's loss under torch autograd on the same random renders.  args.event_loss / rgb_loss
+    (config.py:215-218) switch the two halves off."""
+    from argparse import Namespace
+    from benerf_b200 import image_formation as IF
+    from oracle import image_formation as oif
+    event_on, rgb_on = flags
+    n_poses, R_e, R_b, H, W = 7, 200, 23, 31, 40
+    g = torch.Generator().manual_seed(int(abs(threshold) * 100) + channels + 2 * event_on + rgb_on)
+    rend = {k: (torch.rand(n, channels, generator=g) * 0.9 + 0.02).requires_grad_(True)
+            for k, n in (("ef", 2 * R_e), ("ec", 2 * R_e), ("bf", n_poses * R_b), ("bc", n_poses * R_b))}
+    rend["ef"].data[:5] *= 0.01                                   # a few dark pixels: the piecewise-linear toe of the real-data log
+    accu = torch.randint(-4, 5, (H, W), generator=g).double()
+    idx = torch.randint(0, H * W, (R_e,), generator=g)
+    tgt = torch.rand(R_b, channels, generator=g)
+    args = Namespace(channels=channels, num_interpolated_pose=n_poses, dataset=dataset, event_threshold=threshold,
+                     event_coeff_syn=0.1, event_coeff_real=2.0, rgb_coeff=0.7, event_loss=event_on, rgb_loss=rgb_on)
+    want, parts = oif.training_loss({"rgb_map": rend["ef"], "rgb0": rend["ec"]}, {"rgb_map": rend["bf"], "rgb0": rend["bc"]}, accu, idx,
+                                    tgt, n_poses=n_poses, dataset=dataset, channels=channels, threshold=threshold, rgb_coeff=0.7)
+    want = (parts["event_rgb0"] + parts["event_rgb_map"]) * float(event_on) + (parts["blur_rgb_map"] + parts["blur_rgb0"]) * float(rgb_on)
+    want.backward()
+    dv = {k: v.detach().to(DEV).requires_grad_(True) for k, v in rend.items()}
+    got, got_parts = IF.training_loss({"rgb_map": dv["ef"], "rgb0": dv["ec"]}, {"rgb_map": dv["bf"], "rgb0": dv["bc"]}, accu.to(DEV),
+                                      idx.to(DEV), tgt.to(DEV), args)
+    got.backward()
+    assert got.dtype == torch.float64 and abs(float(got) - float(want)) <= 2e-6 * abs(float(want)) + 1e-12
+    for k in ("event_rgb_map", "event_rgb0") * event_on + ("blur_rgb_map", "blur_rgb0") * rgb_on:
+        assert abs(float(got_parts[k]) - float(parts[k])) <= 2e-6 * abs(float(parts[k])) + 1e-12, k
+    for k in rend:
+        ref = rend[k].grad if rend[k].grad is not None else torch.zeros_like(rend[k])
+        err = float((dv[k].grad.cpu() - ref).abs().max())
+        assert err <= 1e-5 * float(ref.abs().max()) + 1e-9, (k, err, float(ref.abs().max()))
+
+
+def test_trainer_graph_replay_matches_eager_steps():
+    """Trainer captures the iteration in a CUDA graph after two eager steps (global_step, the Philox offset, the learning-rate
+    schedule and the Adam bias corrections live in device memory, so a replay IS the next iteration).  Six steps with the graph
+    against six eager steps (args.cuda_graph = False) from the same state, with a batch that changes every step: same losses and
+    parameters up to the order of the gradient atomics, and the replayed steps must see the new batch."""
+    from benerf_b200 import optimize, run_nerf_helpers
+    from benerf_b200.train import Trainer
+    case = CASES["e2nerf_syn"]
+    runs = {}
+    for use_graph in (True, False):
+        args = case_args(case)
+        args.fused_optimizer, args.cuda_graph = True, use_graph
+        args.lrate, args.pose_lrate, args.transform_lrate = 5e-4, 1e-3, 1e-6
+        args.optimize_nerf, args.optimize_pose, args.optimize_trans = True, True, True
+        torch.manual_seed(0)
+        model = optimize.Model(args)
+        graph = model.build_network(args)
+        run_nerf_helpers.init_nerf(graph.nerf)
+        run_nerf_helpers.init_nerf(graph.nerf_fine)
+        graph.to(DEV)
+        tr = Trainer(model, args)
+        g = torch.Generator().manual_seed(9)
+        losses = []
+        for it in range(6):
+            idx_evt = torch.randint(0, case.H * case.W, (96,), generator=g).to(DEV)
+            idx_rgb = torch.randint(0, case.H * case.W, (16,), generator=g).to(DEV)
+            blur_t = torch.rand(16, case.channels, generator=g).to(DEV)
+            accu = torch.randint(-3, 4, (case.H, case.W), generator=g).double().to(DEV)
+            loss, _ = tr.step(accu, idx_evt, idx_rgb, blur_t, torch.tensor(case.window), torch.tensor(case.exposure), case.H, case.W, case.K, case.K)
+            losses.append(float(loss))
+        assert (tr._cg is not None) == use_graph
+        assert tr.global_step == 6 and int(tr.step_dev) == 6
+        runs[use_graph] = (losses, torch.cat([p.detach().reshape(-1) for p in graph.parameters()]).cpu())
+    (lg, pg), (le, pe) = runs[True], runs[False]
+    print("losses graph", lg, "eager", le)
+    assert len(set(lg)) == 6                                       # every replay saw its own batch
+    for a, b in zip(lg, le):
+        assert abs(a - b) <= 1e-4 * abs(b)
+    assert float((pg - pe).abs().max()) < 2e-4
