@@ -119,6 +119,12 @@ __global__ void __launch_bounds__(256) loss_stage1_kernel(const LossArgs a) {
                 }
             }
         }
+    } else if (a.R_e > 0) {
+        // args.event_loss off: the event render does not enter the loss, its gradient is zero (not "whatever the buffer held")
+        for (int64_t i = tid; i < 2 * a.R_e * C; i += stride) {
+            if (a.d_evt_fine) a.d_evt_fine[i] = 0.0f;
+            if (a.d_evt_coarse) a.d_evt_coarse[i] = 0.0f;
+        }
     }
     double sb[2] = {0, 0};
     if (c.rgb_loss) {
@@ -139,6 +145,11 @@ __global__ void __launch_bounds__(256) loss_stage1_kernel(const LossArgs a) {
                     for (int p = 0; p < P; ++p) d[(int64_t)p * L + e] = g;
                 }
             }
+        }
+    } else if (a.R_b > 0) {
+        for (int64_t i = tid; i < (int64_t)c.n_poses * a.R_b * C; i += stride) {
+            if (a.d_blur_fine) a.d_blur_fine[i] = 0.0f;
+            if (a.d_blur_coarse) a.d_blur_coarse[i] = 0.0f;
         }
     }
     for (int k = 0; k < 7; ++k) block_add(s[k], a.stats + k, sh);

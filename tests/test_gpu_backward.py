@@ -456,7 +456,7 @@ def test_fused_training_loss_matches_oracle_loss_and_autograd(dataset, channels,
     got, got_parts = IF.training_loss({"rgb_map": dv["ef"], "rgb0": dv["ec"]}, {"rgb_map": dv["bf"], "rgb0": dv["bc"]}, accu.to(DEV),
                                       idx.to(DEV), tgt.to(DEV), args)
     got.backward()
-    assert got.dtype == torch.float64 and abs(float(got) - float(want)) <= 2e-6 * abs(float(want)) + 1e-12
+    assert got.dtype == torch.float64 and abs(float(got.detach()) - float(want.detach())) <= 2e-6 * abs(float(want.detach())) + 1e-12
     for k in ("event_rgb_map", "event_rgb0") * event_on + ("blur_rgb_map", "blur_rgb0") * rgb_on:
         assert abs(float(got_parts[k]) - float(parts[k])) <= 2e-6 * abs(float(parts[k])) + 1e-12, k
     for k in rend:
@@ -469,7 +469,8 @@ def test_trainer_graph_replay_matches_eager_steps():
     """Trainer captures the iteration in a CUDA graph after two eager steps (global_step, the Philox offset, the learning-rate
     schedule and the Adam bias corrections live in device memory, so a replay IS the next iteration).  Six steps with the graph
     against six eager steps (args.cuda_graph = False) from the same state, with a batch that changes every step: same losses and
-    parameters up to the order of the gradient atomics, and the replayed steps must see the new batch."""
+    parameters up to the order of the gradient atomics -- which training amplifies: two EAGER runs already differ by 4e-8 in the
+    loss of step 2 and 3e-5 by step 4 -- and the replayed steps must see the new batch."""
     from benerf_b200 import optimize, run_nerf_helpers
     from benerf_b200.train import Trainer
     case = CASES["e2nerf_syn"]
@@ -477,7 +478,8 @@ def test_trainer_graph_replay_matches_eager_steps():
     for use_graph in (True, False):
         args = case_args(case)
         args.fused_optimizer, args.cuda_graph = True, use_graph
-        args.lrate, args.pose_lrate, args.transform_lrate = 5e-4, 1e-3, 1e-6
+        args.lrate, args.pose_lrate, args.transform_lrate, args.rgb_crf_lrate, args.event_crf_lrate = 5e-4, 1e-3, 1e-6, 5e-4, 5e-4
+        args.event_coeff_syn, args.rgb_coeff = 0.1, 1.0
         args.optimize_nerf, args.optimize_pose, args.optimize_trans = True, True, True
         torch.manual_seed(0)
         model = optimize.Model(args)
@@ -501,6 +503,6 @@ def test_trainer_graph_replay_matches_eager_steps():
     (lg, pg), (le, pe) = runs[True], runs[False]
     print("losses graph", lg, "eager", le)
     assert len(set(lg)) == 6                                       # every replay saw its own batch
-    for a, b in zip(lg, le):
-        assert abs(a - b) <= 1e-4 * abs(b)
-    assert float((pg - pe).abs().max()) < 2e-4
+    for i, (a, b) in enumerate(zip(lg, le)):
+        assert abs(a - b) <= (1e-6 if i < 3 else 2e-3) * abs(b), (i, a, b)
+    assert float((pg - pe).abs().max()) < 2e-3
