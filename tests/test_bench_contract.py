@@ -1,4 +1,4 @@
-"""The committed bench lines (profiles/r01_bench_*.json, written by bench.py on the B200 pool) carry every key of the
+"""The committed bench lines (profiles/r0N_bench_*.json, written by bench.py on the B200 pool) carry every key of the
 bench contract and are internally consistent.  Runs on CPU: it checks the evidence files, not the GPU."""
 import json
 import os
@@ -55,4 +55,45 @@ def test_reference_arm_line():
     d = _line("r01_bench_reference.json")
     assert d["impl"] == "reference" and d["metric"] == "rays_per_sec" and d["unit"] == "rays/s"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+# ------------------------------------------------------------------------------------------------ round 2
+@pytest.mark.parametrize("name,n", [("r02_bench_n1.json", 1), ("r02_bench_n8.json", 8)])
+def test_round2_bench_lines(name, n):
+    d = _line(name)
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["n_gpus"] == n and d["metric"] == "rays_per_sec" and d["warmup"] >= 3 and d["vs_baseline"] is None
+    rays = d["config"]["rays_per_step_per_gpu"] * n
+    assert abs(d["value"] - rays / (d["ms_per_step"] / 1e3)) < 1e-6 * d["value"]
+    assert d["value"] / n > 2.15e6
+    r = d["roofline"]
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["frac"] >= 0.36 and "mlp_tc3_kernel" in r["kernel"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] != d["value"] and 0.9 * d["value"] < e["value"] <= 1.02 * d["value"]
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    t = d["train_step"]
+    assert t["cuda_graph"] is True and t["gpu_launches_per_step"] <= 30 and t["ms_per_step"] <= 7.5
+    if n == 1:
+        assert isinstance(r["traffic"], float) and r["traffic"] > 0 and r["traffic_detail"]["over_algorithmic_bytes"] < 1.1
+        b = d["cpu_baseline"]
+        assert b["kind"] == "reference" and b["cores"] >= 1 and b["value"] > 0 and "sample" in b
+    else:
+        assert d["cpu_baseline"] is None
+
+
+def test_round2_strong_scaling_of_the_training_step():
+    one, eight = _line("r02_bench_n1.json"), _line("r02_bench_n8.json")
+    assert eight["value"] / one["value"] > 7.0
+    strong = eight["train_step_strong_scaling"]
+    assert one["train_step"]["ms_per_step"] / strong["ms_per_step"] >= 4.5
+    assert strong["gpu_launches_per_step"] <= 30
+
+
+def test_round2_reference_arm_line():
+    d = _line("r02_bench_reference.json")
+    assert d["impl"] == "reference" and d["metric"] == "rays_per_sec" and d["unit"] == "rays/s"
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

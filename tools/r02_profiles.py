@@ -94,5 +94,10 @@ if __name__ == "__main__":
     shares("r02_launches_train.csv")
     copy_keys("r02_mlp_tc3_bench.csv", "r02_mlp_tc3_ncu_full_key_metrics.csv")
     copy_keys("r02_train_kernels.csv", "r02_train_kernels_ncu_full_key_metrics.csv")
+    for name in ("r02_mlp_tc3_stall_trace.txt", "r02_bwd_stall_trace.txt", "r02_parity_report.json", "r02_bench_n1.json", "r02_bench_n2.json",
+                 "r02_bench_n8.json", "r02_bench_reference.json"):
+        copy_keys(name, name)
+    copy_keys("gradient_parity.json", "r02_gradient_parity.json")
+    copy_keys("parity_bench_batch_sample.json", "r02_parity_bench_batch_sample.json")
     bench_json()
     sass_index()
