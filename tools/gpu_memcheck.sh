@@ -11,7 +11,7 @@ run() {
   timeout 1200 $CS --tool memcheck --error-exitcode 9 python -m pytest "$@" -x -q >> $LOG 2>&1
   echo "exit $?" >> $LOG
 }
-run tests/test_gpu_backward.py -k "training_iteration_gradients_match_reference and tc-"
+run tests/test_gpu_backward.py -k "training_iteration_gradients_match_reference or render_backward_matches_oracle"
 run tests/test_gpu_backward.py -k "trainer or fused_training_loss"
 run tests/test_gpu_ops.py -k "mlp or spline"
 run tests/test_gpu_render.py -k "tone_mappers or binned or identical_samples or graph_forward"
