@@ -227,7 +227,7 @@ static Workspace carve(const bnrf_cfg& c, int64_t n, void* base) {
 }
 
 static int run_mlp(bnrf_ctx* ctx, int net, const float* o, const float* d, const float* vb, const float* z, int64_t n,
-                   int S, float* raw, const ActPtrs* acts, cudaStream_t st) {
+                   int S, float* raw, const ActPtrs* acts, cudaStream_t st, const FuseComposite* fuse = nullptr) {
     if (!ctx->net[net].ready) return fail(ctx, BNRF_ERR_STATE, "weights of network %d not set (bnrf_set_weights)", net);
     const double macs = 63.0 * 256 + 4 * 65536.0 + 319.0 * 256 + 2 * 65536.0 + 256 + 65536.0 + 283.0 * 128 + 128.0 * ctx->cfg.channels;
     MlpTimer timer(ctx, st, 2.0 * macs * (double)n * (double)S);
@@ -236,7 +236,7 @@ static int run_mlp(bnrf_ctx* ctx, int net, const float* o, const float* d, const
     if (ctx->cfg.mlp_mode == BNRF_MLP_SIMT_FP32) return launch_mlp_simt(ctx, net, o, d, vb, z, n, S, raw, st);
     if (ctx->cfg.mlp_mode == BNRF_MLP_TC_1CTA) return launch_mlp_tc(ctx, net, o, d, vb, z, n, S, raw, st);
     if (ctx->cfg.mlp_mode == BNRF_MLP_TC_PAIR_SS) return launch_mlp_tc2(ctx, net, o, d, vb, z, n, S, raw, acts, st);
-    return launch_mlp_tc3(ctx, net, o, d, vb, z, n, S, raw, acts, st);
+    return launch_mlp_tc3(ctx, net, o, d, vb, z, n, S, raw, acts, st, fuse);
 }
 
 }  // namespace bnrf
@@ -269,6 +269,7 @@ int bnrf_create(bnrf_ctx** out, int device, const bnrf_cfg* cfg) {
     ctx->device = device;
     ctx->cfg = *cfg;
     ctx->sm_count = prop.multiProcessorCount;
+    { const char* e = getenv("BNRF_NO_FUSE_COMPOSITE"); ctx->no_fuse = e && e[0] == '1'; }
     auto bail = [&](int rc) { strncpy(g_create_error, ctx->err, 511); bnrf_destroy(ctx); return rc; };
     if (cudaSetDevice(device) != cudaSuccess) return bail(fail(ctx, BNRF_ERR_CUDA, "cudaSetDevice failed"));
     int rc;
@@ -430,12 +431,21 @@ static int render_impl(bnrf_ctx* ctx, const bnrf_render_seg* segs, int n_segs, c
     int rc;
     // rays of all segments (laid out one after the other, each pose-major), view bias of both networks, stratified depths
     if ((rc = launch_ray_setup(ctx, segs, n_segs, &r, Sc, w.o, w.d, w.view, w.vb, fine ? w.vb_f : nullptr, saved ? s.pe_dir : nullptr, w.z_c, st))) return rc;
-    if ((rc = run_mlp(ctx, 0, w.o, w.d, w.vb, w.z_c, n, Sc, raw_c, saved ? &s.acts_c : nullptr, st))) return rc;
+    // A forward-only render on the default MLP kernel composites in that kernel's epilogue when a ray's samples fit a tile
+    // (S = 32, 64, 128): `raw` never reaches HBM and the pass is one launch.  Training mode keeps `raw` for the backward pass.
+    const bool can_fuse = !saved && c.mlp_mode == BNRF_MLP_TC_FP16X2 && !ctx->no_fuse;
     // coarse composite: outputs go to rgb0/disp0/acc0 when a fine pass follows (model/nerf.py:319-343)
     float* sigma_c_out = saved ? sig_c : (fine ? nullptr : out->sigma);
-    if ((rc = launch_composite(ctx, raw_c, w.z_c, w.d, r.noise_c, &r, kStreamNoiseC, n, Sc,
-                               fine ? out->rgb0 : out->rgb_map, fine ? out->disp0 : out->disp_map,
-                               fine ? out->acc0 : out->acc_map, w.w_c, fine ? nullptr : out->depth_map, sigma_c_out, st))) return rc;
+    if (can_fuse && mlp_tc3_can_fuse_composite(Sc)) {
+        const FuseComposite fz{w.d, r.noise_c, r, kStreamNoiseC, fine ? out->rgb0 : out->rgb_map, fine ? out->disp0 : out->disp_map,
+                               fine ? out->acc0 : out->acc_map, w.w_c, fine ? nullptr : out->depth_map, sigma_c_out};
+        if ((rc = run_mlp(ctx, 0, w.o, w.d, w.vb, w.z_c, n, Sc, raw_c, nullptr, st, &fz))) return rc;
+    } else {
+        if ((rc = run_mlp(ctx, 0, w.o, w.d, w.vb, w.z_c, n, Sc, raw_c, saved ? &s.acts_c : nullptr, st))) return rc;
+        if ((rc = launch_composite(ctx, raw_c, w.z_c, w.d, r.noise_c, &r, kStreamNoiseC, n, Sc,
+                                   fine ? out->rgb0 : out->rgb_map, fine ? out->disp0 : out->disp_map,
+                                   fine ? out->acc0 : out->acc_map, w.w_c, fine ? nullptr : out->depth_map, sigma_c_out, st))) return rc;
+    }
     if (!fine) {
         if (saved && out->sigma) BNRF_CUDA(ctx, cudaMemcpyAsync(out->sigma, sig_c, (size_t)n * Sc * sizeof(float), cudaMemcpyDeviceToDevice, st));
         if (out->z_vals) BNRF_CUDA(ctx, cudaMemcpyAsync(out->z_vals, w.z_c, (size_t)n * Sc * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -447,9 +457,14 @@ static int render_impl(bnrf_ctx* ctx, const bnrf_render_seg* segs, int n_segs, c
         return rc;
     }
     if (out->z_vals) BNRF_CUDA(ctx, cudaMemcpyAsync(out->z_vals, w.z_f, (size_t)n * Sf * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if ((rc = run_mlp(ctx, 1, w.o, w.d, w.vb_f, w.z_f, n, Sf, raw_f, saved ? &s.acts_f : nullptr, st))) return rc;
-    if ((rc = launch_composite(ctx, raw_f, w.z_f, w.d, r.noise_f, &r, kStreamNoiseF, n, Sf, out->rgb_map, out->disp_map,
-                               out->acc_map, nullptr, out->depth_map, saved ? sig_f : out->sigma, st))) return rc;
+    if (can_fuse && mlp_tc3_can_fuse_composite(Sf)) {
+        const FuseComposite fz{w.d, r.noise_f, r, kStreamNoiseF, out->rgb_map, out->disp_map, out->acc_map, nullptr, out->depth_map, out->sigma};
+        if ((rc = run_mlp(ctx, 1, w.o, w.d, w.vb_f, w.z_f, n, Sf, raw_f, nullptr, st, &fz))) return rc;
+    } else {
+        if ((rc = run_mlp(ctx, 1, w.o, w.d, w.vb_f, w.z_f, n, Sf, raw_f, saved ? &s.acts_f : nullptr, st))) return rc;
+        if ((rc = launch_composite(ctx, raw_f, w.z_f, w.d, r.noise_f, &r, kStreamNoiseF, n, Sf, out->rgb_map, out->disp_map,
+                                   out->acc_map, nullptr, out->depth_map, saved ? sig_f : out->sigma, st))) return rc;
+    }
     if (saved && out->sigma) BNRF_CUDA(ctx, cudaMemcpyAsync(out->sigma, sig_f, (size_t)n * Sf * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return BNRF_OK;
 }

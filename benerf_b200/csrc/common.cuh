@@ -76,6 +76,7 @@ struct bnrf_ctx {
     float* t_vals;            // device [n_samples] sampling grid (linspace(0,1,S) by default)
     float* enc_scale;         // device [64 + 32]: BARF c2f weights of the 63 point / 27 direction encoding channels (1 when off)
     bool enc_scaled;          // bnrf_set_encoding_weights is in effect
+    bool no_fuse;             // BNRF_NO_FUSE_COMPOSITE=1: keep compositing as its own launch (A/B measurements)
     int* tile_counter;        // device scratch for the persistent tile scheduler
     unsigned int* err_flag;   // device: set by kernels on watchdog timeout
     unsigned long long* trace; // device [sm_count][16] stall counters of the last MLP launch, or NULL (bnrf_debug_mlp_trace)
@@ -149,6 +150,42 @@ struct Philox {
 __device__ inline uint64_t rng_offset(const bnrf_rng& r) { return r.offset + (r.offset_dev ? 64ull * __ldg(r.offset_dev) : 0ull); }
 enum : uint32_t { kStreamTRand = 1, kStreamNoiseC = 2, kStreamU = 3, kStreamNoiseF = 4 };
 
+// ---- warp scans in double (torch's CPU cumsum / cumprod accumulate fp32 inputs in double, composite.cu) ----
+__device__ inline double warp_excl_scan_mul(double v, int lane, double& total) {
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc *= t;
+    }
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    double ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    return lane == 0 ? 1.0 : ex;
+}
+__device__ inline double warp_excl_scan_add(double v, int lane, double& total) {
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    double ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    return lane == 0 ? 0.0 : ex;
+}
+__device__ inline double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Alpha compositing of a render pass as the epilogue of the forward MLP kernel (mlp_tc3.cu; inference mode, S in {32, 64, 128} so that
+// a ray's samples never straddle a 128-row tile): the arguments of launch_composite except raw and z, which the kernel has.
+struct FuseComposite {
+    const float* rays_d; const float* noise; bnrf_rng rng; uint32_t stream_id;
+    float *rgb_map, *disp_map, *acc_map, *weights, *depth_map, *sigma;
+};
+
 // ---- launchers implemented in the individual .cu files ---------------------------------
 int launch_spline(bnrf_ctx*, const float* knots, const float* transform, const float* ts, int P, int n_plain, int traj,
                   float* poses, cudaStream_t);
@@ -184,8 +221,10 @@ size_t tc3_stream_halfs();
 int pack_tc3_stream_pair(bnrf_ctx*, cudaStream_t);                  // both networks, pre-scale derived from NetParams::absmax in the kernel
 int pack_dgrad_chain_pair_stream_both(bnrf_ctx*, cudaStream_t);    // both networks in one launch
 int pack_tc3_stream(bnrf_ctx*, int net, const float* const* table_dev, const float* scale_dev, cudaStream_t);
+bool mlp_tc3_can_fuse_composite(int S);
 int launch_mlp_tc3(bnrf_ctx*, int net, const float* o, const float* d, const float* vb, const float* z,
-                   int64_t n, int S, float* raw, const ActPtrs* acts /*NULL unless training*/, cudaStream_t);
+                   int64_t n, int S, float* raw, const ActPtrs* acts /*NULL unless training*/, cudaStream_t,
+                   const FuseComposite* fuse = nullptr /*inference only: composite in the epilogue, raw is not written*/);
 // the two CTA-pair kernels run nine GEMM steps (feature_linear merged into the view layer) and take the merged view bias
 inline bool mlp_mode_is_pair(int mode) { return mode == BNRF_MLP_TC_FP16X2 || mode == BNRF_MLP_TC_PAIR_SS; }
 

@@ -16,34 +16,6 @@ namespace bnrf {
 
 constexpr int kWarpsPerBlock = 4;
 
-__device__ inline double warp_excl_scan_mul(double v, int lane, double& total) {
-    double inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        double t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc *= t;
-    }
-    total = __shfl_sync(0xffffffffu, inc, 31);
-    double ex = __shfl_up_sync(0xffffffffu, inc, 1);
-    return lane == 0 ? 1.0 : ex;
-}
-__device__ inline double warp_excl_scan_add(double v, int lane, double& total) {
-    double inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        double t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    total = __shfl_sync(0xffffffffu, inc, 31);
-    double ex = __shfl_up_sync(0xffffffffu, inc, 1);
-    return lane == 0 ? 0.0 : ex;
-}
-__device__ inline double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
 // MAXK = ceil(S/32) upper bound; lane owns samples [lane*K, lane*K+K) so the scan is order preserving.
 template <int C>
 __global__ void composite_kernel(const float* __restrict__ raw, const float* __restrict__ z,

@@ -12,10 +12,12 @@
 //     two consecutive K elements).  The accumulator buffer of layer t thereby BECOMES the A operand of layer t + 1, and the
 //     other 256-column buffer (layer t's A, dead once its MMAs retire) receives layer t + 1's accumulator: two buffers
 //     ping-pong, TMEM (512 columns) is exactly enough and the 128 KB of shared memory are free.
-//   * Because A and D never alias, a layer is issued in N-halves -- [N0: kb 0,1] [N1: kb 0,1] [N0: kb 2,3] [N1: kb 2,3] -- and
-//     the epilogue of columns 0..127 runs while the tensor core still works on columns 128..255.  Its output is exactly the
-//     first two K-blocks of the next layer, which therefore starts without draining the pipe.
-//   * Shared memory holds the encoded points (SS-form MMAs for those K-blocks), a deep ring of 8 KB weight stages, the
+//   * Because A and D never alias, the tail of a layer can be issued in N-halves (make_schedule: three full K-blocks, then the
+//     last K-block against columns 0..127 and against 128..255, each half with its own ACC_FULL barrier): the epilogue of
+//     columns 0..127 runs while the tensor core still works on columns 128..255, and its output is exactly the first two
+//     K-blocks of the next layer, which therefore starts without draining the pipe.  (Splitting EVERY K-block made the kernel
+//     bound by the tensor-memory read port: an A operand from TMEM costs 4 KB per MMA whatever N is.)
+//   * Shared memory holds the encoded points (SS-form MMAs for those K-blocks), a deep ring of 16 KB weight stages, the
 //     epilogue constants, and -- in training mode -- a 3-slot staging ring from which ONE thread bulk-stores the bf16 hi/lo
 //     activation tiles and ReLU mask bits the backward pass reads (no re-read / convert pass over A as in mlp_tc2).
 //
@@ -24,6 +26,9 @@
 //   W_EMPTY[slot], ACC_FULL[buffer][N-half], PE_EMPTY   tcgen05.commit multicast to both CTAs
 //   A_READY[8], PE_FULL   on the leader only: one elected-lane arrival per producing warp of BOTH CTAs (8 per phase)
 //   ST_FULL[3], ST_EMPTY[3]   per CTA (training mode): staging slot filled by the 8 epilogue warps / read by the copy engine
+//
+// FUSE (forward-only renders with S = 32 / 64 / 128): the epilogue parks (rgb, sigma) of every row in shared memory instead of storing
+// `raw`, and the front-end warps run NeRF.raw2output (model/nerf.py:118-148) on them between two encodings (RAW_FULL / RAW_EMPTY).
 //
 // Replaces model/embedder.py:9-34 + model/nerf.py:67-116.
 #include <stdlib.h>
@@ -55,10 +60,11 @@ template <bool TRAIN> struct Cfg {
     static constexpr uint32_t OFF_ST = OFF_W + NS * SLOT_W_BYTES;
     static constexpr uint32_t OFF_CONST = OFF_ST + (TRAIN ? NSLOT * SLOT_BYTES : 0);
     static constexpr uint32_t OFF_XCHG = OFF_CONST + CONST_FLOATS * 4;
-    static constexpr uint32_t OFF_BAR = OFF_XCHG + XCHG_BYTES;
+    static constexpr uint32_t OFF_FUSE = OFF_XCHG + XCHG_BYTES;            // fused compositing: [128] float4 (rgb, sigma) of the tile, then 4 warp
+    static constexpr uint32_t OFF_BAR = OFF_FUSE + (TRAIN ? 0 : 2048 + 256);   // products + 4 x 5 partial sums (double)
     static constexpr int BAR_W_FULL = 0, BAR_W_EMPTY = NS, BAR_PE_FULL = 2 * NS, BAR_PE_EMPTY = 2 * NS + 1, BAR_A_READY = 2 * NS + 2,
                          BAR_ACC_FULL = BAR_A_READY + 8, BAR_ST_FULL = BAR_ACC_FULL + 4, BAR_ST_EMPTY = BAR_ST_FULL + NSLOT,
-                         BAR_COUNT = BAR_ST_EMPTY + NSLOT;
+                         BAR_RAW_FULL = BAR_ST_EMPTY + NSLOT, BAR_RAW_EMPTY = BAR_RAW_FULL + 1, BAR_COUNT = BAR_RAW_EMPTY + 1;
     static constexpr uint32_t SMEM_BYTES = OFF_BAR + 8 * BAR_COUNT + 16 + 1024;   // + tmem slot + alignment slack
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
     static_assert(OFF_ST % 1024 == 0 && OFF_CONST % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
@@ -115,9 +121,9 @@ __device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t b
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
 }
 
-template <int C, bool TRAIN>
+template <int C, bool TRAIN, bool FUSE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-mlp_tc3_kernel(const __grid_constant__ Schedule sched, TcParams p, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+mlp_tc3_kernel(const __grid_constant__ Schedule sched, const __grid_constant__ FuseComposite fz, TcParams p, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                const float* __restrict__ viewbias, const float* __restrict__ z, int64_t rows, int S, int num_pairs, size_t stream_bytes,
                float* __restrict__ raw, const ActPtrs acts, unsigned int* err_flag, unsigned long long* __restrict__ trace) {
     // trace (debug, normally NULL): per-CTA stall accounting in clock64 cycles, [blockIdx.x * 16 + i] --
@@ -168,6 +174,7 @@ mlp_tc3_kernel(const __grid_constant__ Schedule sched, TcParams p, const float* 
         for (int i = 0; i < 8; ++i) mbar_init(bar(L::BAR_A_READY + i), 8);     // 4 epilogue warps (one column half) x 2 CTAs
         for (int i = 0; i < 4; ++i) mbar_init(bar(L::BAR_ACC_FULL + i), 1);
         for (int i = 0; i < NSLOT; ++i) { mbar_init(bar(L::BAR_ST_FULL + i), 8); mbar_init(bar(L::BAR_ST_EMPTY + i), 1); }
+        mbar_init(bar(L::BAR_RAW_FULL), 4); mbar_init(bar(L::BAR_RAW_EMPTY), 4);   // fused compositing: 4 epilogue warps -> 4 front-end warps
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -474,14 +481,21 @@ mlp_tc3_kernel(const __grid_constant__ Schedule sched, TcParams p, const float* 
                         named_bar_sync(1 + q, 64);
                         const float4 o = *reinterpret_cast<const float4*>(xchg);
                         named_bar_arrive(5 + q, 64);
-                        if (row < rows) {
-                            const float sgm = sigma_acc + o.w + __ldg(p.b_alpha);
-                            if (C == 3) {
-                                *reinterpret_cast<float4*>(raw + row * 4) =
-                                    make_float4(rgb[0] + o.x + __ldg(p.b_rgb), rgb[1] + o.y + __ldg(p.b_rgb + 1), rgb[2] + o.z + __ldg(p.b_rgb + 2), sgm);
-                            } else {
-                                *reinterpret_cast<float2*>(raw + row * 2) = make_float2(rgb[0] + o.x + __ldg(p.b_rgb), sgm);
+                        const float sgm = sigma_acc + o.w + __ldg(p.b_alpha);
+                        float out_c[3] = {rgb[0] + o.x + __ldg(p.b_rgb), 0.f, 0.f};
+                        if (C == 3) { out_c[1] = rgb[1] + o.y + __ldg(p.b_rgb + 1); out_c[2] = rgb[2] + o.z + __ldg(p.b_rgb + 2); }
+                        if (!FUSE) {
+                            if (row < rows) {
+                                if (C == 3) *reinterpret_cast<float4*>(raw + row * 4) = make_float4(out_c[0], out_c[1], out_c[2], sgm);
+                                else *reinterpret_cast<float2*>(raw + row * 2) = make_float2(out_c[0], sgm);
                             }
+                        } else {
+                            // fused compositing: hand the four values to the front-end warps (idle most of a tile), which run
+                            // NeRF.raw2output on them off the critical path; `raw` never reaches HBM
+                            timed_wait(bar(L::BAR_RAW_EMPTY), ((uint32_t)it & 1u) ^ 1u, 13, w_acc);
+                            reinterpret_cast<float4*>(sm + L::OFF_FUSE)[r] = make_float4(out_c[0], out_c[1], out_c[2], sgm);
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar(L::BAR_RAW_FULL));
                         }
                     }
                 }
@@ -496,6 +510,83 @@ mlp_tc3_kernel(const __grid_constant__ Schedule sched, TcParams p, const float* 
         const int r = threadIdx.x - 128;
         unsigned long long w_pee = 0;
         const long long f_t0 = clock64();
+        // fused compositing (FUSE): NeRF.raw2output (model/nerf.py:118-148) of tile `itp` from the (rgb, sigma) rows the epilogue warps
+        // parked in shared memory.  The samples of a ray are S consecutive rows of the tile (S = 32, 64 or 128), one per lane of
+        // S / 32 of these four warps.  Same arithmetic as composite_kernel (composite.cu): fp32 steps rounded separately, scans in
+        // double.  Runs between two encodings, off the critical path of the tensor pipe.
+        const int q = warp - 4;
+        auto composite_tile = [&](int itp) {
+            const int64_t row = tile_of(itp) * TILE_M + r;
+            unsigned long long w_raw = 0;
+            timed_wait(bar(L::BAR_RAW_FULL), (uint32_t)itp & 1u, 14, w_raw);
+            const float4 rv = reinterpret_cast<const float4*>(sm + L::OFF_FUSE)[r];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(L::BAR_RAW_EMPTY));
+            const float out_c[3] = {rv.x, rv.y, rv.z};
+            const float sgm = rv.w;
+            const bool valid = row < rows;                 // rows = n S: a ray is inside the batch or not at all
+            const int s_idx = r & (S - 1), wpr = S >> 5;   // sample index; warps per ray
+            const int64_t ray_c = valid ? row / S : 0;
+            float a_ = 0.0f, zi = 0.0f;
+            double fct = 1.0;
+            if (valid) {
+                zi = z[row];
+                float dist = (s_idx + 1 < S) ? __fsub_rn(z[row + 1], zi) : 1e10f;
+                const float* rd = fz.rays_d + ray_c * 3;
+                const float dn = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(rd[0], rd[0]), __fmul_rn(rd[1], rd[1])), __fmul_rn(rd[2], rd[2])));
+                dist = __fmul_rn(dist, dn);
+                float nz;
+                if (fz.noise) {
+                    nz = fz.noise[row];
+                } else {
+                    uint32_t w4[4];
+                    Philox::draw(fz.rng.seed, rng_offset(fz.rng), fz.rng.ray_base + (uint64_t)ray_c, (uint32_t)s_idx, fz.stream_id, w4);
+                    nz = Philox::normal(w4[0], w4[1]);
+                }
+                const float dens = fmaxf(__fadd_rn(sgm, nz), 0.0f);      // relu(sigma_raw + noise)
+                if (fz.sigma) fz.sigma[row] = dens;
+                a_ = __fsub_rn(1.0f, expf(__fmul_rn(-dens, dist)));
+                fct = (double)__fadd_rn(__fsub_rn(1.0f, a_), 1e-10f);
+            }
+            double* scratch = reinterpret_cast<double*>(sm + L::OFF_FUSE + 2048);   // [4] warp products, [4][5] warp sums
+            double w_total;
+            const double ex = warp_excl_scan_mul(fct, lane, w_total);
+            if (lane == 0) scratch[q] = w_total;
+            named_bar_sync(9, 128);
+            const int q0 = q & ~(wpr - 1);                   // first warp of this ray
+            double pre = 1.0;
+            for (int j = q0; j < q; ++j) pre *= scratch[j];
+            const float T = (float)(pre * ex);               // cumprod rounds every prefix to fp32
+            const float wgt = __fmul_rn(a_, T);
+            if (valid && fz.weights) fz.weights[row] = wgt;
+            double part[5];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                part[c] = (c < C && valid) ? (double)__fmul_rn(wgt, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-out_c[c])))) : 0.0;   // sigmoid
+            part[3] = valid ? (double)__fmul_rn(wgt, zi) : 0.0;
+            part[4] = valid ? (double)wgt : 0.0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                part[k] = warp_sum(part[k]);
+                if (lane == 0) scratch[4 + q * 5 + k] = part[k];
+            }
+            named_bar_sync(10, 128);
+            if (q == q0 && lane == 0 && valid) {
+                for (int j = q0 + 1; j < q0 + wpr; ++j)
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) part[k] += scratch[4 + j * 5 + k];
+                const float depth = (float)part[3], acc = (float)part[4];
+                if (fz.rgb_map)
+                    for (int c = 0; c < C; ++c) fz.rgb_map[ray_c * C + c] = (float)part[c];
+                if (fz.depth_map) fz.depth_map[ray_c] = depth;
+                if (fz.acc_map) fz.acc_map[ray_c] = acc;
+                if (fz.disp_map) {                   // 1 / max(1e-10, depth / acc); NaN when acc == 0 (Q14)
+                    const float rr = __fdiv_rn(depth, acc);
+                    const float m = (rr != rr) ? rr : fmaxf(1e-10f, rr);
+                    fz.disp_map[ray_c] = __fdiv_rn(1.0f, m);
+                }
+            }
+        };
         for (int it = 0; it < my_iters; ++it) {
             const int64_t tile = tile_of(it);
             const int64_t row = tile * TILE_M + r;
@@ -534,6 +625,7 @@ mlp_tc3_kernel(const __grid_constant__ Schedule sched, TcParams p, const float* 
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(lbar(L::BAR_PE_FULL));
+            if (FUSE && it > 0) composite_tile(it - 1);
             if (TRAIN) {
 #pragma unroll
                 for (int c8 = 0; c8 < 8; ++c8) {
@@ -542,6 +634,7 @@ mlp_tc3_kernel(const __grid_constant__ Schedule sched, TcParams p, const float* 
                 }
             }
         }
+        if (FUSE && my_iters > 0) composite_tile(my_iters - 1);
         if (trace && threadIdx.x == 128) {
             trace[blockIdx.x * 16 + 8] = w_pee; trace[blockIdx.x * 16 + 9] = (unsigned long long)(clock64() - f_t0);
         }
@@ -677,24 +770,28 @@ int pack_tc3_stream_pair(bnrf_ctx* ctx, cudaStream_t st) {
     return BNRF_OK;
 }
 
-template <int C, bool TRAIN>
+template <int C, bool TRAIN, bool FUSE = false>
 static int launch_one3(bnrf_ctx* ctx, const tcp::TcParams& p, int clusters, const float* o, const float* d, const float* vb,
-                       const float* z, int64_t rows, int S, int pairs, float* raw, const ActPtrs& acts, cudaStream_t st) {
+                       const float* z, int64_t rows, int S, int pairs, float* raw, const ActPtrs& acts, cudaStream_t st,
+                       const FuseComposite& fz = FuseComposite{}) {
     using namespace tc3;
     static bool configured = false;                 // per instantiation: the attribute is a property of the function
     if (!configured) {
-        BNRF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc3_kernel<C, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<TRAIN>::SMEM_BYTES));
+        BNRF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc3_kernel<C, TRAIN, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<TRAIN>::SMEM_BYTES));
         configured = true;
     }
     const Schedule& sc = tc3_schedule();
-    mlp_tc3_kernel<C, TRAIN><<<2 * clusters, NUM_THREADS, Cfg<TRAIN>::SMEM_BYTES, st>>>(sc, p, o, d, vb, z, rows, S, pairs, schedule_stream_bytes(sc), raw, acts,
-                                                                                      ctx->err_flag, ctx->trace);
+    mlp_tc3_kernel<C, TRAIN, FUSE><<<2 * clusters, NUM_THREADS, Cfg<TRAIN>::SMEM_BYTES, st>>>(sc, fz, p, o, d, vb, z, rows, S, pairs, schedule_stream_bytes(sc), raw,
+                                                                                            acts, ctx->err_flag, ctx->trace);
     BNRF_LAUNCH_CHECK(ctx);
     return BNRF_OK;
 }
 
+// a ray's samples must be S consecutive rows of ONE 128-row tile, a whole number of warps
+bool mlp_tc3_can_fuse_composite(int S) { return S == 32 || S == 64 || S == 128; }
+
 int launch_mlp_tc3(bnrf_ctx* ctx, int net, const float* o, const float* d, const float* vb, const float* z,
-                   int64_t n, int S, float* raw, const ActPtrs* acts, cudaStream_t st) {
+                   int64_t n, int S, float* raw, const ActPtrs* acts, cudaStream_t st, const FuseComposite* fuse) {
     using namespace tc3;
     const NetParams& np = ctx->net[net];
     TcParams p;
@@ -714,6 +811,11 @@ int launch_mlp_tc3(bnrf_ctx* ctx, int net, const float* o, const float* d, const
                   : launch_one3<1, true>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, *acts, st);
     }
     const ActPtrs none{};
+    if (fuse) {
+        if (!mlp_tc3_can_fuse_composite(S) || !fuse->rays_d) return fail(ctx, BNRF_ERR_ARG, "mlp: fused compositing needs S in {32, 64, 128}");
+        return c3 ? launch_one3<3, false, true>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, none, st, *fuse)
+                  : launch_one3<1, false, true>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, none, st, *fuse);
+    }
     return c3 ? launch_one3<3, false>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, none, st)
               : launch_one3<1, false>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, none, st);
 }
