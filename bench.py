@@ -257,7 +257,7 @@ def workload_config(n_pixels, n_gpus, note=None):
                      "(BASELINE.json configs[1], throughput shape)",
          "pixels_per_gpu": n_pixels, "rays_per_step_per_gpu": (N_POSES + 2) * n_pixels, "n_poses": N_POSES,
          "samples": [S_C, S_C + N_I], "parallelism": f"pixel-sharded x{n_gpus}, weights replicated",
-         "l2": "no flush needed: per-step workspace + outputs >> 126 MB L2 (4.1 KB/ray scratch)"}
+         "l2": "no flush needed: per-step workspace + outputs >> 126 MB L2 (1.8 KB/ray scratch: rays, view biases, sample depths)"}
     if note:
         c["note"] = note
     return c

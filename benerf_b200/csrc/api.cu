@@ -436,9 +436,18 @@ static int render_impl(bnrf_ctx* ctx, const bnrf_render_seg* segs, int n_segs, c
     const bool can_fuse = !saved && c.mlp_mode == BNRF_MLP_TC_FP16X2 && !ctx->no_fuse;
     // coarse composite: outputs go to rgb0/disp0/acc0 when a fine pass follows (model/nerf.py:319-343)
     float* sigma_c_out = saved ? sig_c : (fine ? nullptr : out->sigma);
+    bool resampled = false;                  // the coarse launch has already produced the fine depths
     if (can_fuse && mlp_tc3_can_fuse_composite(Sc)) {
-        const FuseComposite fz{w.d, r.noise_c, r, kStreamNoiseC, fine ? out->rgb0 : out->rgb_map, fine ? out->disp0 : out->disp_map,
-                               fine ? out->acc0 : out->acc_map, w.w_c, fine ? nullptr : out->depth_map, sigma_c_out};
+        FuseComposite fz{w.d, r.noise_c, r, kStreamNoiseC, fine ? out->rgb0 : out->rgb_map, fine ? out->disp0 : out->disp_map,
+                         fine ? out->acc0 : out->acc_map, w.w_c, fine ? nullptr : out->depth_map, sigma_c_out, nullptr, nullptr, 0, 0};
+        if (fine && !r.z_fine) {
+            int sort_n = 1;
+            while (sort_n < Sf) sort_n <<= 1;
+            if ((128 / Sc) * (2 * Sc + sort_n) * 4 <= 5120) {            // the resampler's scratch fits beside the tile: fuse it too
+                fz.z_f = w.z_f; fz.u = r.u; fz.K = c.n_importance; fz.sort_n = sort_n; fz.weights = nullptr;
+                resampled = true;
+            }
+        }
         if ((rc = run_mlp(ctx, 0, w.o, w.d, w.vb, w.z_c, n, Sc, raw_c, nullptr, st, &fz))) return rc;
     } else {
         if ((rc = run_mlp(ctx, 0, w.o, w.d, w.vb, w.z_c, n, Sc, raw_c, saved ? &s.acts_c : nullptr, st))) return rc;
@@ -453,7 +462,7 @@ static int render_impl(bnrf_ctx* ctx, const bnrf_render_seg* segs, int n_segs, c
     }
     if (r.z_fine) {
         BNRF_CUDA(ctx, cudaMemcpyAsync(w.z_f, r.z_fine, (size_t)n * Sf * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    } else if ((rc = launch_resample(ctx, w.z_c, w.w_c, r.u, &r, n, Sc, c.n_importance, w.z_f, st))) {
+    } else if (!resampled && (rc = launch_resample(ctx, w.z_c, w.w_c, r.u, &r, n, Sc, c.n_importance, w.z_f, st))) {
         return rc;
     }
     if (out->z_vals) BNRF_CUDA(ctx, cudaMemcpyAsync(out->z_vals, w.z_f, (size_t)n * Sf * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -184,6 +184,9 @@ __device__ inline double warp_sum(double v) {
 struct FuseComposite {
     const float* rays_d; const float* noise; bnrf_rng rng; uint32_t stream_id;
     float *rgb_map, *disp_map, *acc_map, *weights, *depth_map, *sigma;
+    // coarse pass with a fine pass behind it: also the inverse-CDF resampling (sample_pdf + sort, composite.cuh) on the weights just
+    // produced -- z_f [n, S + K] receives the fine depths (NULL: no resampling); u [n, K] injected draws or NULL (Philox)
+    float* z_f; const float* u; int K, sort_n;
 };
 
 // ---- launchers implemented in the individual .cu files ---------------------------------

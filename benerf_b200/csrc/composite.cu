@@ -11,6 +11,7 @@
 // (ATen ReduceOps cumsum_cpu_kernel, acc_type<float,false> = double); both scans here do the
 // same, which keeps weights and cdf within an ulp of the reference whatever the scan order.
 #include "common.cuh"
+#include "composite.cuh"
 
 namespace bnrf {
 
@@ -99,10 +100,7 @@ __global__ void composite_kernel(const float* __restrict__ raw, const float* __r
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// resample: S coarse depths + weights -> K new depths by inverse CDF over the S-1 mid-points
-// (S-2 bins, weights[1:-1]), then sort(concat).  Per warp shared memory: cdf[S-1], bins[S-1],
-// sort buffer of next_pow2(S+K).
+// resample_kernel: one warp per ray around resample_ray (composite.cuh)
 __global__ void resample_kernel(const float* __restrict__ z_c, const float* __restrict__ w_c,
                                 const float* __restrict__ u_in, bnrf_rng rng, int64_t n_rays, int S, int K,
                                 int sort_n, float* __restrict__ z_f) {
@@ -114,74 +112,7 @@ __global__ void resample_kernel(const float* __restrict__ z_c, const float* __re
     float* bins = cdf + S;                    // [S-1]
     float* buf = bins + S;                    // [sort_n]
     if (ray >= n_rays) return;
-    const float* zr = z_c + ray * S;
-    const float* wr = w_c + ray * S;
-    const int nb = S - 2;                     // number of pdf bins
-    // bins = mid-points of consecutive coarse depths (model/nerf.py:321)
-    for (int i = lane; i < S - 1; i += 32) bins[i] = __fmul_rn(0.5f, __fadd_rn(zr[i + 1], zr[i]));
-    // weights + 1e-5, their sum (double), pdf, inclusive scan in double rounded per prefix
-    const int per = (nb + 31) / 32;
-    double local = 0.0;
-    for (int k = 0; k < per; ++k) {
-        const int i = lane * per + k;
-        if (i < nb) local += (double)__fadd_rn(wr[i + 1], 1e-5f);
-    }
-    const float wsum = (float)warp_sum(local);
-    double run = 0.0, tot;
-    double pre_local = 0.0;
-    for (int k = 0; k < per; ++k) {
-        const int i = lane * per + k;
-        if (i < nb) pre_local += (double)__fdiv_rn(__fadd_rn(wr[i + 1], 1e-5f), wsum);
-    }
-    run = warp_excl_scan_add(pre_local, lane, tot);
-    if (lane == 0) cdf[0] = 0.0f;
-    for (int k = 0; k < per; ++k) {
-        const int i = lane * per + k;
-        if (i < nb) {
-            run += (double)__fdiv_rn(__fadd_rn(wr[i + 1], 1e-5f), wsum);
-            cdf[i + 1] = (float)run;
-        }
-    }
-    for (int i = lane; i < S; i += 32) buf[i] = zr[i];
-    for (int i = S + K + lane; i < sort_n; i += 32) buf[i] = __int_as_float(0x7f800000);   // +inf padding
-    __syncwarp();
-    const int nc = S - 1;                     // cdf / bins length
-    for (int j = lane; j < K; j += 32) {
-        float u;
-        if (u_in) {
-            u = u_in[ray * K + j];
-        } else {
-            uint32_t w[4];
-            Philox::draw(rng.seed, rng_offset(rng), rng.ray_base + (uint64_t)ray, (uint32_t)j, kStreamU, w);
-            u = Philox::uniform(w[0]);
-        }
-        // searchsorted(cdf, u, right=True): first index with cdf[idx] > u
-        int lo = 0, hi = nc;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
-        }
-        const int below = max(lo - 1, 0), above = min(lo, nc - 1);
-        float denom = __fsub_rn(cdf[above], cdf[below]);
-        if (denom < 1e-5f) denom = 1.0f;
-        const float t = __fdiv_rn(__fsub_rn(u, cdf[below]), denom);
-        buf[S + j] = __fadd_rn(bins[below], __fmul_rn(t, __fsub_rn(bins[above], bins[below])));
-    }
-    __syncwarp();
-    // bitonic sort of buf[0, sort_n)
-    for (int size = 2; size <= sort_n; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = lane; t < sort_n / 2; t += 32) {
-                const int i = 2 * t - (t & (stride - 1));     // lower index of the pair
-                const int j = i + stride;
-                const bool up = ((i & size) == 0);
-                const float a = buf[i], b = buf[j];
-                if ((a > b) == up) { buf[i] = b; buf[j] = a; }
-            }
-            __syncwarp();
-        }
-    }
-    for (int i = lane; i < S + K; i += 32) z_f[ray * (S + K) + i] = buf[i];
+    resample_ray(z_c + ray * S, w_c + ray * S, u_in ? u_in + ray * K : nullptr, rng, ray, S, K, sort_n, cdf, bins, buf, z_f + ray * (S + K), lane);
 }
 
 int launch_composite(bnrf_ctx* ctx, const float* raw, const float* z, const float* d, const float* noise,

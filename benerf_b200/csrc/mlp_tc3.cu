@@ -34,6 +34,7 @@
 #include <stdlib.h>
 #include "tc_ptx.cuh"
 #include "bwd_tiles.cuh"
+#include "composite.cuh"
 
 namespace bnrf {
 namespace tc3 {
@@ -61,7 +62,8 @@ template <bool TRAIN> struct Cfg {
     static constexpr uint32_t OFF_CONST = OFF_ST + (TRAIN ? NSLOT * SLOT_BYTES : 0);
     static constexpr uint32_t OFF_XCHG = OFF_CONST + CONST_FLOATS * 4;
     static constexpr uint32_t OFF_FUSE = OFF_XCHG + XCHG_BYTES;            // fused compositing: [128] float4 (rgb, sigma) of the tile, then 4 warp
-    static constexpr uint32_t OFF_BAR = OFF_FUSE + (TRAIN ? 0 : 2048 + 256);   // products + 4 x 5 partial sums (double)
+    static constexpr uint32_t FUSE_BYTES = 2048 + 256 + 512 + 5120;        // products + 4 x 5 partial sums (double); the tile's 128 weights; resampling
+    static constexpr uint32_t OFF_BAR = OFF_FUSE + (TRAIN ? 0 : FUSE_BYTES);   // scratch of up to 4 rays (cdf, bins, sort buffer: <= 5 KB)
     static constexpr int BAR_W_FULL = 0, BAR_W_EMPTY = NS, BAR_PE_FULL = 2 * NS, BAR_PE_EMPTY = 2 * NS + 1, BAR_A_READY = 2 * NS + 2,
                          BAR_ACC_FULL = BAR_A_READY + 8, BAR_ST_FULL = BAR_ACC_FULL + 4, BAR_ST_EMPTY = BAR_ST_FULL + NSLOT,
                          BAR_RAW_FULL = BAR_ST_EMPTY + NSLOT, BAR_RAW_EMPTY = BAR_RAW_FULL + 1, BAR_COUNT = BAR_RAW_EMPTY + 1;
@@ -559,6 +561,8 @@ mlp_tc3_kernel(const __grid_constant__ Schedule sched, const __grid_constant__ F
             const float T = (float)(pre * ex);               // cumprod rounds every prefix to fp32
             const float wgt = __fmul_rn(a_, T);
             if (valid && fz.weights) fz.weights[row] = wgt;
+            float* wbuf = reinterpret_cast<float*>(sm + L::OFF_FUSE + 2048 + 256);           // the tile's weights, for the resampler
+            if (fz.z_f) wbuf[r] = wgt;
             double part[5];
 #pragma unroll
             for (int c = 0; c < 3; ++c)
@@ -585,6 +589,13 @@ mlp_tc3_kernel(const __grid_constant__ Schedule sched, const __grid_constant__ F
                     const float m = (rr != rr) ? rr : fmaxf(1e-10f, rr);
                     fz.disp_map[ray_c] = __fdiv_rn(1.0f, m);
                 }
+            }
+            if (fz.z_f && q == q0 && valid) {
+                // sample_pdf + sort (run_nerf_helpers.py:74-115, model/nerf.py:322-326) by the first warp of the ray, on the weights in
+                // shared memory: the coarse weights never reach HBM.  (wbuf is rewritten only after the next call's first barrier.)
+                float* sc = reinterpret_cast<float*>(sm + L::OFF_FUSE + 2048 + 256 + 512) + (q0 / wpr) * (2 * S + fz.sort_n);
+                resample_ray(z + ray_c * S, wbuf + q0 * 32, fz.u ? fz.u + ray_c * fz.K : nullptr, fz.rng, ray_c, S, fz.K, fz.sort_n,
+                             sc, sc + S, sc + 2 * S, fz.z_f + ray_c * (S + fz.K), lane);
             }
         };
         for (int it = 0; it < my_iters; ++it) {
@@ -813,6 +824,7 @@ int launch_mlp_tc3(bnrf_ctx* ctx, int net, const float* o, const float* d, const
     const ActPtrs none{};
     if (fuse) {
         if (!mlp_tc3_can_fuse_composite(S) || !fuse->rays_d) return fail(ctx, BNRF_ERR_ARG, "mlp: fused compositing needs S in {32, 64, 128}");
+        if (fuse->z_f && (128 / S) * (2 * S + fuse->sort_n) * 4 > 5120) return fail(ctx, BNRF_ERR_ARG, "mlp: fused resampling scratch too small");
         return c3 ? launch_one3<3, false, true>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, none, st, *fuse)
                   : launch_one3<1, false, true>(ctx, p, clusters, o, d, vb, z, rows, S, pairs, raw, none, st, *fuse);
     }

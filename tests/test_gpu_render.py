@@ -625,3 +625,45 @@ def test_multi_bin_event_render_and_chunked_full_frame():
         # different chunks draw different noise (as the reference's own chunked eval does); the scene is the same
         assert float(((ret["rgb_map"] - whole["rgb_map"]) ** 2).mean()) < 0.05
         assert whole["acc_map"].shape == ret["acc_map"].shape == (H, W) and torch.isfinite(ret["acc_map"]).all()
+
+
+@pytest.mark.parametrize("name", ["unreal_rgb", "e2nerf_syn", "blender_gray_coarse"])
+def test_forward_only_render_fuses_compositing_and_resampling_into_the_mlp_launches(name, monkeypatch):
+    """A forward-only render on the default kernel composites inside the MLP kernel (S = 32 / 64 / 128) and, for the coarse pass,
+    also runs sample_pdf + sort there: ray setup + one launch per pass.  Against the same render with the stand-alone
+    composite_kernel / resample_kernel (BNRF_NO_FUSE_COMPOSITE=1, read when the context is created): same arithmetic, so the
+    outputs agree to fp32 rounding of the reductions -- and the launch counts show which path ran."""
+    case = CASES[name]
+    inp = make_inputs(case)
+    gold = load_golden(name)
+    fine = case.n_importance > 0
+    outs, launches = {}, {}
+    for fused in (True, False):
+        if fused:
+            monkeypatch.delenv("BNRF_NO_FUSE_COMPOSITE", raising=False)
+        else:
+            monkeypatch.setenv("BNRF_NO_FUSE_COMPOSITE", "1")
+        eng = make_engine(case, "tc")
+        eng.set_weights(0, to_dev(inp["coarse"]))
+        if fine:
+            eng.set_weights(1, to_dev(inp["fine"]))
+        before = eng.launch_count()
+        ret = eng.render(gold["poses_rgb"].to(DEV).contiguous(), inp["idx_rgb"].to(DEV), case.H, case.W, case.K, rng=to_dev(dict(inp["rng_rgb"])),
+                         want_z=fine)
+        torch.cuda.synchronize()
+        launches[fused] = eng.launch_count() - before
+        outs[fused] = ret
+    Sc, Sf = case.n_samples, case.n_samples + case.n_importance
+    fusable = lambda S: S in (32, 64, 128)                     # noqa: E731
+    want_fused = 1 + (1 if fusable(Sc) else 2)                 # ray setup; coarse MLP (+ composite)
+    if fine:
+        want_fused += (0 if fusable(Sc) else 1) + (1 if fusable(Sf) else 2)      # resample rides on a fused coarse pass; fine MLP (+ composite)
+    assert launches[False] == (6 if fine else 3), launches
+    assert launches[True] == want_fused, (launches, want_fused)
+    assert launches[True] < launches[False]
+    worst = {k: max_abs(outs[True][k], v) for k, v in outs[False].items() if v is not None}
+    print("fused vs stand-alone compositing / resampling:", name, launches, {k: f"{e:.1e}" for k, e in worst.items()})
+    # same arithmetic; the transmittance product is associated differently (one sample per lane), so a weight may move by an ulp,
+    # which the 2^9 encoding frequency of the fine pass amplifies: well inside the 1e-4 parity bound
+    for k, e in worst.items():
+        assert e <= (1e-6 if k in ("rgb0", "acc0", "disp0", "z_vals") or not fine else 2e-5), (k, e)
