@@ -46,10 +46,10 @@ def bench_json():
     rows = pixels * poses * s_fine
     macs = 63 * 256 + 4 * 65536 + 319 * 256 + 2 * 65536 + 256 + 65536 + 283 * 128 + 128 * bench.CH      # the reference's MACs per sample
     rd, wr = to_bytes("dram__bytes_read.sum"), to_bytes("dram__bytes_write.sum")
-    # algorithmic bytes per sample: origin / direction / depth in (rays are shared by a ray's samples: 4 B depth per sample + 24 B per
-    # ray), raw [C + 1] fp32 out, view bias 128 fp32 per ray in
-    alg = rows * (4 + 4 * (bench.CH + 1)) + pixels * poses * (24 + 128 * 4)
-    doc = {"kernel": "bnrf::tc3::mlp_tc3_kernel<3,false> (4th MLP launch of a bench step: fine pass of the 19-pose blur render)",
+    # algorithmic bytes of the fine pass with compositing in the kernel: per sample the depth in (4 B) and the density out (4 B, the
+    # `sigma` output Graph.render returns); per ray origin + direction (24 B) and the view bias (128 fp32) in, rgb / disp / acc out
+    alg = rows * (4 + 4) + pixels * poses * (24 + 128 * 4 + 4 * (bench.CH + 2))
+    doc = {"kernel": "bnrf::tc3::mlp_tc3_kernel<3,false,true> (4th MLP launch of a bench step: fine pass of the 19-pose blur render, compositing fused)",
            "rows": rows, "algorithmic_flop": 2.0 * macs * rows, "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes": rd + wr,
            "gpu_time_ms_under_ncu": m["gpu__time_duration.sum"], "sm_ghz_under_ncu": m["sm__cycles_elapsed.max.per_second"],
            "tensor_pipe_active_pct": m["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"],
