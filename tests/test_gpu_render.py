@@ -627,15 +627,20 @@ def test_multi_bin_event_render_and_chunked_full_frame():
         assert whole["acc_map"].shape == ret["acc_map"].shape == (H, W) and torch.isfinite(ret["acc_map"]).all()
 
 
-@pytest.mark.parametrize("name", ["unreal_rgb", "e2nerf_syn", "blender_gray_coarse"])
-def test_forward_only_render_fuses_compositing_and_resampling_into_the_mlp_launches(name, monkeypatch):
+@pytest.mark.parametrize("name,samples", [("unreal_rgb", None), ("e2nerf_syn", None), ("blender_gray_coarse", None),
+                                          ("unreal_rgb", (32, 32)), ("unreal_rgb", (32, 96)), ("unreal_rgb", (128, 64)), ("unreal_rgb", (64, 128)),
+                                          ("unreal_rgb", (48, 80))])
+def test_forward_only_render_fuses_compositing_and_resampling_into_the_mlp_launches(name, samples, monkeypatch):
     """A forward-only render on the default kernel composites inside the MLP kernel (S = 32 / 64 / 128) and, for the coarse pass,
     also runs sample_pdf + sort there: ray setup + one launch per pass.  Against the same render with the stand-alone
     composite_kernel / resample_kernel (BNRF_NO_FUSE_COMPOSITE=1, read when the context is created): same arithmetic, so the
     outputs agree to fp32 rounding of the reductions -- and the launch counts show which path ran."""
+    import dataclasses
     case = CASES[name]
-    inp = make_inputs(case)
     gold = load_golden(name)
+    if samples is not None:        # other sample counts: 4 / 2 / 1 rays per tile; a fusable coarse pass with a fine pass that is not; neither
+        case = dataclasses.replace(case, n_samples=samples[0], n_importance=samples[1])
+    inp = make_inputs(case)
     fine = case.n_importance > 0
     outs, launches = {}, {}
     for fused in (True, False):
@@ -660,7 +665,7 @@ def test_forward_only_render_fuses_compositing_and_resampling_into_the_mlp_launc
         want_fused += (0 if fusable(Sc) else 1) + (1 if fusable(Sf) else 2)      # resample rides on a fused coarse pass; fine MLP (+ composite)
     assert launches[False] == (6 if fine else 3), launches
     assert launches[True] == want_fused, (launches, want_fused)
-    assert launches[True] < launches[False]
+    assert launches[True] < launches[False] or not (fusable(Sc) or fusable(Sf))
     worst = {k: max_abs(outs[True][k], v) for k, v in outs[False].items() if v is not None}
     print("fused vs stand-alone compositing / resampling:", name, launches, {k: f"{e:.1e}" for k, e in worst.items()})
     # same arithmetic; the transmittance product is associated differently (one sample per lane), so a weight may move by an ulp,
