@@ -98,6 +98,7 @@ PROTOTYPES = {
     "bnrf_adam_step": (_I, [_P, _P, _P, _P, _L, C.POINTER(AdamGroup), _I, _L, C.c_float, C.c_float, C.c_float, C.c_float, _I, _P]),
     "bnrf_adam_step_sched": (_I, [_P, _P, _P, _P, _L, C.POINTER(AdamSchedGroup), _I, _P, C.c_double, C.c_float, C.c_float, C.c_float, C.c_float, _I, _P, _P]),
     "bnrf_step_advance": (_I, [_P, _P]),
+    "bnrf_wait_fine_gradients": (_I, [_P, _P]),
     "bnrf_profile": (_I, [_P, _I]),
     "bnrf_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "bnrf_debug_mlp_trace": (_I, [_P, _P]),

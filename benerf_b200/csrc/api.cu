@@ -282,6 +282,7 @@ int bnrf_create(bnrf_ctx** out, int device, const bnrf_cfg* cfg) {
         return bail(fail(ctx, BNRF_ERR_CUDA, "cudaMalloc failed"));
     cudaMemset(ctx->tile_counter, 0, 64 * sizeof(int));
     cudaMemset(ctx->err_flag, 0, sizeof(unsigned int));
+    if (cudaEventCreateWithFlags(&ctx->fine_grads_done, cudaEventDisableTiming) != cudaSuccess) return bail(fail(ctx, BNRF_ERR_CUDA, "cudaEventCreate failed"));
     // default sampling grid = torch.linspace(0, 1, S) as the CUDA kernel of the reference's device computes it:
     // start + step*i below the midpoint, end - step*(S-1-i) above, single rounding (fma).
     const int S = cfg->n_samples;
@@ -300,6 +301,7 @@ void bnrf_destroy(bnrf_ctx* ctx) {
     for (int n = 0; n < 2; ++n) free_net(ctx, n);
     cudaFree(ctx->t_vals); cudaFree(ctx->tile_counter); cudaFree(ctx->err_flag); cudaFree(ctx->enc_scale);
     if (ctx->prof_ev[0]) for (int i = 0; i < 2 * 512; ++i) cudaEventDestroy(ctx->prof_ev[i]);
+    if (ctx->fine_grads_done) cudaEventDestroy(ctx->fine_grads_done);
     delete ctx;
 }
 

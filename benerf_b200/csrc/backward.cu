@@ -755,6 +755,9 @@ static int render_backward_impl(bnrf_ctx* ctx, const bnrf_render_seg* segs, int 
             net_tail_kernel<<<t.nA + t.nB + t.nC + 2 * (kHalf + kWidth), 128, 0, st>>>(t);
             BNRF_LAUNCH_CHECK(ctx);
         }
+        // the fine network is done first: a data-parallel caller may start reducing its gradients while the coarse network's
+        // backward pass runs (bnrf_wait_fine_gradients)
+        if (net == 1) BNRF_CUDA(ctx, cudaEventRecord(ctx->fine_grads_done, st));
     }
     {
         RaysBwd a{};
@@ -768,6 +771,12 @@ static int render_backward_impl(bnrf_ctx* ctx, const bnrf_render_seg* segs, int 
         rays_backward_kernel<<<(unsigned)ceil_div(off, 128), 128, 0, st>>>(a);
         BNRF_LAUNCH_CHECK(ctx);
     }
+    return BNRF_OK;
+}
+
+int bnrf_wait_fine_gradients(bnrf_ctx* ctx, void* stream) {
+    if (!ctx) return BNRF_ERR_ARG;
+    BNRF_CUDA(ctx, cudaStreamWaitEvent((cudaStream_t)stream, ctx->fine_grads_done, 0));
     return BNRF_OK;
 }
 

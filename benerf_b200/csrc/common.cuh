@@ -76,6 +76,7 @@ struct bnrf_ctx {
     float* t_vals;            // device [n_samples] sampling grid (linspace(0,1,S) by default)
     float* enc_scale;         // device [64 + 32]: BARF c2f weights of the 63 point / 27 direction encoding channels (1 when off)
     bool enc_scaled;          // bnrf_set_encoding_weights is in effect
+    cudaEvent_t fine_grads_done;  // recorded by the render backward pass once the fine network's parameter gradients are complete
     bool no_fuse;             // BNRF_NO_FUSE_COMPOSITE=1: keep compositing as its own launch (A/B measurements)
     int* tile_counter;        // device scratch for the persistent tile scheduler
     unsigned int* err_flag;   // device: set by kernels on watchdog timeout

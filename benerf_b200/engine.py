@@ -245,6 +245,11 @@ class Engine:
             _ptr(saved, torch.uint8, name="saved"), saved.numel() if saved is not None else 0, _stream()), "bnrf_render_forward_multi")
         return ret
 
+    def wait_fine_gradients(self, stream):
+        """bnrf_wait_fine_gradients: `stream` waits until the fine network's parameter gradients of the last render backward pass
+        enqueued on this engine are complete (the coarse network's backward pass may still be running)."""
+        self._check(self.lib.bnrf_wait_fine_gradients(self._ctx, C.c_void_p(stream.cuda_stream)), "bnrf_wait_fine_gradients")
+
     def render_backward_multi(self, segs, saved, d_rgb_map, d_rgb0, grads_coarse, grads_fine, d_poses):
         """bnrf_render_backward_multi: d_rgb_map / d_rgb0 over the concatenated rays; d_poses: one [P_i,3,4] tensor per segment."""
         arr, n = self._segs(segs)

@@ -2,7 +2,8 @@
 
 train.py itself stays the caller's script; this helper is the step it performs per iteration, used by
 bench.py and the tests: poses -> two Graph.render calls -> image formation + the four loss terms -> backward ->
-ONE gradient all-reduce -> the reference's Adam steps and exponential learning-rate decay (Q17).
+the gradient all-reduce (one exchange of the flat buffer, issued in two parts so that the fine network's half overlaps the coarse
+network's backward pass) -> the reference's Adam steps and exponential learning-rate decay (Q17).
 
 Two executions of the same arithmetic:
   * the DIRECT step (default, fused_optimizer=True): every stage is an explicit call into libbenerf_b200.so -- spline poses,
@@ -30,7 +31,9 @@ class Trainer:
         self.optims = model.setup_optimizer(args)                       # nerf, pose, transform, rgb_crf, event_crf (optimize.py:36-55)
         g = self.graph
         self.nets = [g.nerf] + ([g.nerf_fine] if hasattr(g, "nerf_fine") else [])
-        params = [p for m in self.nets for p in m.parameters()]
+        # flat layout: fine network, coarse network, knots, transform -- the backward pass finishes the fine network first, so its
+        # gradients are one leading range that can be all-reduced early, and everything else is one trailing range
+        params = [p for m in reversed(self.nets) for p in m.parameters()]
         params += [g.evt_knot_pose_se3.params.weight, g.transform.params.weight]
         if not all(p.requires_grad for p in params):
             raise ValueError("Trainer lays parameters, gradients and moments out as flat buffers in one order: freeze an optimiser "
@@ -53,6 +56,7 @@ class Trainer:
             self.step_dev = torch.zeros(1, device=self.flat_params.device, dtype=torch.int64)        # train.py's global_step, on the device
             self.step_scratch = torch.zeros(1, device=self.flat_params.device, dtype=torch.int64)    # block arrival count of the Adam launch
         self.flat = FlatGrads(params)
+        self._side = torch.cuda.Stream(device=params[0].device) if params[0].is_cuda else None   # issue point of the early all-reduce
         self.base_lr = [[grp["lr"] for grp in o.param_groups] for o in self.optims]
         self.global_step = 0
         self.phase_ms = None           # set to a list to get synchronised per-phase wall times (debug aid; serialises the step)
@@ -167,10 +171,25 @@ class Trainer:
         d_pe, d_pr = d_poses[:poses_evt.shape[0]], d_poses[poses_evt.shape[0]:]
         gc, gf = grad_tabs[0], grad_tabs[1] if fine else None
         eng.render_backward_multi(segs, saved, d_fine, d_coarse if fine else None, gc, gf, [d_pe, d_pr])
+        # The exchange of the step, overlapped with what is left of the backward pass: the fine network's gradients (its backward
+        # pass runs first) are reduced while the coarse network's still runs, the coarse network's while the pose gradients are
+        # formed.  NCCL runs on its own stream; the only join is in front of the optimiser.
+        pending, n_early = [], 0
+        if world() > 1 and fine and getattr(a, "overlap_all_reduce", True):
+            import torch.distributed as dist
+            n_early = sum(p.numel() for p in self.nets[1].parameters())      # the fine network's gradients lead the flat buffer
+            eng.wait_fine_gradients(self._side)
+            with torch.cuda.stream(self._side):
+                pending.append(dist.all_reduce(self.flat.flat[:n_early], async_op=True))
+            torch.cuda.current_stream().wait_stream(self._side)          # (joins the side stream for graph capture; NCCL is not on it)
         gk, gt = g.evt_knot_pose_se3.params.weight.grad, g.transform.params.weight.grad.reshape(6)
         eng.spline_poses_pair_backward(knots, transform, t["ts"], n_pe, d_poses, gk, gt, a.traj)
         mark("backward")
-        self.flat.all_reduce_sum()                                       # the single exchange of the step
+        if world() > 1:
+            import torch.distributed as dist
+            pending.append(dist.all_reduce(self.flat.flat[n_early:], async_op=True))     # coarse network, knots, transform
+            for work in pending:
+                work.wait()
         mark("all_reduce")
         flags = [getattr(a, "optimize_nerf", True), getattr(a, "optimize_pose", True), getattr(a, "optimize_trans", False)]
         rates = self._rates()
@@ -201,7 +220,7 @@ class Trainer:
         # kernels launched through the context + the ones that do not go through it: the loss (two stages when the event loss is the
         # normalised one), Adam, torch's fill of d_poses, and the NCCL all-reduce(s) of the gradient buffer / batch norms
         normalised = self.args.event_threshold <= 0
-        self.launches_per_step = eng.launch_count() - before + (2 if normalised else 1) + 1 + 1 + (world() > 1) * (1 + normalised)
+        self.launches_per_step = eng.launch_count() - before + (2 if normalised else 1) + 1 + 1 + (world() > 1) * (2 + normalised)
         self._cg = (cg, sig, static, out, {k: None for k in static})
         return self._replay(inputs)
 

@@ -228,6 +228,10 @@ int bnrf_render_backward_multi(bnrf_ctx* ctx, const bnrf_render_seg* segs, int n
                                const void* saved, size_t saved_bytes, const bnrf_param_grads* grads_coarse,
                                const bnrf_param_grads* grads_fine, float* const* d_poses, void* workspace, size_t workspace_bytes,
                                void* stream);
+/* Make `stream` wait until the FINE network's parameter gradients of the last bnrf_render_backward[_multi] enqueued on this context
+ * are complete (the backward pass handles the fine network first): a data-parallel training loop starts the all-reduce of that
+ * half of the gradient buffer on a second stream while the coarse network's backward pass still runs.  Capturable. */
+int bnrf_wait_fine_gradients(bnrf_ctx* ctx, void* stream);
 /* Backward of bnrf_spline_poses: adds d L / d knots (device [4,6]) and, when transform != NULL,
  * d L / d transform (device [6]) given d L / d poses (device [P,3,4]).  spline.py:247-331 under autograd. */
 int bnrf_spline_poses_backward(bnrf_ctx* ctx, const float* knots, const float* transform, const float* ts,
