@@ -163,7 +163,12 @@ int bnrf_spline_poses_pair_backward(bnrf_ctx* ctx, const float* knots, const flo
 size_t bnrf_workspace_bytes(const bnrf_ctx* ctx, int64_t n_rays);
 
 /* poses device [P,3,4]; ray_idx device int64 [R] (flat pixel index j*W+i); K host float[9]
- * row-major; remap device [H,W,2] or NULL (TUM-VIE LUT, model/nerf.py:247-250). */
+ * row-major; remap device [H,W,2] or NULL (TUM-VIE LUT, model/nerf.py:247-250).
+ * Launches: ray setup (rays, view biases, stratified depths), then one per network pass -- with the default mlp_mode and
+ * n_samples / n_samples + n_importance in {32, 64, 128}, raw2output (and, for the coarse pass, sample_pdf + sort) run inside the
+ * MLP kernel and neither the per-sample MLP outputs nor the coarse weights are written to the workspace; other sample counts,
+ * other mlp_modes and bnrf_render_forward_train use the stand-alone compositing / resampling kernels (same arithmetic, bit-identical
+ * results; BNRF_NO_FUSE_COMPOSITE=1 in the environment of bnrf_create forces them). */
 int bnrf_render_forward(bnrf_ctx* ctx, const float* poses, const int64_t* ray_idx, int P, int R,
                         int H, int W, const float* K, const float* remap, const bnrf_rng* rng,
                         const bnrf_outputs* out, void* workspace, size_t workspace_bytes, void* stream);
