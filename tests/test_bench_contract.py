@@ -59,7 +59,7 @@ def test_reference_arm_line():
 
 
 # ------------------------------------------------------------------------------------------------ round 2
-@pytest.mark.parametrize("name,n", [("r02_bench_n1.json", 1), ("r02_bench_n8.json", 8)])
+@pytest.mark.parametrize("name,n", [("r02_bench_n1.json", 1), ("r02_bench_n2.json", 2), ("r02_bench_n4.json", 4), ("r02_bench_n8.json", 8)])
 def test_round2_bench_lines(name, n):
     d = _line(name)
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
