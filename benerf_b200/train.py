@@ -88,7 +88,14 @@ class Trainer:
             if self._cg is not None and self._cg[1] == sig:
                 out = self._replay(inputs)
             elif self._eager_direct_steps >= 2:
-                out = self._capture(sig, inputs, consts)
+                try:
+                    out = self._capture(sig, inputs, consts)
+                except RuntimeError as e:      # capture refused here (driver / NCCL combination): the same launches, enqueued eagerly
+                    import warnings
+                    warnings.warn(f"benerf_b200.train.Trainer: CUDA-graph capture of the step failed ({e}); stepping eagerly")
+                    self.use_graph, self._cg = False, None
+                    torch.cuda.synchronize()
+                    out = self._step_direct({k: _dev(v, dev) for k, v in inputs.items()}, consts)
             else:
                 out = self._step_direct({k: _dev(v, dev) for k, v in inputs.items()}, consts)
                 self._eager_direct_steps += 1
