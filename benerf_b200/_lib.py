@@ -103,6 +103,7 @@ PROTOTYPES = {
     "bnrf_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "bnrf_debug_mlp_trace": (_I, [_P, _P]),
     "bnrf_debug_umma_probe": (_I, [_P, _P, _I, _I, _P, _P]),
+    "bnrf_debug_tc3_schedule": (_I, [_I, _P, _I, _P]),
     "bnrf_debug_umma_probe_fmt": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "bnrf_debug_umma_ts_probe": (_I, [_P, _P, _I, _I, _P, _P]),
     "bnrf_debug_tile_dgrad": (_I, [_P, _L, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P]),

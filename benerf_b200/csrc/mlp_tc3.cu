@@ -833,3 +833,17 @@ int launch_mlp_tc3(bnrf_ctx* ctx, int net, const float* o, const float* d, const
 }
 
 }  // namespace bnrf
+
+// Host-only (no device needed): the MMA issue schedule of one tile as the forward kernel receives it, 4 ints per group --
+// GEMM step t, kind (0 all columns, 1 / 2 the lower / upper 128-column half), K-block (-1 = encoded points), flags -- and the bytes
+// of weight stream one tile consumes per CTA.  tests/test_library.py checks its invariants on the CPU.
+extern "C" int bnrf_debug_tc3_schedule(int split, int32_t* groups, int max_groups, int64_t* stream_bytes_per_cta) {
+    using namespace bnrf::tc3;
+    if (split < 0 || split > 4 || !groups || max_groups < MAX_GROUPS) return BNRF_ERR_ARG;
+    const Schedule sc = make_schedule(split);
+    for (int i = 0; i < sc.n; ++i) {
+        groups[4 * i] = sc.g[i].t; groups[4 * i + 1] = sc.g[i].kind; groups[4 * i + 2] = sc.g[i].kb; groups[4 * i + 3] = sc.g[i].flags;
+    }
+    if (stream_bytes_per_cta) *stream_bytes_per_cta = (int64_t)schedule_stream_bytes(sc);
+    return sc.n;
+}

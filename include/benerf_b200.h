@@ -393,6 +393,11 @@ int bnrf_profile_read(bnrf_ctx* ctx, double* mlp_ms, int64_t* mlp_timed, double*
  * swizzle, UMMA descriptors, tcgen05.mma and tcgen05.ld helpers as the MLP kernel.  A, B device
  * fp16 row-major; D device fp32 [128,N]; lbo_field = raw 14-bit leading-byte-offset field. */
 int bnrf_debug_umma_probe(const void* A_half, const void* B_half, int N, int lbo_field, float* D, void* stream);
+/* Host-only: the forward kernel's MMA issue schedule for one tile (tests; no device needed).  groups: max_groups >= 64 entries of
+ * 4 ints (GEMM step, kind 0 = all columns / 1, 2 = lower, upper 128-column half, K-block or -1 for the encoded points, flags:
+ * 1 first write of an accumulator half, 2 / 4 commit of half 0 / 1, 8 encoded points free, 16 wait for encoded points,
+ * 32 wait for the previous layer's converted chunks).  Returns the number of groups, or a negative status. */
+int bnrf_debug_tc3_schedule(int split, int32_t* groups, int max_groups, int64_t* stream_bytes_per_cta);
 /* Same with the element formats of the instruction descriptor chosen per operand (a_bf16 / b_bf16: 0 = fp16, 1 = bf16):
  * only equal formats are executable on B200 (a mixed pair ends the launch with "illegal instruction" and poisons the CUDA
  * context), which is why the forward pass re-splits its activations as bf16 for the weight-gradient kernel. */
