@@ -126,7 +126,7 @@ def load():
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype, fn.argtypes = res, args
-    if lib.bnrf_abi_version() != 1:
+    if lib.bnrf_abi_version() != 2:
         raise RuntimeError("libbenerf_b200.so ABI version mismatch")
     _lib = lib
     return lib

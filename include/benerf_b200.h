@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BNRF_ABI_VERSION 1
+#define BNRF_ABI_VERSION 2   /* 2: bnrf_rng grew ray_base / offset_dev, bnrf_adam_step_sched takes advance_scratch, multi-segment render */
 
 typedef enum {
     BNRF_OK = 0,

@@ -23,7 +23,7 @@ def test_header_symbols_are_exported_and_typed(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/benerf_b200.h but not exported"
     assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
-    assert lib.bnrf_abi_version() == 1
+    assert lib.bnrf_abi_version() == 2
 
 
 def test_create_fails_loudly_without_gpu(lib):
