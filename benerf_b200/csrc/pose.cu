@@ -63,6 +63,27 @@ __device__ T taylor_series(T x, int first) {
     return total;
 }
 
+// The backward kernel's instance: the same series with x^(2i) built by repeated multiplication instead of powf (two powf per term,
+// 176 per pose and knot element, were most of the kernel's 78 us of dependent latency).  The forward kernel keeps powf: it is
+// compared with the reference's poses at fp32 rounding, the derivatives only at the gradient tolerance.
+template <>
+__device__ Dual taylor_series<Dual>(Dual x, int first) {
+    Dual total(0.0f);
+    double den = 1.0;
+    const float x2 = x.v * x.v;
+    float p = 1.0f, pm1 = 0.0f;            // x^(2i), x^(2i-1)
+#pragma unroll 1
+    for (int i = 0; i <= 10; ++i) {
+        den *= (double)((2 * i + first) * (2 * i + first + 1));
+        const float inv = 1.0f / (float)den;
+        const Dual term(p * inv, (float)(2 * i) * pm1 * x.d * inv);
+        total = (i & 1) ? total - term : total + term;
+        pm1 = p * x.v;
+        p *= x2;
+    }
+    return total;
+}
+
 // exp map, both regimes (spline.py:79-100); the series branch is selected for half-angle < 1e-9
 template <class T>
 __device__ Quat<T> rotvec_to_quat(Vec3<T> r) {
