@@ -153,10 +153,11 @@ class Engine:
                                                _ptr(ts, name="ts"), P, TRAJ[traj], _ptr(out), _stream()), "bnrf_spline_poses")
         return out
 
-    def spline_poses_pair(self, knots, transform, ts, n_plain, traj="spline"):
+    def spline_poses_pair(self, knots, transform, ts, n_plain, traj="spline", out=None):
         """Event poses (first n_plain timestamps, knots only) and RGB poses (the rest, knots + transform) in one launch."""
         P = ts.numel()
-        out = torch.empty(P, 3, 4, device=self.device, dtype=torch.float32)
+        if out is None:
+            out = torch.empty(P, 3, 4, device=self.device, dtype=torch.float32)
         self._check(self.lib.bnrf_spline_poses_pair(self._ctx, _ptr(knots, name="knots"), _ptr(transform, name="transform"), _ptr(ts, name="ts"),
                                                     P, int(n_plain), TRAJ[traj], _ptr(out), _stream()), "bnrf_spline_poses_pair")
         return out

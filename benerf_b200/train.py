@@ -150,15 +150,22 @@ class Trainer:
         weights, grad_tabs = self._tables(eng)
         if getattr(a, "use_barf_c2f", False):
             g._sync_barf(eng, self.global_step, a)
-        if len(weights) == 2:                                            # the parameters changed (bnrf_adam_step_sched wrote them in place)
-            eng.set_weights_pair(weights[0], weights[1])
-        else:
-            eng.set_weights(0, weights[0])
         knots = g.evt_knot_pose_se3.params.weight.data
         transform = g.transform.params.weight.data.reshape(6)
         seed = g.seed()
         n_pe = 2                                                                       # get_pose_evt: window start / end (model/optimize.py:58-82)
-        poses = eng.spline_poses_pair(knots, transform, t["ts"], n_pe, a.traj)         # get_pose_evt + get_pose_rgb, one launch
+        # get_pose_evt + get_pose_rgb, one launch -- on the side stream: a 26 us chain of dependent latency that needs nothing of the
+        # four weight-packing launches (another 80 us of small dependent kernels), so the two run side by side
+        poses = torch.empty(t["ts"].numel(), 3, 4, device=eng.device, dtype=torch.float32)
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            eng.spline_poses_pair(knots, transform, t["ts"], n_pe, a.traj, out=poses)
+        if len(weights) == 2:                                            # the parameters changed (bnrf_adam_step_sched wrote them in place)
+            eng.set_weights_pair(weights[0], weights[1])
+        else:
+            eng.set_weights(0, weights[0])
+        cur.wait_stream(self._side)
         poses_evt, poses_rgb = poses[:n_pe], poses[n_pe:]
         fine = len(self.nets) > 1
         # the event pose pair and the N blur poses (model/nerf.py:217,227) as two segments of ONE ray batch: every stage of the
