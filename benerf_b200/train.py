@@ -1,18 +1,19 @@
 """One optimisation step of the reference's loop (train.py:153-394) on the CUDA engine, data-parallel over pixels.
 
 train.py itself stays the caller's script; this helper is the step it performs per iteration, used by
-bench.py and the tests: poses -> two Graph.render calls -> image formation + the four loss terms -> backward ->
+bench.py and the tests: poses -> the two Graph.render calls of an iteration -> image formation + the four loss terms -> backward ->
 the gradient all-reduce (one exchange of the flat buffer, issued in two parts so that the fine network's half overlaps the coarse
 network's backward pass) -> the reference's Adam steps and exponential learning-rate decay (Q17).
 
 Two executions of the same arithmetic:
-  * the DIRECT step (default, fused_optimizer=True): every stage is an explicit call into libbenerf_b200.so -- spline poses,
-    bnrf_render_forward_train x2, bnrf_training_loss (loss + the gradients w.r.t. the renders), bnrf_render_backward x2,
-    bnrf_spline_poses_backward x2, all-reduce, bnrf_adam_step_sched -- with no autograd graph in between.  Everything that
-    changes from iteration to iteration (global_step -> Adam bias corrections, the three decayed learning rates, the Philox
-    stream offset) lives in DEVICE memory, so after two eager iterations the step is captured in a CUDA graph and replayed:
-    the host enqueues one graph launch instead of ~80 kernel launches (the strong-scaled 8-GPU step was bounded by the
-    2.6 ms the host needed for those).
+  * the DIRECT step (default, fused_optimizer=True): every stage is an explicit call into libbenerf_b200.so -- bnrf_set_weights_pair,
+    bnrf_spline_poses_pair (on a second stream, beside the packing), bnrf_render_forward_multi (event pose pair + blur poses as one
+    ray batch), bnrf_training_loss (loss + the gradients w.r.t. the renders), bnrf_render_backward_multi,
+    bnrf_spline_poses_pair_backward, all-reduce, bnrf_adam_step_sched -- with no autograd graph in between: 28 kernels.
+    Everything that changes from iteration to iteration (global_step -> Adam bias corrections, the three decayed learning rates,
+    the Philox stream offset) lives in DEVICE memory, so after two eager iterations the step is captured in a CUDA graph and
+    replayed: the host enqueues one graph launch (round 1's strong-scaled 8-GPU step was bounded by the 2.6 ms the host needed
+    for ~80 launches).
   * the AUTOGRAD step (fused_optimizer=False, or a tone-mapper being optimised): Graph.render / image_formation.training_loss
     under torch autograd and the reference's own torch.optim.Adam objects; the reference-shaped cross-check of the former.
 """
