@@ -1,20 +1,20 @@
 // Backward pass of Graph.render (the part of train.py:340 loss.backward() that runs through
 // model/nerf.py:236-343): d(rgb_map, rgb0) -> d(NeRF parameters of both networks), d(poses).
 //
-// The forward pass in training mode (bnrf_render_forward_train) keeps, per network, the encoded
-// points and the nine hidden activations of every sample as bf16 hi/lo tile matrices (written by
-// the tensor-core kernel's epilogue, mlp_tc2.cu; format in bwd_tiles.cuh) plus raw / z / sigma.
-// The backward pass is layer-by-layer:
+// The forward pass in training mode (bnrf_render_forward_train / _multi) keeps, per network, the encoded
+// points and the hidden activations of every sample as bf16 hi/lo tile matrices (written by
+// the tensor-core kernel's epilogue, mlp_tc3.cu; format in bwd_tiles.cuh) plus raw / z / sigma.
+// Per network, six launches:
 //   composite_backward   raw2output (model/nerf.py:118-148): sigmoid, relu(sigma+noise), alpha,
 //                        exclusive cumprod, sum(w*rgb) -- one warp per ray, suffix scan
-//   heads / dgrad / wgrad the 12 linears of NeRF.forward (model/nerf.py:93-112): the 256-wide ones
-//                        through the tile kernels of bwd_tiles.cu (gradients stay bf16 hi/lo tile
-//                        matrices between layers; activation gradients of all ten in ONE launch,
-//                        dgrad_chain.cu), the narrow heads (rgb_linear C x 128, the 128 x 27 direction
-//                        block) through small reduction kernels here
-//   pe_ray_backward      sin/cos encoding (model/embedder.py:9-34) and pts = o + d*z
-//   viewdir_backward     direction encoding + the per-ray view bias
-//   rays_backward        ndc_rays + get_specific_rays + viewdirs (run_nerf_helpers.py:35-71) -> d poses
+//   heads_fused          rgb_linear and the view layer's ReLU: dZ9 tiles, d view bias, sum dZ9, dW / dB of rgb_linear
+//   dgrad chain          d activations of the whole network in ONE launch (dgrad_chain2.cu), dZ_l tile matrices out
+//   wgrad (pair, 64-wide) d weights / d biases of the wide linears (wgrad_pair.cu) and of the two encoded-point blocks
+//                        (bwd_tiles.cu), operands straight from the tile matrices
+//   net_tail             by block range: sin/cos encoding (model/embedder.py:9-34) and pts = o + d*z summed over a ray's
+//                        samples; direction encoding + per-ray view bias; direction block of views_linears.0;
+//                        feature_linear / views_linears.0 from the merged contraction
+// and once: rays_backward  ndc_rays + get_specific_rays + viewdirs (run_nerf_helpers.py:35-71) -> d poses, all segments.
 // z_vals carry no gradient (stratified depths have no parameters; z_samples are detached,
 // model/nerf.py:324), exactly as in the reference.  d poses -> d knots is pose.cu (dual numbers).
 #include "common.cuh"
