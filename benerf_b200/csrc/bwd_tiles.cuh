@@ -7,7 +7,7 @@
 //                                                                        rows of 128 B, SWIZZLE_128B (16-byte chunk ^= row & 7)
 //
 // value = hi + lo, both bf16 (keeps the fp32 exponent range, so gradients need no scaling; kind::f16 MMAs want one format
-// for both operands).  Activations are written by the forward kernel's epilogue (mlp_tc2.cu) next to its own fp16 A
+// for both operands).  Activations are written by the forward kernel's epilogue (mlp_tc3.cu; mlp_tc2.cu in its mode) next to its own fp16 A
 // operand, gradients by the dgrad epilogues.  The
 // same block serves as a K-major operand (contraction over its 64 columns: dgrad) and as an MN-major operand
 // (contraction over its rows: wgrad), so no kernel of the backward pass converts or transposes anything: operands move

@@ -52,7 +52,7 @@ struct NetParams {
     bool ready;
 };
 
-// Activations the training-mode forward pass keeps for one network (written by mlp_tc2.cu, read by backward.cu).
+// Activations the training-mode forward pass keeps for one network (written by mlp_tc3.cu / mlp_tc2.cu, read by backward.cu).
 struct ActPtrs {
     float* pe_f32;             // [rows, 64] encoded points, fp32 (encoding backward)
     float* h9_f32;             // [rows, 128] view-layer activations, fp32 (rgb head)

@@ -12,7 +12,7 @@
 // K=16 slice) in shared memory in the SWIZZLE_128B K-major layout and rewritten in place by the epilogue warps, fp32
 // accumulators ping-ponging between two 256-column TMEM buffers, transposed weights streaming through a 6-stage ring of
 // [N x 32] SWIZZLE_64B tiles filled by cp.async.bulk from an L2-resident image, layer hand-off per 32-column K-half.
-// Differences: the first A operand (dZ9, written by heads_backward_kernel as a tile matrix) arrives by cp.async.bulk; the
+// Differences: the first A operand (dZ9, written by heads_fused_kernel as a tile matrix) arrives by cp.async.bulk; the
 // epilogue applies the ReLU mask from 1 bit per activation emitted by the training-mode forward pass (32 B per row and
 // layer instead of re-reading activations); and every dZ_l, which in shared memory already IS a tile of its tile matrix,
 // is copied to global memory by the bulk-copy engine (one thread, cp.async.bulk.global.shared) for the weight-gradient
