@@ -97,3 +97,26 @@ def test_round2_reference_arm_line():
     assert d["impl"] == "reference" and d["metric"] == "rays_per_sec" and d["unit"] == "rays/s"
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_runs_here_and_reports_our_config():
+    """`bench.py --impl reference` is CPU-only: run it for real on a tiny sample.  It must print ONE JSON line with the contract keys of
+    the reference arm, the same `config` dict our arm prints (the workload both numbers are about) and, with the reference staged
+    by __graft_entry__.build(), time the unmodified reference (kind "reference"); without it, the oracle port (kind "port")."""
+    import subprocess
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--cpu-pixels", "8"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "rays_per_sec" and d["unit"] == "rays/s" and d["higher_is_better"] is True
+    assert d["config"] == bench.workload_config(65536, 1)
+    assert d["sample_rays_per_step"] == 8 * (bench.N_POSES + 2)
+    b = d["cpu_baseline"]
+    staged = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "model"))
+    assert b["kind"] == ("reference" if staged else "port") and b["value"] == d["value"] > 0 and b["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
