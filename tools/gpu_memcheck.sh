@@ -14,5 +14,5 @@ run() {
 run tests/test_gpu_backward.py -k "training_iteration_gradients_match_reference or render_backward_matches_oracle"
 run tests/test_gpu_backward.py -k "trainer or fused_training_loss"
 run tests/test_gpu_ops.py -k "mlp or spline"
-run tests/test_gpu_render.py -k "tone_mappers or binned or identical_samples or graph_forward"
+run tests/test_gpu_render.py -k "tone_mappers or binned or identical_samples or free_running or fuses_compositing or graph_forward"
 grep -n "^###\|^exit\|ERROR SUMMARY\|passed\|failed" $LOG
